@@ -1,0 +1,40 @@
+"""GPU parity of the tcgen05 implicit-GEMM conv engine (forward, data gradient, weight gradient) against a plain torch
+fp32 reference of the same op on the same bf16-rounded operands.  Tolerances: the product accumulates in fp32 from bf16
+operands exactly like the reference's inputs, so only summation order and the final bf16 rounding of stored activations
+differ: |err| <= 2^-8 * |ref|_max + small absolute slack."""
+import pytest
+import torch
+
+from convref import run_conv_case
+from unsupervised_detection_b200._lib import ACT_NONE, ACT_ELU, ACT_LEAKY
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # N, H, W, cins, cout, k, stride, dil, act, bn, post_add
+    dict(N=2, H=16, W=24, cins=[64], cout=64, k=3),
+    dict(N=2, H=16, W=24, cins=[128], cout=128, k=3, act=ACT_ELU, bn=True),
+    dict(N=1, H=32, W=40, cins=[5], cout=32, k=5, act=ACT_ELU, bn=True),
+    dict(N=2, H=16, W=28, cins=[32], cout=64, k=3, stride=2, act=ACT_ELU, bn=True),
+    dict(N=1, H=24, W=24, cins=[128], cout=128, k=3, dil=4, act=ACT_ELU, bn=True, post_add=True),
+    dict(N=1, H=17, W=23, cins=[3], cout=16, k=7, stride=2, act=ACT_LEAKY),
+    dict(N=3, H=8, W=14, cins=[128, 128, 128, 2], cout=128, k=4, act=ACT_LEAKY, n_mod_last=0),
+    dict(N=3, H=8, W=14, cins=[128, 128, 2, 128], cout=2, k=3),
+    dict(N=6, H=9, W=7, cins=[64, 64, 64], cout=64, k=4, act=ACT_LEAKY, n_mod_last=2),
+    dict(N=1, H=12, W=20, cins=[16], cout=32, k=5, stride=2, act=ACT_LEAKY),
+    dict(N=2, H=6, W=10, cins=[196], cout=196, k=3, act=ACT_LEAKY, alpha=0.1, backward=False),
+    dict(N=1, H=20, W=20, cins=[16], cout=2, k=3),
+]
+
+
+@pytest.mark.parametrize('case', CASES, ids=lambda c: 'k%d_s%d_d%d_c%s_o%d' % (c['k'], c.get('stride', 1), c.get('dil', 1), '+'.join(map(str, c['cins'])), c['cout']))
+def test_conv_engine(case):
+    r = run_conv_case(**case)
+    tol = lambda ref: 2 ** -7 * ref + 1e-3
+    assert r['fwd_err'] <= tol(r['fwd_ref']), r
+    if 'dx_err' in r:
+        assert r['dx_err'] <= tol(r['dx_ref']), r
+        assert r['dw_err'] <= 2 ** -9 * r['dw_ref'] + 1e-3, r
+        assert r['db_err'] <= 2 ** -9 * r['db_ref'] + 1e-3, r
+    if 'dgamma_err' in r:
+        assert r['dgamma_err'] <= 2 ** -6 * r['dgamma_ref'] + 1e-2, r

@@ -1,0 +1,510 @@
+// tcgen05 implicit-GEMM convolution engine for sm_100a (forward / data-gradient / transposed conv / weight-gradient).
+//
+// Replaces the TF1 op classes K1/K3/K5/K6 of SURVEY.md section 2.2 (tf.layers.conv2d, tf.nn.conv2d,
+// tf.layers.conv2d_transpose and their tf.gradients twins; reference call sites
+// models/utils/convolution_utils.py:46,81 and models/PWCNet/model_pwcnet.py:161-165,286,484-504,562-574).
+//
+// Design: one CTA = one 128-row tile of the GEMM (rows = output pixels).  Four producer warps gather the
+// im2col A tile (128 rows x 64 bf16 of K) and the packed-weight B tile straight into the canonical SWIZZLE_128B K-major
+// shared-memory layout with 16-byte cp.async (zero-fill = SAME padding); one thread of a fifth warp issues
+// tcgen05.mma.kind::f16 (M=128, N=BN, K=16) with the fp32 accumulator in TMEM; smem stages are recycled with
+// tcgen05.commit -> mbarrier.  The producer warps then become the epilogue: tcgen05.ld the accumulator, apply
+// bias / residuals / activation and store bf16 and/or fp32 NHWC.
+#include "ptx.cuh"
+#include "../../include/cis_b200.h"
+#include "common.cuh"
+
+namespace cis {
+
+static constexpr int kBM = 128;       // GEMM rows per CTA
+static constexpr int kBK = 64;        // bf16 K elements per stage (128-byte swizzled rows)
+static constexpr int kAStage = kBM * 128;
+static constexpr int kProducerThreads = 128;
+static constexpr int kThreads = 160;  // 4 producer/epilogue warps + 1 MMA warp
+static constexpr int kLag = 2;        // cp.async groups kept in flight per producer thread
+
+struct SrcS {
+  const __nv_bfloat16* ptr;
+  int pitch, c_off, chunks, n_mod;
+};
+
+template <int BN>
+struct FwdCfg {
+  static constexpr int kStages = (BN == 128) ? 3 : 4;
+  static constexpr int kBStage = BN * 128;
+  static constexpr int kSmem = kStages * (kAStage + kBStage) + 1024;
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_constant__ CisConv p) {
+  using Cfg = FwdCfg<BN>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[2 * S + 1];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_dh[CIS_MAX_TAPS], s_dw[CIS_MAX_TAPS];
+  __shared__ SrcS s_src[CIS_MAX_SRC];
+
+  const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = tile_base;
+  const uint32_t b_base = tile_base + S * kAStage;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[S]);
+  const uint32_t bar_accum = smem_u32(&bars[2 * S]);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int M = p.N * p.OH * p.OW;
+  const int m_chunks = [&] {
+    int s = 0;
+    for (int i = 0; i < p.nsrc; ++i) s += p.src[i].chunks;
+    return s;
+  }();
+  const int k_chunks = p.ntaps * m_chunks;
+  const int nkb = p.K_pad / kBK;
+  const int ny = blockIdx.y;
+
+  if (tid < p.ntaps) {
+    s_dh[tid] = p.dh[tid];
+    s_dw[tid] = p.dw[tid];
+  }
+  if (tid < p.nsrc) {
+    s_src[tid].ptr = reinterpret_cast<const __nv_bfloat16*>(p.src[tid].ptr);
+    s_src[tid].pitch = p.src[tid].pitch;
+    s_src[tid].c_off = p.src[tid].c_off;
+    s_src[tid].chunks = p.src[tid].chunks;
+    s_src[tid].n_mod = p.src[tid].n_mod;
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(bar_full + 8 * s, kProducerThreads);
+        mbar_init(bar_empty + 8 * s, 1);
+      }
+      mbar_init(bar_accum, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<Cfg::kTmemCols>(smem_u32(&tmem_slot));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers
+    const int j = tid & 7;          // 16-byte chunk within the 128-byte K row
+    const int rl = tid >> 3;        // 0..15
+    const uint32_t sw_off = (uint32_t)((j ^ (rl & 7)) << 4);
+    int hb[8], wb[8], nb[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int g = blockIdx.x * kBM + rl + 16 * i;
+      if (g < M) {
+        const int ow = g % p.OW;
+        const int t = g / p.OW;
+        const int oh = t % p.OH;
+        nb[i] = t / p.OH;
+        hb[i] = oh * p.sh;
+        wb[i] = ow * p.sw;
+      } else {
+        nb[i] = 0;
+        hb[i] = -(1 << 20);
+        wb[i] = 0;
+      }
+    }
+    const __nv_bfloat16* wrow = reinterpret_cast<const __nv_bfloat16*>(p.wpack) + (size_t)(ny * BN + rl) * p.K_pad + j * 8;
+
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % S;
+      const uint32_t ph = (uint32_t)((kb / S) & 1);
+      mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+      // ---- A: decode this thread's K chunk -> (tap, source, channel chunk)
+      const int q = kb * 8 + j;
+      const bool kvalid = q < k_chunks;
+      int t = 0, c = 0;
+      if (kvalid) {
+        t = q / m_chunks;
+        c = q - t * m_chunks;
+      }
+      int si = 0;
+      while (si < p.nsrc - 1 && c >= s_src[si].chunks) {
+        c -= s_src[si].chunks;
+        ++si;
+      }
+      const __nv_bfloat16* sp = s_src[si].ptr;
+      const int pitch = s_src[si].pitch;
+      const int coff = s_src[si].c_off + c * 8;
+      const int nmod = s_src[si].n_mod;
+      const int dh = s_dh[t], dw = s_dw[t];
+      const uint32_t a_dst = a_base + s * kAStage + rl * 128 + sw_off;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int h = hb[i] + dh, w = wb[i] + dw;
+        const bool ok = kvalid && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
+        const int n = nmod ? (nb[i] % nmod) : nb[i];
+        const size_t off = ok ? ((size_t)((n * p.H + h) * p.W + w) * pitch + coff) : 0;
+        cp_async16(a_dst + i * 16 * 128, sp + off, ok ? 16u : 0u);
+      }
+      // ---- B: packed weights, rows rl + 16 i
+      const uint32_t b_dst = b_base + s * Cfg::kBStage + rl * 128 + sw_off;
+#pragma unroll
+      for (int i = 0; i < BN / 16; ++i) cp_async16(b_dst + i * 16 * 128, wrow + (size_t)i * 16 * p.K_pad + kb * kBK, 16u);
+      cp_async_commit();
+      if (kb >= kLag) {
+        cp_async_wait<kLag>();
+        fence_proxy_async();
+        mbar_arrive(bar_full + 8 * ((kb - kLag) % S));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int kb = (nkb > kLag ? nkb - kLag : 0); kb < nkb; ++kb) mbar_arrive(bar_full + 8 * (kb % S));
+
+    // ------------------------------------------------------------------ epilogue
+    mbar_wait(bar_accum, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    const int g = blockIdx.x * kBM + row;
+    const bool valid = g < M;
+    size_t dpix = 0;
+    if (valid) {
+      const int ow = g % p.OW;
+      const int t = g / p.OW;
+      const int oh = t % p.OH;
+      const int n = t / p.OH;
+      dpix = (size_t)(n * p.DH + oh * p.osh + p.oa) * p.DW + ow * p.osw + p.ob;
+    }
+    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const int cbase = ny * BN;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      tmem_ld16(t_row + c0, v);
+      if (!valid) continue;
+      const int cg = cbase + c0;  // global output channel of v[0]
+      if (p.bias) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] += __ldg(p.bias + cg + e);
+      }
+      if (p.add_pre && cg < p.out_ch) {
+        const uint4* a = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.add_pre) +
+                                                        dpix * p.add_pre_pitch + p.add_pre_coff + cg);
+        const int nv = (p.out_ch - cg >= 16) ? 2 : 1;
+        for (int h2 = 0; h2 < nv; ++h2) {
+          const uint4 u = __ldg(a + h2);
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[h2 * 8 + 2 * e] += bf16lo(w4[e]);
+            v[h2 * 8 + 2 * e + 1] += bf16hi(w4[e]);
+          }
+        }
+      }
+      if (p.addf_pre) {
+        for (int e = 0; e < 16 && cg + e < p.outf_ch; ++e) v[e] += __ldg(p.addf_pre + dpix * p.addf_pitch + p.addf_coff + cg + e);
+      }
+      if (p.act == CIS_ACT_ELU) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.f ? v[e] : expm1f(v[e]);
+      } else if (p.act == CIS_ACT_LEAKY) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * p.alpha;
+      }
+      if (p.add_post && cg < p.out_ch) {
+        const uint4* a = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.add_post) +
+                                                        dpix * p.add_post_pitch + p.add_post_coff + cg);
+        const int nv = (p.out_ch - cg >= 16) ? 2 : 1;
+        for (int h2 = 0; h2 < nv; ++h2) {
+          const uint4 u = __ldg(a + h2);
+          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            v[h2 * 8 + 2 * e] += bf16lo(w4[e]);
+            v[h2 * 8 + 2 * e + 1] += bf16hi(w4[e]);
+          }
+        }
+      }
+      if (p.mode == 1) {
+        if (cg == 0) p.outf[dpix] = 1.f / (1.f + __expf(-(v[0] - v[1]) * 0.1f));
+        continue;
+      }
+      if (p.out && cg < p.out_ch) {
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + dpix * p.out_pitch + p.out_coff + cg;
+        if (((p.out_ch | p.out_coff | p.out_pitch) & 7) == 0) {
+          uint4 u0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+          *reinterpret_cast<uint4*>(o) = u0;
+          if (p.out_ch - cg >= 16) {
+            uint4 u1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+            *reinterpret_cast<uint4*>(o + 8) = u1;
+          }
+        } else {
+          for (int e = 0; e < 16 && cg + e < p.out_ch; ++e) o[e] = __float2bfloat16(v[e]);
+        }
+      }
+      if (p.outf && cg < p.outf_ch) {
+        float* o = p.outf + dpix * p.outf_pitch + p.outf_coff + cg;
+        for (int e = 0; e < 16 && cg + e < p.outf_ch; ++e) o[e] = v[e];
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (warp 4)
+    constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % S;
+      const uint32_t ph = (uint32_t)((kb / S) & 1);
+      mbar_wait(bar_full + 8 * s, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = a_base + s * kAStage;
+        const uint32_t b_addr = b_base + s * Cfg::kBStage;
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
+          const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
+          umma_bf16(tmem, da, db, idesc, (uint32_t)((kb | k) != 0));
+        }
+        umma_commit(bar_empty + 8 * s);
+        if (kb == nkb - 1) umma_commit(bar_accum);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<Cfg::kTmemCols>(tmem);
+}
+
+// ======================================================================================================= wgrad
+// D[co][kcol] = sum_pix g[pix][co] * A[pix][kcol]; both operands are "MN-major" (the reduction dim = pixels is the slow
+// dimension of NHWC), staged as two [64 pixels][64 channels] SWIZZLE_128B sub-tiles each.
+static constexpr int kWStages = 3;
+static constexpr int kWTile = 64 * 128;            // one [64 pix][64 ch] bf16 sub-tile
+static constexpr int kWStage = 4 * kWTile;         // A (2 sub-tiles) + B (2 sub-tiles)
+static constexpr int kWSmem = kWStages * kWStage + 1024;
+
+__global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_constant__ CisWgrad p) {
+  constexpr int S = kWStages;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[2 * S + 1];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_dh[CIS_MAX_TAPS], s_dw[CIS_MAX_TAPS];
+  const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[S]);
+  const uint32_t bar_accum = smem_u32(&bars[2 * S]);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < p.ntaps) {
+    s_dh[tid] = p.dh[tid];
+    s_dw[tid] = p.dw[tid];
+  }
+  const int M = p.N * p.OH * p.OW;  // reduction length (pixels)
+  int m_chunks = 0;
+  for (int i = 0; i < p.nsrc; ++i) m_chunks += p.src[i].chunks;
+  const int k_chunks = p.ntaps * m_chunks;
+  const int nkb_total = (M + 63) / 64;
+  const int per = (nkb_total + p.splits - 1) / p.splits;
+  const int kb0 = blockIdx.y * per;
+  const int kb1 = min(kb0 + per, nkb_total);
+  const int nkb = kb1 - kb0;
+  if (nkb <= 0) return;  // uniform per CTA: safe before any barrier / TMEM allocation
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(bar_full + 8 * s, kProducerThreads);
+        mbar_init(bar_empty + 8 * s, 1);
+      }
+      mbar_init(bar_accum, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc<128>(smem_u32(&tmem_slot));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 4) {
+    const int j = tid & 7, rl = tid >> 3;
+    const uint32_t sw_off = (uint32_t)((j ^ (rl & 7)) << 4);
+    // fixed per-thread decode of the two B (activation) chunks and two A (gradient) chunks
+    const __nv_bfloat16* bptr[2];
+    int bpitch[2], bcoff[2], bnmod[2], bdh[2], bdw[2];
+    bool bvalid[2], avalid[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int q = blockIdx.x * 16 + u * 8 + j;
+      bvalid[u] = q < k_chunks;
+      int t = 0, c = 0;
+      if (bvalid[u]) {
+        t = q / m_chunks;
+        c = q - t * m_chunks;
+      }
+      int si = 0;
+      while (si < p.nsrc - 1 && c >= p.src[si].chunks) {
+        c -= p.src[si].chunks;
+        ++si;
+      }
+      // static unrolled select keeps p.src[] accesses at constant indices
+      CisSrc sd = p.src[0];
+      if (si == 1) sd = p.src[1];
+      if (si == 2) sd = p.src[2];
+      if (si == 3) sd = p.src[3];
+      bptr[u] = reinterpret_cast<const __nv_bfloat16*>(sd.ptr);
+      bpitch[u] = sd.pitch;
+      bcoff[u] = sd.c_off + c * 8;
+      bnmod[u] = sd.n_mod;
+      bdh[u] = s_dh[t];
+      bdw[u] = s_dw[t];
+      avalid[u] = (u * 8 + j) < p.g_chunks;
+    }
+    const __nv_bfloat16* gp = reinterpret_cast<const __nv_bfloat16*>(p.g);
+
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (uint32_t)((it / S) & 1);
+      mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+      const uint32_t st = tile_base + s * kWStage;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = rl + 16 * i;
+        const int g = (kb0 + it) * 64 + r;
+        const bool rv = g < M;
+        int n = 0, h0 = 0, w0 = 0;
+        if (rv) {
+          const int ow = g % p.OW;
+          const int t = g / p.OW;
+          h0 = (t % p.OH) * p.sh;
+          n = t / p.OH;
+          w0 = ow * p.sw;
+        }
+        const uint32_t dst = st + r * 128 + sw_off;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const bool ok = rv && avalid[u];
+          const size_t off = ok ? ((size_t)g * p.g_pitch + p.g_coff + (u * 8 + j) * 8) : 0;
+          cp_async16(dst + u * kWTile, gp + off, ok ? 16u : 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int h = h0 + bdh[u], w = w0 + bdw[u];
+          const bool ok = rv && bvalid[u] && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
+          const int ne = bnmod[u] ? (n % bnmod[u]) : n;
+          const size_t off = ok ? ((size_t)((ne * p.H + h) * p.W + w) * bpitch[u] + bcoff[u]) : 0;
+          cp_async16(dst + (2 + u) * kWTile, bptr[u] + off, ok ? 16u : 0u);
+        }
+      }
+      cp_async_commit();
+      if (it >= kLag) {
+        cp_async_wait<kLag>();
+        fence_proxy_async();
+        mbar_arrive(bar_full + 8 * ((it - kLag) % S));
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int it = (nkb > kLag ? nkb - kLag : 0); it < nkb; ++it) mbar_arrive(bar_full + 8 * (it % S));
+
+    // epilogue: row = output channel co, columns = packed K columns of this n-tile
+    mbar_wait(bar_accum, 0);
+    tc_fence_after();
+    const int co = warp * 32 + lane;
+    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const int kcol0 = blockIdx.x * 128;
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 16) {
+      float v[16];
+      tmem_ld16(t_row + c0, v);
+      if (co < p.Cout) {
+        float* o = p.dwp + (size_t)co * p.K_pad + kcol0 + c0;
+        for (int e = 0; e < 16; ++e)
+          if (kcol0 + c0 + e < p.K_pad) atomicAdd(o + e, v[e]);
+      }
+    }
+  } else {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 128, 1, 1);
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % S;
+      const uint32_t ph = (uint32_t)((it / S) & 1);
+      mbar_wait(bar_full + 8 * s, ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t st = tile_base + s * kWStage;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // 16 pixels (K) per MMA = 16 rows x 128 B; MN atoms (64 channels) are kWTile apart (LBO), 8-row K groups 1024 B (SBO)
+          const uint64_t da = make_smem_desc(st + k * 2048, kWTile, 1024);
+          const uint64_t db = make_smem_desc(st + 2 * kWTile + k * 2048, kWTile, 1024);
+          umma_bf16(tmem, da, db, idesc, (uint32_t)((it | k) != 0));
+        }
+        umma_commit(bar_empty + 8 * s);
+        if (it == nkb - 1) umma_commit(bar_accum);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc<128>(tmem);
+}
+
+}  // namespace cis
+
+using namespace cis;
+
+template <int BN>
+static int launch_fwd(const CisConv* d, cudaStream_t st) {
+  using Cfg = FwdCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmem);
+    if (e != cudaSuccess) return cis_set_cuda_error(e, "cudaFuncSetAttribute(conv_igemm)");
+    attr_set = true;
+  }
+  const int M = d->N * d->OH * d->OW;
+  dim3 grid((M + kBM - 1) / kBM, d->n_tiles);
+  conv_igemm_kernel<BN><<<grid, kThreads, Cfg::kSmem, st>>>(*d);
+  return cis_check_launch("conv_igemm");
+}
+
+extern "C" int cis_conv_igemm(const CisConv* d, cis_stream_t stream) {
+  if (!d || d->ntaps < 1 || d->ntaps > CIS_MAX_TAPS || d->nsrc < 1 || d->nsrc > CIS_MAX_SRC || d->K_pad % 64 != 0 || d->K_pad <= 0 ||
+      d->n_tiles < 1 || !d->wpack)
+    return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm: bad descriptor");
+  int chunks = 0;
+  for (int i = 0; i < d->nsrc; ++i) {
+    if ((d->src[i].pitch | d->src[i].c_off) & 7) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm: source pitch/c_off must be multiples of 8");
+    chunks += d->src[i].chunks;
+  }
+  if (d->ntaps * chunks * 8 > d->K_pad) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm: K_pad smaller than taps*channels");
+  if (d->mode == 1 && !d->outf) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm: mode 1 needs outf");
+  if ((d->add_pre || d->add_post) && (((d->add_pre_pitch | d->add_pre_coff | d->add_post_pitch | d->add_post_coff | d->out_ch) & 7) != 0))
+    return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm: residual slices must be 8-channel aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d->BN) {
+    case 16: return launch_fwd<16>(d, st);
+    case 32: return launch_fwd<32>(d, st);
+    case 64: return launch_fwd<64>(d, st);
+    case 128: return launch_fwd<128>(d, st);
+    default: return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_conv_igemm: BN must be 16/32/64/128");
+  }
+}
+
+extern "C" int cis_conv_wgrad(const CisWgrad* d, cis_stream_t stream) {
+  if (!d || d->ntaps < 1 || d->ntaps > CIS_MAX_TAPS || d->nsrc < 1 || d->nsrc > CIS_MAX_SRC || d->K_pad % 64 != 0 || d->Cout < 1 ||
+      d->Cout > 128 || d->splits < 1 || !d->g || !d->dwp)
+    return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_wgrad: bad descriptor");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem);
+    if (e != cudaSuccess) return cis_set_cuda_error(e, "cudaFuncSetAttribute(conv_wgrad)");
+    attr_set = true;
+  }
+  dim3 grid((d->K_pad + 127) / 128, d->splits);
+  conv_wgrad_kernel<<<grid, kThreads, kWSmem, (cudaStream_t)stream>>>(*d);
+  return cis_check_launch("conv_wgrad");
+}

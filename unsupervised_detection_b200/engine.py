@@ -1,0 +1,566 @@
+"""Static launch-list executor for the hot path: bf16 NHWC activations in HBM, every op a call into libcis_b200.so.
+
+Networks are described once (shapes are static), which produces three launch lists -- forward, backward for the recover
+step and backward for the generator step -- that are then replayed (optionally inside a CUDA graph) every iteration.
+PyTorch only owns device memory and streams here; there is no autograd and no torch compute on the hot path.
+"""
+import ctypes as C
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CisConv, CisWgrad, CisSrc, ACT_NONE, ACT_ELU, ACT_LEAKY
+
+
+def ru(x, m):
+    return (x + m - 1) // m * m
+
+
+def same_pad(n_in, k, s=1, d=1):
+    """TF 'SAME' padding split."""
+    out = -(-n_in // s)
+    total = max((out - 1) * s + (k - 1) * d + 1 - n_in, 0)
+    return total // 2, total - total // 2
+
+
+class Plan(object):
+    """An ordered list of C-ABI launches (and a few torch memsets) replayable on any stream."""
+
+    def __init__(self, name=''):
+        self.name = name
+        self.ops = []
+        self.keep = []  # ctypes structs / tensors that must outlive the plan
+
+    def add(self, fname, *args):
+        fn = getattr(_lib.load(), fname)
+        self.ops.append((fn, args, fname))
+
+    def add_py(self, fn, label='py'):
+        self.ops.append((None, fn, label))
+
+    def zero(self, t):
+        self.add_py(t.zero_, 'zero')
+
+    def run(self, stream=None):
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        for fn, args, name in self.ops:
+            if fn is None:
+                args()
+            else:
+                rc = fn(*args, st)
+                if rc != 0:
+                    _lib.check(rc, name)
+
+    def count(self):
+        return sum(1 for fn, _, _ in self.ops if fn is not None)
+
+    def extend(self, other):
+        self.ops += other.ops
+        self.keep += other.keep
+
+
+class Act(object):
+    """A bf16 NHWC activation: a channel slice [c_off, c_off+C8) of a buffer [N,H,W,pitch]."""
+
+    def __init__(self, N, H, W, C, device, buf=None, c_off=0, chanmap=None, n_mod=0, dep=frozenset(), name=''):
+        if chanmap is not None and not C:
+            C = max(chanmap) + 1
+        self.N, self.H, self.W, self.C = N, H, W, C
+        self.C8 = ru(C, 8) if chanmap is None else len(chanmap)
+        if buf is None:
+            buf = torch.zeros(N, H, W, self.C8, dtype=torch.bfloat16, device=device)
+        self.buf = buf
+        self.pitch = buf.shape[-1]
+        self.c_off = c_off
+        self.chanmap = list(chanmap) if chanmap is not None else list(range(C)) + [-1] * (self.C8 - C)
+        self.n_mod = n_mod
+        self.dep = frozenset(dep)
+        self.name = name
+        self.grad = None
+        self.grad_written = {}   # mode -> bool
+        self.device = device
+        self.gen_rows = None     # batch rows processed by the generator-step backward (2B of 3B)
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr()
+
+    def src(self):
+        return CisSrc(self.ptr, self.pitch, self.c_off, self.C8 // 8, self.n_mod)
+
+    def rows(self, mode):
+        return self.gen_rows if (mode == 'G' and self.gen_rows) else self.N
+
+    def alias(self, n_mod):
+        """Same storage seen as a batch-broadcast source (features shared by the three recover_net calls)."""
+        a = Act(self.N, self.H, self.W, self.C, self.device, buf=self.buf, c_off=self.c_off, chanmap=self.chanmap, n_mod=n_mod,
+                dep=self.dep, name=self.name + '.shared')
+        a._owner = self
+        a.grad_written = self.grad_written
+        return a
+
+    def get_grad(self):
+        if getattr(self, '_owner', None) is not None:
+            return self._owner.get_grad()
+        if self.grad is None:
+            self.grad = Act(self.N, self.H, self.W, self.C, self.device, chanmap=self.chanmap, name=self.name + '.grad')
+        return self.grad
+
+    def float(self):
+        """Debug/test helper: real channels as fp32 [N,H,W,C] (a torch op, not on the hot path)."""
+        idx = [i for i, m in enumerate(self.chanmap) if m >= 0]
+        return self.buf[..., self.c_off:self.c_off + self.C8].float()[..., idx]
+
+
+def _fill_taps(d, taps):
+    d.ntaps = len(taps)
+    for i, (a, b) in enumerate(taps):
+        d.dh[i] = a
+        d.dw[i] = b
+
+
+def _fill_srcs(d, srcs):
+    d.nsrc = len(srcs)
+    for i, s in enumerate(srcs):
+        d.src[i] = s.src()
+
+
+def pick_bn(cout):
+    if cout <= 16:
+        return 16, 1
+    if cout <= 32:
+        return 32, 1
+    if cout <= 64:
+        return 64, 1
+    return 128, -(-cout // 128)
+
+
+class ParamStore(object):
+    """One flat fp32 parameter buffer (+ grad, Adam m/v) per variable scope; names follow the TF variable layout
+    (adversarial_learner.py:211-214 scopes 'MaskNet' / 'FlownetS'; model_pwcnet.py 'pwcnet')."""
+
+    def __init__(self, device):
+        self.device = device
+        self.entries = []   # (name, shape, real_numel, offset, padded_numel)
+        self.index = {}
+        self.size = 0
+        self.flat = None
+
+    def declare(self, name, shape, padded=None):
+        n = int(np.prod(shape))
+        pn = ru(padded or n, 4)
+        self.index[name] = len(self.entries)
+        self.entries.append((name, tuple(shape), n, self.size, pn))
+        self.size += pn
+
+    def finalize(self, trainable):
+        self.flat = torch.zeros(self.size, dtype=torch.float32, device=self.device)
+        if trainable:
+            self.grad = torch.zeros_like(self.flat)
+            self.m = torch.zeros_like(self.flat)
+            self.v = torch.zeros_like(self.flat)
+            seg = [0]
+            for _, _, n, off, _ in self.entries:
+                seg.append(off + n)
+            # segment i = [offset_i, offset_i + n_i): built as explicit (start,end) pairs flattened for the kernel
+            self.seg_pairs = [(off, off + n) for _, _, n, off, _ in self.entries]
+
+    def off(self, name):
+        return self.entries[self.index[name]][3]
+
+    def ptr(self, name, which='flat'):
+        return getattr(self, which).data_ptr() + 4 * self.off(name)
+
+    def view(self, name, which='flat'):
+        _, shape, n, off, _ = self.entries[self.index[name]]
+        return getattr(self, which)[off:off + n].view(shape)
+
+    def load(self, params):
+        for name, shape, n, off, _ in self.entries:
+            if name not in params:
+                raise KeyError('missing parameter ' + name)
+            t = params[name].detach().to(torch.float32).reshape(-1)
+            if t.numel() != n:
+                raise ValueError('shape mismatch for %s: %d vs %d' % (name, t.numel(), n))
+            self.flat[off:off + n].copy_(t)
+
+    def export(self, which='flat'):
+        return {name: getattr(self, which)[off:off + n].view(shape).clone() for name, shape, n, off, _ in self.entries}
+
+    def real_count(self):
+        return sum(e[2] for e in self.entries)
+
+
+class ConvLayer(object):
+    """One conv layer's static data: parameter views, packed bf16 operands (forward and data-gradient orientation),
+    the fp32 packed weight-gradient buffer and the channel maps that tie packed K positions to HWIO indices."""
+
+    def __init__(self, store, name, k, cin, cout, stride=1, dil=1, act=ACT_NONE, alpha=0.2, tag='', bn=False,
+                 wname='kernel', bname='bias', transposed=False):
+        self.store, self.name, self.k, self.cin, self.cout = store, name, k, cin, cout
+        self.stride, self.dil, self.act, self.alpha, self.tag, self.bn = stride, dil, act, alpha, tag, bn
+        self.transposed = transposed
+        self.BN, self.n_tiles = pick_bn(cout)
+        self.npad = self.BN * self.n_tiles
+        self.wkey, self.bkey = '%s/%s' % (name, wname), '%s/%s' % (name, bname)
+        if transposed:
+            store.declare(self.wkey, (k, k, cout, cin))
+        else:
+            store.declare(self.wkey, (k, k, cin, cout))
+        store.declare(self.bkey, (cout,), padded=self.npad)
+        if bn:
+            store.declare('%s/gamma' % name, (cout,))
+            store.declare('%s/beta' % name, (cout,))
+        self.fwd_pack = None
+        self.dgrad_packs = None
+        self.device = store.device
+
+    # ---- packed operands -------------------------------------------------------------------------------------
+    def _kmap(self, taps_idx, chanmap, per_tap_stride, chan_stride):
+        """kmap[k=(ti,pos)] = taps_idx[ti]*per_tap_stride + chanmap[pos]*chan_stride (or -1)."""
+        m = len(chanmap)
+        K = len(taps_idx) * m
+        Kp = ru(K, 64)
+        km = np.full(Kp, -1, dtype=np.int32)
+        cm = np.asarray(chanmap, dtype=np.int64)
+        for ti, t in enumerate(taps_idx):
+            v = np.where(cm >= 0, t * per_tap_stride + cm * chan_stride, -1)
+            km[ti * m:(ti + 1) * m] = v
+        return torch.from_numpy(km).to(self.device), Kp
+
+    def setup_fwd(self, chanmap):
+        """chanmap: packed input position -> original input channel (or -1)."""
+        assert max(chanmap) == self.cin - 1, (self.name, max(chanmap), self.cin)
+        self.in_chanmap = list(chanmap)
+        kk = self.k * self.k
+        if self.transposed:
+            raise RuntimeError('use setup_transposed')
+        kmap, Kp = self._kmap(range(kk), chanmap, self.cin * self.cout, self.cout)
+        self.fwd_kmap, self.K_pad = kmap, Kp
+        self.fwd_pack = torch.zeros(self.npad, Kp, dtype=torch.bfloat16, device=self.device)
+        if self.bn:
+            self.w_eff = torch.zeros(kk * self.cin * self.cout, dtype=torch.float32, device=self.device)
+            self.b_eff = torch.zeros(self.npad, dtype=torch.float32, device=self.device)
+            self.db_eff = torch.zeros(self.npad, dtype=torch.float32, device=self.device)
+
+    def w_src_ptr(self):
+        return self.w_eff.data_ptr() if self.bn else self.store.ptr(self.wkey)
+
+    def bias_ptr(self):
+        return self.b_eff.data_ptr() if self.bn else self.store.ptr(self.bkey)
+
+    def plan_pack(self, plan, dgrad=False):
+        """(Re)build the packed bf16 operands from the fp32 master weights."""
+        s = self.store
+        if self.bn:
+            plan.add('cis_bn_fold', s.ptr(self.wkey), s.ptr(self.bkey), s.ptr(self.name + '/gamma'), s.ptr(self.name + '/beta'),
+                     self.k * self.k * self.cin * self.cout, self.cout, self.w_eff.data_ptr(), self.b_eff.data_ptr())
+        if self.fwd_pack is not None:
+            if self.transposed:
+                for pk in self.tr_packs:
+                    plan.add('cis_pack_weights', self.w_src_ptr(), pk['kmap'].data_ptr(), pk['K_pad'], self.npad, self.cout, self.cin,
+                             None, pk['w'].data_ptr())
+            else:
+                plan.add('cis_pack_weights', self.w_src_ptr(), self.fwd_kmap.data_ptr(), self.K_pad, self.npad, self.cout, 1,
+                         None, self.fwd_pack.data_ptr())
+        if dgrad and self.dgrad_packs:
+            for pk in self.dgrad_packs:
+                plan.add('cis_pack_weights', self.w_src_ptr(), pk['kmap'].data_ptr(), pk['K_pad'], pk['rows'], len(self.in_chanmap),
+                         self.cout, pk['nmap'].data_ptr(), pk['w'].data_ptr())
+
+    def plan_zero_grads(self, bp):
+        if hasattr(self, 'dwp'):
+            bp.zero(self.dwp)
+            if self.bn:
+                bp.zero(self.db_eff)
+
+    def plan_finalize(self, bp):
+        """packed fp32 weight gradient -> HWIO slot of the flat gradient buffer (+ BN chain rule for the generator)."""
+        if not hasattr(self, 'dwp'):
+            return
+        s = self.store
+        bp.add('cis_unpack_wgrad', self.dwp.data_ptr(), self.fwd_kmap.data_ptr(), self.K_pad, self.cout, s.ptr(self.wkey, 'grad'))
+        if self.bn:
+            bp.add('cis_bn_chain', s.ptr(self.wkey), s.ptr(self.bkey), s.ptr(self.name + '/gamma'), s.ptr(self.wkey, 'grad'),
+                   self.db_eff.data_ptr(), self.k * self.k * self.cin * self.cout, self.cout, s.ptr(self.bkey, 'grad'),
+                   s.ptr(self.name + '/gamma', 'grad'), s.ptr(self.name + '/beta', 'grad'))
+
+    # ---- tap tables ------------------------------------------------------------------------------------------
+    def fwd_taps(self, H, W):
+        pt, _ = same_pad(H, self.k, self.stride, self.dil)
+        pl, _ = same_pad(W, self.k, self.stride, self.dil)
+        return [(r * self.dil - pt, c * self.dil - pl) for r in range(self.k) for c in range(self.k)], pt, pl
+
+    def setup_dgrad(self, H, W):
+        """Packed weights for the data gradient on an input of size HxW: one launch for stride 1, four output-parity
+        launches for stride 2 (each with the tap subset that lands on that parity)."""
+        if self.dgrad_packs is not None:
+            return
+        _, pt, pl = self.fwd_taps(H, W)
+        k, s, d = self.k, self.stride, self.dil
+        g_chan = list(range(self.cout)) + [-1] * (ru(self.cout, 8) - self.cout)
+        cin8 = len(self.in_chanmap)
+        bn_, nt = pick_bn(cin8)
+        rows = bn_ * nt
+        nmap = torch.tensor(list(self.in_chanmap) + [-1] * (rows - cin8), dtype=torch.int32, device=self.device)
+        packs = []
+        for a in range(s):
+            for b in range(s):
+                tl, offs = [], []
+                for r in range(k):
+                    if (a + pt - r * d) % s:
+                        continue
+                    for c in range(k):
+                        if (b + pl - c * d) % s:
+                            continue
+                        tl.append(r * k + c)
+                        offs.append(((a + pt - r * d) // s, (b + pl - c * d) // s))
+                # value = W[t, ci, co] -> flat (t*cin + ci)*cout + co ; K position (ti, co), row n = ci
+                kmap, Kp = self._kmap(tl, g_chan, self.cin * self.cout, 1)
+                packs.append(dict(a=a, b=b, taps=offs, kmap=kmap, K_pad=Kp, rows=rows, BN=bn_, n_tiles=nt, nmap=nmap,
+                                  w=torch.zeros(rows, Kp, dtype=torch.bfloat16, device=self.device)))
+        self.dgrad_packs = packs
+
+    def setup_transposed(self, chanmap):
+        """tf.layers.conv2d_transpose(k=4, s=2, 'same') as four output-parity stride-1 launches (model_pwcnet.py:286)."""
+        assert self.transposed and self.k == 4
+        self.in_chanmap = list(chanmap)
+        packs = []
+        for a in range(2):
+            for b in range(2):
+                tl, offs = [], []
+                for ky in range(4):
+                    if (a + 1 - ky) % 2:
+                        continue
+                    for kx in range(4):
+                        if (b + 1 - kx) % 2:
+                            continue
+                        tl.append(ky * 4 + kx)
+                        offs.append(((a + 1 - ky) // 2, (b + 1 - kx) // 2))
+                # kernel [kh,kw,Cout,Cin]: flat ((t*Cout + co)*Cin + ci) ; K position (ti, ci), row n = co (stride Cin)
+                kmap, Kp = self._kmap(tl, chanmap, self.cout * self.cin, 1)
+                packs.append(dict(a=a, b=b, taps=offs, kmap=kmap, K_pad=Kp,
+                                  w=torch.zeros(self.npad, Kp, dtype=torch.bfloat16, device=self.device)))
+        self.tr_packs = packs
+        self.fwd_pack = True
+
+
+# ================================================================================================ graph builder
+class Builder(object):
+    """Builds the forward plan and records backward closures (reverse-mode, hand-scheduled)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.fwd = Plan('fwd')
+        self.tape = []       # backward closures in forward order
+        self.scratch = []
+
+    # ---- helpers
+    def new_act(self, N, H, W, C, name='', dep=frozenset(), n_mod=0):
+        return Act(N, H, W, C, self.device, name=name, dep=dep, n_mod=n_mod)
+
+    def conv(self, layer, srcs, out=None, post_add=None, addf=None, outf=None, outf_ch=0, mode=0, want_bf16=True, name=None,
+             plan=None, out_rows=None):
+        """y = act(conv(concat(srcs)) + bias [+ addf]) [+ post_add]; returns the output Act."""
+        plan = plan or self.fwd
+        s0 = srcs[0]
+        N = out_rows or max(s.N for s in srcs)
+        H, W = s0.H, s0.W
+        for s in srcs:
+            assert (s.H, s.W) == (H, W), (layer.name, [(q.H, q.W) for q in srcs])
+        chanmap = []
+        base = 0
+        for s in srcs:
+            chanmap += [(m + base if m >= 0 else -1) for m in s.chanmap]
+            base += s.C
+        if layer.fwd_pack is None:
+            layer.setup_fwd(chanmap)
+        else:
+            assert layer.in_chanmap == chanmap, layer.name
+        OH, OW = -(-H // layer.stride), -(-W // layer.stride)
+        dep = frozenset().union(*[s.dep for s in srcs]) | ({layer.tag} if layer.tag else frozenset())
+        if post_add is not None:
+            dep = dep | post_add.dep
+        if out is None and want_bf16:
+            out = self.new_act(N, OH, OW, layer.cout, name=name or layer.name, dep=dep)
+        if out is not None:
+            out.dep = out.dep | dep
+            gr = [s.gen_rows for s in srcs if s.gen_rows]
+            if gr:
+                out.gen_rows = gr[0]
+        taps, _, _ = layer.fwd_taps(H, W)
+        d = CisConv()
+        d.N, d.H, d.W, d.OH, d.OW, d.sh, d.sw = N, H, W, OH, OW, layer.stride, layer.stride
+        _fill_taps(d, taps)
+        _fill_srcs(d, srcs)
+        d.wpack, d.K_pad, d.BN, d.n_tiles = layer.fwd_pack.data_ptr(), layer.K_pad, layer.BN, layer.n_tiles
+        d.bias, d.act, d.alpha = layer.bias_ptr(), layer.act, layer.alpha
+        d.DH, d.DW, d.osh, d.osw, d.oa, d.ob = OH, OW, 1, 1, 0, 0
+        if out is not None:
+            d.out, d.out_pitch, d.out_coff, d.out_ch = out.ptr, out.pitch, out.c_off, out.C8
+        if outf is not None:
+            d.outf, d.outf_pitch, d.outf_coff, d.outf_ch = outf.data_ptr(), outf.shape[-1], 0, outf_ch or outf.shape[-1]
+        if addf is not None:
+            d.addf_pre, d.addf_pitch, d.addf_coff = addf.data_ptr(), addf.shape[-1], 0
+            if outf is None:
+                d.outf_ch = addf.shape[-1]
+        if post_add is not None:
+            d.add_post, d.add_post_pitch, d.add_post_coff = post_add.ptr, post_add.pitch, post_add.c_off
+        d.mode = mode
+        plan.keep.append(d)
+        plan.add('cis_conv_igemm', C.byref(d))
+        if layer.tag:
+            self.tape.append(lambda bp, m, L=layer, S=list(srcs), O=out, P=post_add: self._conv_bwd(bp, m, L, S, O, P))
+        return out
+
+    def _conv_bwd(self, bp, mode, layer, srcs, out, post_add):
+        if out is None or mode not in out.dep or not out.grad_written.get(mode):
+            return
+        G = out.get_grad()
+        nb = out.rows(mode)
+        npix = nb * out.H * out.W
+        if post_add is not None and mode in post_add.dep:
+            pg = post_add.get_grad()
+            bp.add('cis_add_slice', pg.ptr, pg.pitch, pg.c_off, G.ptr, G.pitch, G.c_off, npix, G.C8 // 8, 1,
+                   1 if post_add.grad_written.get(mode) else 0)
+            post_add.grad_written[mode] = True
+        if layer.act != ACT_NONE:
+            bp.add('cis_dact_mul', G.ptr, G.pitch, G.c_off, out.ptr, out.pitch, out.c_off,
+                   post_add.ptr if post_add is not None else None, post_add.pitch if post_add is not None else 0,
+                   post_add.c_off if post_add is not None else 0, npix, G.C8 // 8, layer.act, layer.alpha)
+        s0 = srcs[0]
+        H, W = s0.H, s0.W
+        taps, _, _ = layer.fwd_taps(H, W)
+        if layer.tag == mode:   # weight + bias gradients
+            if not hasattr(layer, 'dwp'):
+                layer.dwp = torch.zeros(layer.cout, layer.K_pad, dtype=torch.float32, device=self.device)
+            w = CisWgrad()
+            w.N, w.H, w.W, w.OH, w.OW, w.sh, w.sw = nb, H, W, out.H, out.W, layer.stride, layer.stride
+            _fill_taps(w, taps)
+            _fill_srcs(w, srcs)
+            w.g, w.g_pitch, w.g_coff, w.g_chunks = G.ptr, G.pitch, G.c_off, G.C8 // 8
+            w.dwp, w.Cout, w.K_pad = layer.dwp.data_ptr(), layer.cout, layer.K_pad
+            nkb = -(-npix // 64)
+            ntile = -(-layer.K_pad // 128)
+            w.splits = max(1, min(nkb // 4 if nkb >= 4 else 1, max(1, (2 * 148) // ntile)))
+            bp.keep.append(w)
+            bp.add('cis_conv_wgrad', C.byref(w))
+            layer.wgrad_modes = getattr(layer, 'wgrad_modes', set()) | {mode}
+            bp.add('cis_colsum', G.ptr, G.pitch, G.c_off, npix, layer.cout,
+                   (layer.db_eff.data_ptr() if layer.bn else layer.store.ptr(layer.bkey, 'grad')))
+        need = [s for s in srcs if mode in s.dep]
+        if not need:
+            return
+        layer.setup_dgrad(H, W)
+        layer.dgrad_used = True
+        cin8 = len(layer.in_chanmap)
+        single = (len(srcs) == 1 and srcs[0].n_mod == 0)
+        if single:
+            tgt = srcs[0].get_grad()
+            acc = bool(srcs[0].grad_written.get(mode))
+        else:
+            if not hasattr(layer, 'dcat'):
+                layer.dcat = Act(max(s.N for s in srcs), H, W, cin8, self.device, chanmap=layer.in_chanmap, name=layer.name + '.dcat')
+            tgt, acc = layer.dcat, False
+        for pk in layer.dgrad_packs:
+            s = layer.stride
+            oh = -(-(H - pk['a']) // s)
+            ow = -(-(W - pk['b']) // s)
+            if oh <= 0 or ow <= 0:
+                continue
+            d = CisConv()
+            d.N, d.H, d.W, d.OH, d.OW, d.sh, d.sw = nb, out.H, out.W, oh, ow, 1, 1
+            _fill_taps(d, pk['taps'])
+            d.nsrc = 1
+            d.src[0] = G.src()
+            d.wpack, d.K_pad, d.BN, d.n_tiles = pk['w'].data_ptr(), pk['K_pad'], pk['BN'], pk['n_tiles']
+            d.bias, d.act = None, ACT_NONE
+            d.DH, d.DW, d.osh, d.osw, d.oa, d.ob = H, W, s, s, pk['a'], pk['b']
+            d.out, d.out_pitch, d.out_coff, d.out_ch = tgt.ptr, tgt.pitch, tgt.c_off, tgt.C8
+            if acc:
+                d.add_pre, d.add_pre_pitch, d.add_pre_coff = tgt.ptr, tgt.pitch, tgt.c_off
+            bp.keep.append(d)
+            bp.add('cis_conv_igemm', C.byref(d))
+        if single:
+            srcs[0].grad_written[mode] = True
+        else:
+            off = 0
+            for s_ in srcs:
+                if mode in s_.dep:
+                    sg = s_.get_grad()
+                    reps = 1
+                    rows = s_.rows(mode)
+                    if s_.n_mod:
+                        reps = nb // s_.n_mod
+                        rows = s_.n_mod
+                    bp.add('cis_add_slice', sg.ptr, sg.pitch, sg.c_off, tgt.ptr, tgt.pitch, off, rows * H * W, s_.C8 // 8, reps,
+                           1 if s_.grad_written.get(mode) else 0)
+                    s_.grad_written[mode] = True
+                off += s_.C8
+
+    # ---- transposed conv (PWC-Net up_flow / up_feat), forward only
+    def conv_transpose(self, layer, src, out=None, outf=None, plan=None, name=None):
+        plan = plan or self.fwd
+        if layer.fwd_pack is None:
+            layer.setup_transposed(src.chanmap)
+        N, H, W = src.N, src.H, src.W
+        if out is None:
+            out = self.new_act(N, 2 * H, 2 * W, layer.cout, name=name or layer.name, dep=src.dep)
+        for pk in layer.tr_packs:
+            d = CisConv()
+            d.N, d.H, d.W, d.OH, d.OW, d.sh, d.sw = N, H, W, H, W, 1, 1
+            _fill_taps(d, pk['taps'])
+            _fill_srcs(d, [src])
+            d.wpack, d.K_pad, d.BN, d.n_tiles = pk['w'].data_ptr(), pk['K_pad'], layer.BN, layer.n_tiles
+            d.bias, d.act = layer.bias_ptr(), ACT_NONE
+            d.DH, d.DW, d.osh, d.osw, d.oa, d.ob = 2 * H, 2 * W, 2, 2, pk['a'], pk['b']
+            d.out, d.out_pitch, d.out_coff, d.out_ch = out.ptr, out.pitch, out.c_off, layer.cout
+            if outf is not None:
+                d.outf, d.outf_pitch, d.outf_coff, d.outf_ch = outf.data_ptr(), outf.shape[-1], 0, layer.cout
+            plan.keep.append(d)
+            plan.add('cis_conv_igemm', C.byref(d))
+        return out
+
+    # ---- resampling ops
+    def resize_bilinear(self, src, OH, OW, name=''):
+        """tf.image.resize_images legacy bilinear (convolution_utils.py:88); identity when the size matches."""
+        if (src.H, src.W) == (OH, OW):
+            return src
+        out = Act(src.N, OH, OW, src.C, self.device, chanmap=src.chanmap, n_mod=src.n_mod, dep=src.dep, name=name or src.name + '.rs')
+        out.gen_rows = src.gen_rows
+        self.fwd.add('cis_resize_bilinear_bf16', src.ptr, src.pitch, src.c_off, src.N, src.H, src.W, out.ptr, out.pitch, out.c_off, OH, OW,
+                     src.C8 // 8)
+
+        def bwd(bp, mode):
+            if mode not in out.dep or not out.grad_written.get(mode):
+                return
+            g, sg = out.get_grad(), src.get_grad()
+            bp.add('cis_resize_bilinear_bf16_bwd', g.ptr, g.pitch, g.c_off, out.rows(mode), OH, OW, sg.ptr, sg.pitch, sg.c_off, src.H, src.W,
+                   src.C8 // 8, 1 if src.grad_written.get(mode) else 0)
+            src.grad_written[mode] = True
+        self.tape.append(bwd)
+        return out
+
+    def upsample_nn2x(self, src, name=''):
+        """tf.image.resize_nearest_neighbor(align_corners=True) x2 (convolution_utils.py:71)."""
+        assert src.c_off == 0 and src.pitch == src.C8
+        out = Act(src.N, 2 * src.H, 2 * src.W, src.C, self.device, chanmap=src.chanmap, dep=src.dep, name=name or src.name + '.up')
+        self.fwd.add('cis_upsample_nn2x', src.ptr, src.N, src.H, src.W, src.pitch, out.ptr)
+
+        def bwd(bp, mode):
+            if mode not in out.dep or not out.grad_written.get(mode):
+                return
+            g, sg = out.get_grad(), src.get_grad()
+            bp.add('cis_upsample_nn2x_bwd', g.ptr, src.N, src.H, src.W, src.pitch, sg.ptr, 1 if src.grad_written.get(mode) else 0)
+            src.grad_written[mode] = True
+        self.tape.append(bwd)
+        return out
+
+    def build_backward(self, mode, seeds):
+        """seeds: Acts whose .grad has been written by the loss backward.  Returns the backward Plan for `mode`."""
+        bp = Plan('bwd_' + mode)
+        for a in seeds:
+            a.grad_written[mode] = True
+        for fn in reversed(self.tape):
+            fn(bp, mode)
+        return bp

@@ -1,0 +1,223 @@
+"""Device-side step graph: everything adversarial_learner.py:72-258 puts in the TF graph, as static launch lists.
+
+One `CISGraph` owns the parameters (flat fp32 master copies per scope), all activation buffers for a fixed
+(batch, 384x640 -> HxW) geometry, and the launch lists: forward (PWC-Net -> resize -> generator -> mask (x) flow ->
+3x recover -> Charbonnier losses), backward for the recover step, backward for the generator step, and clip + TF-Adam.
+"""
+import math
+import torch
+
+from . import _lib
+from .engine import Builder, ParamStore, Plan, Act
+from .models.nets import GeneratorNet, RecoverNet
+from .models.PWCNet.model_pwcnet import ModelPWCNet
+
+PWC_H, PWC_W = 384, 640   # data/davis2016_data_utils.py:87-88: frames are resized to 384x640 before PWC-Net
+
+
+class CISGraph(object):
+    def __init__(self, img_height, img_width, batch, device='cuda', global_batch=None, flow_normalizer=80.0, cbn=0.5, epsilon=75.0,
+                 beta1=0.9, with_pwc=True, train=True, pwc_hw=(PWC_H, PWC_W), seed=8964):
+        _lib.load()
+        self.H, self.W, self.B = img_height, img_width, batch
+        self.GB = global_batch or batch
+        self.dev = device
+        self.cbn, self.eps_rr, self.flow_norm, self.beta1 = cbn, epsilon, flow_normalizer, beta1
+        self.with_pwc, self.train = with_pwc, train
+        self.seed = seed
+        f32 = lambda *s: torch.zeros(*s, dtype=torch.float32, device=device)
+        B, H, W = batch, img_height, img_width
+        # ---- parameter stores (scopes of adversarial_learner.py:211-214 and model_pwcnet.py)
+        self.gen_store, self.rec_store, self.pwc_store = ParamStore(device), ParamStore(device), ParamStore(device)
+        self.gen = GeneratorNet(self.gen_store)
+        self.rec = RecoverNet(self.rec_store)
+        self.gen_store.finalize(True)
+        self.rec_store.finalize(True)
+        if with_pwc:
+            self.pwc = ModelPWCNet(self.pwc_store)
+            self.pwc_store.finalize(False)
+        self.step_state = torch.zeros(1, dtype=torch.int64, device=device)   # shared Adam beta-power step (App. A.14)
+        self.avg_abs = f32(1)
+        # ---- static buffers
+        bld = Builder(device)
+        self.bld = bld
+        P = bld.fwd
+        if with_pwc:
+            ph, pw = pwc_hw
+            self.img1, self.img2 = f32(B, ph, pw, 3), f32(B, ph, pw, 3)
+            self.flow_full = f32(B, ph, pw, 2)
+            i1 = Act(B, ph, pw, 3, device, name='img1_8')
+            i2 = Act(B, ph, pw, 3, device, name='img2_8')
+            npx = B * ph * pw
+            P.add('cis_pack_f32_to_bf16', self.img1.data_ptr(), npx, 3, 0.5, i1.ptr, 8, 0)     # adapt_x: img + 0.5
+            P.add('cis_pack_f32_to_bf16', self.img2.data_ptr(), npx, 3, 0.5, i2.ptr, 8, 0)
+            self.pwc.build(bld, i1, i2, self.flow_full)
+        self.image = f32(B, H, W, 3)
+        self.flow = f32(B, H, W, 2)
+        if with_pwc:
+            # adversarial_learner.py:87-97: legacy bilinear to (H,W); flow / flow_normalizer
+            P.add('cis_resize_bilinear_f32', self.img1.data_ptr(), B, ph, pw, 3, self.image.data_ptr(), H, W, 1.0)
+            P.add('cis_resize_bilinear_f32', self.flow_full.data_ptr(), B, ph, pw, 2, self.flow.data_ptr(), H, W, 1.0 / flow_normalizer)
+        self.stats = torch.zeros(B, 4, dtype=torch.float64, device=device)
+        self.gen_in = Act(B, H, W, 5, device, name='gen_in')
+        self.img8 = Act(B, H, W, 3, device, name='img8')
+        hw = H * W
+        P.zero(self.stats)
+        P.add('cis_flow_stats', self.flow.data_ptr(), B, hw, self.stats.data_ptr())                       # flow_utils.py:10
+        P.add('cis_pack_generator_input', self.image.data_ptr(), self.flow.data_ptr(), self.stats.data_ptr(), B, hw, self.gen_in.ptr)
+        P.add('cis_pack_f32_to_bf16', self.image.data_ptr(), B * hw, 3, 0.0, self.img8.ptr, 8, 0)
+        self.mask = f32(B, H, W, 1)
+        self.gen.build(bld, self.gen_in, self.mask)
+        # mask (x) flow -> recover inputs for the 3 calls (adversarial_learner.py:107-131)
+        self.rec_in = Act(3 * B, H, W, 4, device, name='rec_in', dep={'G'})
+        self.rec_in.gen_rows = 2 * B
+        P.add('cis_mask_apply', self.flow.data_ptr(), self.mask.data_ptr(), B, hw, self.rec_in.ptr)
+        self.dmask = f32(B, H, W)
+        logits = self.gen.logits
+
+        def mask_bwd(bp, mode):
+            if mode != 'G':
+                return
+            g = self.rec_in.get_grad()
+            assert self.rec_in.grad_written.get('G'), 'recover backward did not reach the mask inputs'
+            lg = logits.get_grad()
+            bp.add('cis_mask_bwd', self.flow.data_ptr(), self.mask.data_ptr(), self.dmask.data_ptr(), g.ptr, B, hw, lg.ptr)
+            logits.grad_written['G'] = True
+        bld.tape.append(mask_bwd)
+        h1, w1 = -(-H // 2), -(-W // 2)
+        self.h1, self.w1 = h1, w1
+        self.flow1 = f32(3 * B, h1, w1, 2)
+        self.rec.build(bld, self.img8, self.rec_in, self.flow1)
+        # ---- losses (adversarial_learner.py:141-204)
+        self.sums = torch.zeros(B, 5, dtype=torch.float64, device=device)
+        self.scalars = f32(8)
+        self.coef = f32(B, 4)
+        self.pred = f32(3 * B, H, W, 2)
+        P.zero(self.sums)
+        P.add('cis_cis_loss_fwd', self.flow.data_ptr(), self.mask.data_ptr(), self.flow1.data_ptr(), B, H, W, h1, w1, cbn,
+              self.sums.data_ptr(), self.pred.data_ptr())
+        P.add('cis_cis_loss_reduce', self.sums.data_ptr(), B, self.GB, hw, epsilon, self.scalars.data_ptr(), self.coef.data_ptr())
+        self.fwd = P
+        # ---- weight packing plans
+        self.pack_pwc = Plan('pack_pwc')
+        if with_pwc:
+            for L in self.pwc.all_layers():
+                L.plan_pack(self.pack_pwc)
+        self.bwd = {}
+        self.adam = {}
+        if train:
+            self.dpred = f32(3 * B, H, W, 2)
+            for mode, which in (('R', 0), ('G', 1)):
+                nb = 3 * B if mode == 'R' else 2 * B
+                head = Plan('loss_bwd_' + mode)
+                head.add('cis_cis_loss_bwd', self.flow.data_ptr(), self.mask.data_ptr(), self.flow1.data_ptr(), self.coef.data_ptr(),
+                         self.scalars.data_ptr(), B, H, W, h1, w1, cbn, which, self.dpred.data_ptr(), self.dmask.data_ptr())
+                fg = self.rec.flow1.get_grad()
+                head.add('cis_resize_f32_bwd_to_bf16', self.dpred.data_ptr(), nb, H, W, 2, h1, w1, fg.ptr, fg.pitch)
+                body = bld.build_backward(mode, [self.rec.flow1])
+                store = self.rec_store if mode == 'R' else self.gen_store
+                layers = self.rec.all_layers() if mode == 'R' else self.gen.all_layers()
+                pre = Plan('zero_' + mode)
+                pre.zero(store.grad)
+                for L in layers:
+                    L.plan_zero_grads(pre)
+                fin = Plan('fin_' + mode)
+                for L in layers:
+                    L.plan_finalize(fin)
+                full = Plan('bwd_' + mode)
+                for pl in (pre, head, body, fin):
+                    full.extend(pl)
+                self.bwd[mode] = full
+                ad = Plan('adam_' + mode)
+                if mode == 'G':
+                    # can_change branch of train_op (loss_utils.py:18-26)
+                    self.seg = torch.tensor([v for pr in store.seg_pairs for v in pr], dtype=torch.int64, device=device)
+                    ad.zero(self.avg_abs)
+                    ad.add('cis_grad_avg_abs', store.grad.data_ptr(), self.seg.data_ptr(), len(store.seg_pairs), self.avg_abs.data_ptr())
+                ad.add('cis_clip_adam', store.flat.data_ptr(), store.m.data_ptr(), store.v.data_ptr(), store.grad.data_ptr(), store.size, 1.0,
+                       0.2, 1e-4, beta1, 0.999, 1e-8, self.step_state.data_ptr(), self.avg_abs.data_ptr(), 1 if mode == 'G' else 0, seed)
+                self.adam[mode] = ad
+        # packing of the trainable nets (forward + data-gradient orientation), after backward planning decided what is needed
+        self.pack_gen, self.pack_rec = Plan('pack_gen'), Plan('pack_rec')
+        for L in self.gen.all_layers():
+            L.plan_pack(self.pack_gen, dgrad=train)
+        for L in self.rec.all_layers():
+            L.plan_pack(self.pack_rec, dgrad=train)
+        self._pwc_packed = False
+        self.graphs = {}
+
+    # ------------------------------------------------------------------------------------------------ parameters
+    def load_params(self, params):
+        """params: dict name -> tensor with the reference's variable layout (see oracle/params.py for the names)."""
+        self.gen_store.load(params)
+        self.rec_store.load(params)
+        if self.with_pwc:
+            self.pwc_store.load(params)
+            self._pwc_packed = False
+
+    def export_params(self):
+        out = {}
+        out.update(self.gen_store.export())
+        out.update(self.rec_store.export())
+        if self.with_pwc:
+            out.update(self.pwc_store.export())
+        return out
+
+    def param_count(self):
+        return self.gen_store.real_count() + self.rec_store.real_count() + (self.pwc_store.real_count() if self.with_pwc else 0)
+
+    # ------------------------------------------------------------------------------------------------ execution
+    def _ensure_pwc(self):
+        if self.with_pwc and not self._pwc_packed:
+            self.pack_pwc.run()
+            self._pwc_packed = True
+
+    def forward(self):
+        self._ensure_pwc()
+        self.pack_gen.run()
+        self.pack_rec.run()
+        self.fwd.run()
+
+    def launches_per_step(self, mode):
+        return self.pack_gen.count() + self.pack_rec.count() + self.fwd.count() + self.bwd[mode].count() + self.adam[mode].count()
+
+    def train_step(self, mode, allreduce=None, use_graph=False):
+        """One alternating step body (adversarial_learner.py:380-397): mode 'R' = train_recover_op, 'G' = train_generator_op."""
+        self._ensure_pwc()
+        if use_graph:
+            g = self.graphs.get(mode)
+            if g is None:
+                g = self._capture(mode)
+            g[0].replay()
+            if allreduce is not None:
+                allreduce((self.rec_store if mode == 'R' else self.gen_store).grad)
+            g[1].replay()
+            return
+        self.pack_gen.run()
+        self.pack_rec.run()
+        self.fwd.run()
+        self.bwd[mode].run()
+        if allreduce is not None:
+            allreduce((self.rec_store if mode == 'R' else self.gen_store).grad)
+        self.adam[mode].run()
+
+    def _capture(self, mode):
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            # warm-up outside capture (sets function attributes, lazy allocations)
+            self.pack_gen.run(); self.pack_rec.run(); self.fwd.run(); self.bwd[mode].run()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            self.pack_gen.run(); self.pack_rec.run(); self.fwd.run(); self.bwd[mode].run()
+        with torch.cuda.graph(g2):
+            self.adam[mode].run()
+        self.graphs[mode] = (g1, g2)
+        return self.graphs[mode]
+
+    def losses(self):
+        s = self.scalars.tolist()
+        return dict(generator=s[0], recover=s[1], red_rate=s[2], red_rate_compl=s[3])

@@ -1,0 +1,56 @@
+"""CLI eval, same flag surface as the reference's test_generator.py (:42-144): per-category IoU / MAE of the generated
+masks (threshold 0.1, border-score disambiguation).  PNG / .mat dumps are a later row."""
+import sys
+
+import numpy as np
+from absl import flags as gflags
+
+from unsupervised_detection_b200.common_flags import FLAGS
+from unsupervised_detection_b200.models.adversarial_learner import AdversarialLearner
+from unsupervised_detection_b200.models.utils.general_utils import compute_IoU, compute_mae
+
+
+def _test_masks():
+    learner = AdversarialLearner()
+    learner.setup_inference(FLAGS, aug_test=False)
+    if not FLAGS.ckpt_file:
+        raise IOError("Checkpoint file not found")           # test_generator.py:58
+    learner.restore(FLAGS.ckpt_file)
+    print("Resume model from checkpoint {}".format(FLAGS.ckpt_file))
+    CategoryIou, CategoryMae = {}, {}
+    n_steps = int(np.ceil(learner.test_samples / float(FLAGS.batch_size)))
+    i = 0
+    for step in range(n_steps):
+        inference = learner.inference(None)
+        for b in range(inference['input_image'].shape[0]):
+            generated_mask = inference['gen_masks'][b]
+            gt_mask = inference['gt_masks'][b]
+            category = inference['img_fname'][b].decode("utf-8").split('/')[-2]
+            iou, out_mask = compute_IoU(gt_mask=gt_mask, pred_mask_f=generated_mask)
+            mae = compute_mae(gt_mask=gt_mask, pred_mask_f=out_mask)
+            CategoryIou.setdefault(category, []).append(iou)
+            CategoryMae.setdefault(category, []).append(mae)
+            i += 1
+    tot_ious = tot_maes = 0
+    per_cat_iou = []
+    for cat, list_iou in CategoryIou.items():
+        print("Category {}: IoU is {} and MAE is {}".format(cat, np.mean(list_iou), np.mean(CategoryMae[cat])))
+        tot_ious += np.sum(list_iou)
+        tot_maes += np.sum(CategoryMae[cat])
+        per_cat_iou.append(np.mean(list_iou))
+    print("The Average over the dataset: IoU is {} and MAE is {}".format(tot_ious / float(i), tot_maes / float(i)))
+    print("The Average over sequences IoU is {}".format(np.mean(per_cat_iou)))
+    print("Success: Processed {} frames".format(i))
+
+
+def main(argv):
+    try:
+        argv = FLAGS(argv)
+    except gflags.Error:
+        print('Usage: %s ARGS\n%s' % (sys.argv[0], FLAGS))
+        sys.exit(1)
+    _test_masks()
+
+
+if __name__ == "__main__":
+    main(sys.argv)

@@ -353,11 +353,21 @@ class Builder(object):
         self.device = device
         self.fwd = Plan('fwd')
         self.tape = []       # backward closures in forward order
-        self.scratch = []
+        self.keep = []       # every buffer referenced by raw pointer from a descriptor must outlive the plans
 
     # ---- helpers
     def new_act(self, N, H, W, C, name='', dep=frozenset(), n_mod=0):
-        return Act(N, H, W, C, self.device, name=name, dep=dep, n_mod=n_mod)
+        a = Act(N, H, W, C, self.device, name=name, dep=dep, n_mod=n_mod)
+        self.keep.append(a)
+        return a
+
+    def hold(self, obj):
+        """Register a tensor / Act whose storage is referenced by raw pointer from a launch descriptor."""
+        self.keep.append(obj)
+        return obj
+
+    def f32(self, *shape):
+        return self.hold(torch.zeros(*shape, dtype=torch.float32, device=self.device))
 
     def conv(self, layer, srcs, out=None, post_add=None, addf=None, outf=None, outf_ch=0, mode=0, want_bf16=True, name=None,
              plan=None, out_rows=None):
@@ -408,6 +418,7 @@ class Builder(object):
             d.add_post, d.add_post_pitch, d.add_post_coff = post_add.ptr, post_add.pitch, post_add.c_off
         d.mode = mode
         plan.keep.append(d)
+        plan.keep += [srcs, out, outf, addf, post_add, layer]
         plan.add('cis_conv_igemm', C.byref(d))
         if layer.tag:
             self.tape.append(lambda bp, m, L=layer, S=list(srcs), O=out, P=post_add: self._conv_bwd(bp, m, L, S, O, P))
@@ -518,6 +529,7 @@ class Builder(object):
             if outf is not None:
                 d.outf, d.outf_pitch, d.outf_coff, d.outf_ch = outf.data_ptr(), outf.shape[-1], 0, layer.cout
             plan.keep.append(d)
+            plan.keep += [src, out, outf, layer]
             plan.add('cis_conv_igemm', C.byref(d))
         return out
 
@@ -528,6 +540,7 @@ class Builder(object):
             return src
         out = Act(src.N, OH, OW, src.C, self.device, chanmap=src.chanmap, n_mod=src.n_mod, dep=src.dep, name=name or src.name + '.rs')
         out.gen_rows = src.gen_rows
+        self.keep += [src, out]
         self.fwd.add('cis_resize_bilinear_bf16', src.ptr, src.pitch, src.c_off, src.N, src.H, src.W, out.ptr, out.pitch, out.c_off, OH, OW,
                      src.C8 // 8)
 
@@ -545,6 +558,7 @@ class Builder(object):
         """tf.image.resize_nearest_neighbor(align_corners=True) x2 (convolution_utils.py:71)."""
         assert src.c_off == 0 and src.pitch == src.C8
         out = Act(src.N, 2 * src.H, 2 * src.W, src.C, self.device, chanmap=src.chanmap, dep=src.dep, name=name or src.name + '.up')
+        self.keep += [src, out]
         self.fwd.add('cis_upsample_nn2x', src.ptr, src.N, src.H, src.W, src.pitch, out.ptr)
 
         def bwd(bp, mode):

@@ -91,6 +91,7 @@ class ModelPWCNet(object):
                 x = B.conv(self.L['featpyr/conv%db' % l], [x], out=out)
                 pyr.append(x)
         self.c1, self.c2 = c1, c2
+        B.hold((c1, c2, E))
         up_flow_f32 = None
         self.flows = {}
         for l in range(PYR_LVLS, FLOW_PRED_LVL - 1, -1):
@@ -108,20 +109,20 @@ class ModelPWCNet(object):
                 dst = Act(N, h, w, co, dev, buf=E[l], c_off=A_OFF[i], name='act%d_%d' % (l, i))
                 B.conv(self.L['predict_flow/conv%d_%d' % (l, i)], [src], out=dst)
             upfeat = Act(N, h, w, 0, dev, buf=E[l], c_off=0, chanmap=self._chanmap(l, 0), name='upfeat%d' % l)
-            flow_raw = torch.zeros(N, h, w, 2, dtype=torch.float32, device=dev)
+            flow_raw = B.f32(N, h, w, 2)
             B.conv(self.L['predict_flow/flow%d' % l], [upfeat], outf=flow_raw, want_bf16=False)
             # ---- context network (:559-576): flow += ctx(upfeat)
             x = upfeat
             for i in range(1, 7):
                 x = B.conv(self.L['ctxt/dc_conv%d%d' % (l, i)], [x])
-            flow = torch.zeros(N, h, w, 2, dtype=torch.float32, device=dev)
+            flow = B.f32(N, h, w, 2)
             flow_bf = B.conv(self.L['ctxt/dc_conv%d7' % l], [x], addf=flow_raw, outf=flow)
             self.flows[l] = flow
             if l != FLOW_PRED_LVL:
                 # ---- 4x4 stride-2 transposed convs into the next level's buffer tail (:634-635)
                 nh, nw = hs[l - 1]
                 tail = C1_OFF + NUM_CHANN[l - 1]
-                up_flow_f32 = torch.zeros(N, nh, nw, 2, dtype=torch.float32, device=dev)
+                up_flow_f32 = B.f32(N, nh, nw, 2)
                 o1 = Act(N, nh, nw, 2, dev, buf=E[l - 1], c_off=tail, chanmap=[0, 1], name='up_flow%d' % l)
                 o2 = Act(N, nh, nw, 2, dev, buf=E[l - 1], c_off=tail + 2, chanmap=[0, 1], name='up_feat%d' % l)
                 assert (nh, nw) == (2 * h, 2 * w), 'PWC-Net needs H, W divisible by 64'

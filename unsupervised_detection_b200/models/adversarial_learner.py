@@ -1,0 +1,281 @@
+"""AdversarialLearner: the reference's learner surface (models/adversarial_learner.py:18-623) on the B200 step graph.
+
+Kept API: AdversarialLearner().train(config) / .setup_inference(config, aug_test=False) / .inference(sess) with the same
+result keys (:617-619), plus .step() = one iteration of the loop body (:380-409).  `sess` arguments are accepted and
+ignored (there is no tf.Session).  Data parallelism (not in the reference): one process per GPU, the frame-pair batch is
+sharded over ranks and the active network's flat gradient buffer is summed with ONE NCCL all-reduce per step
+(SURVEY.md section 8e); clip / noise test / Adam then run identically on every rank.
+"""
+import math
+import os
+import time
+from itertools import count
+
+import numpy as np
+import torch
+
+from ..step_graph import CISGraph, PWC_H, PWC_W
+from ..data.synthetic import SyntheticReader
+from .. import params_init
+from .utils.general_utils import compute_all_IoU
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+class AdversarialLearner(object):
+    def __init__(self):
+        self.graph = None
+        self.global_step = 0
+        self._step = 0
+        self.aug_test = False
+
+    # ------------------------------------------------------------------------------------------------ data
+    def load_training_data(self):
+        """adversarial_learner.py:22-70.  Dataset readers are host-side code outside the accelerated path;
+        'SYNTHETIC' yields seeded frame pairs of the readers' shape.  Unknown datasets raise IOError like the reference."""
+        ds = self.config.dataset
+        if ds == 'SYNTHETIC':
+            self.reader = SyntheticReader(PWC_H, PWC_W, seed=8964 + self.rank)
+            self.num_samples_val = self.reader.val_samples
+            return
+        if ds in ('DAVIS2016', 'FBMS', 'SEGTRACK'):
+            if not os.path.isdir(self.config.root_dir):
+                raise IOError("Dataset folder %s not found" % self.config.root_dir)
+            raise NotImplementedError("dataset readers for %s are a later row of the scope table (SURVEY.md 8f-2); "
+                                      "use --dataset=SYNTHETIC" % ds)
+        raise IOError("Dataset should be DAVIS2016 / FBMS / SEGTRACK")
+
+    # ------------------------------------------------------------------------------------------------ graphs
+    def _init_dist(self):
+        self.world, self.rank, self.local_rank = 1, 0, 0
+        if int(os.environ.get('WORLD_SIZE', '1')) > 1:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                dist.init_process_group('nccl' if torch.cuda.is_available() else 'gloo')
+            self.world, self.rank = dist.get_world_size(), dist.get_rank()
+            self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        self.device = 'cuda:%d' % self.local_rank
+        torch.cuda.set_device(self.local_rank)
+
+    def build_train_graph(self):
+        """adversarial_learner.py:72-258: PWC-Net -> resize -> generator -> 3x recover -> losses -> two train ops."""
+        cfg = self.config
+        self._init_dist()
+        if cfg.batch_size % self.world:
+            raise ValueError('batch_size must be divisible by the number of ranks')
+        self.local_batch = cfg.batch_size // self.world
+        self.load_training_data()
+        self.graph = CISGraph(cfg.img_height, cfg.img_width, self.local_batch, device=self.device, global_batch=cfg.batch_size,
+                              flow_normalizer=cfg.flow_normalizer, cbn=cfg.cbn, epsilon=cfg.epsilon, beta1=cfg.beta1, with_pwc=True, train=True)
+        self.train_steps_per_epoch = int(math.ceil(cfg.num_samples_train / cfg.batch_size))
+        self.val_steps_per_epoch = int(np.ceil(float(self.num_samples_val) / cfg.batch_size))
+        self._init_params()
+        self._pinned = None
+
+    def _init_params(self):
+        cfg = self.config
+        p = {}
+        p.update(params_init.init_generator())
+        p.update(params_init.init_recover())
+        g = self.graph
+        fc = getattr(cfg, 'flow_ckpt', '')
+        if fc.startswith('synthetic'):
+            p.update(params_init.init_pwcnet(g.pwc_store.entries))
+        elif fc and os.path.isfile(fc):
+            p.update(torch.load(fc, map_location='cpu'))
+            print("Flow net loaded from {}".format(fc))
+        else:
+            raise IOError("Could not find flow ckpt file. Aborting.")          # adversarial_learner.py:343
+        if getattr(cfg, 'resume_train', False):
+            ck = cfg.full_model_ckpt if os.path.isfile(cfg.full_model_ckpt) else self._latest_checkpoint(cfg.checkpoint_dir)
+            assert ck, "Found no checkpoint to resume training!"               # :351
+            st = torch.load(ck, map_location='cpu')
+            p.update(st['params'])
+            self.global_step = int(st.get('global_step', 0))
+            print("Resumed training from model {}".format(ck))
+        elif getattr(cfg, 'recover_ckpt', '') and os.path.isfile(cfg.recover_ckpt):
+            st = torch.load(cfg.recover_ckpt, map_location='cpu')
+            p.update({k: v for k, v in st.get('params', st).items() if k.startswith('FlownetS/')})
+            print("Recover net loaded from previous ckpt")
+        else:
+            print("No recover checkpoint found! Train Recover from Scratch")   # :360
+        g.load_params(p)
+
+    @staticmethod
+    def _latest_checkpoint(d):
+        if not d or not os.path.isdir(d):
+            return None
+        c = [f for f in os.listdir(d) if f.startswith('model') and f.endswith('.pt')]
+        return os.path.join(d, max(c, key=lambda f: os.path.getmtime(os.path.join(d, f)))) if c else None
+
+    def save(self, sess, checkpoint_dir, step):
+        """adversarial_learner.py:300-310.  Native format: torch file holding the trainables keyed by TF variable names
+        + global_step (Adam slots are not saved, like the reference's Saver)."""
+        if self.rank != 0:
+            return
+        name = 'model.best.pt' if step == 'best' else 'model-%s.pt' % step
+        print(" [*] Saving checkpoint to {}/model-{}".format(checkpoint_dir, step))
+        os.makedirs(checkpoint_dir, exist_ok=True)
+        torch.save({'params': {k: v.cpu() for k, v in self.graph.export_params().items()}, 'global_step': self.global_step},
+                   os.path.join(checkpoint_dir, name))
+
+    # ------------------------------------------------------------------------------------------------ stepping
+    def _allreduce(self):
+        d = _dist()
+        if d is None or self.world == 1:
+            return None
+        return lambda t: d.all_reduce(t)     # sum: every rank's loss is already divided by the global batch
+
+    def feed(self, img1, img2):
+        """Host -> device copy of one batch of frame pairs [B,384,640,3] fp32 (pinned host tensors copy asynchronously)."""
+        g = self.graph
+        g.img1.copy_(img1, non_blocking=True)
+        g.img2.copy_(img2, non_blocking=True)
+
+    def step(self, batch=None, fetch_losses=None, use_graph=True):
+        """One iteration of the training loop body (adversarial_learner.py:380-409): picks train_recover_op or
+        train_generator_op from the running step counter, consumes one batch, returns {global_step, loss_*?}."""
+        cfg = self.config
+        self._step += 1
+        step = self._step
+        sum_iters = cfg.iters_rec + cfg.iters_gen
+        if step % sum_iters == 0:
+            self.global_step += 1                                              # :382-384
+        mode = 'R' if (step % sum_iters) < cfg.iters_rec else 'G'              # :386-389
+        if batch is None:
+            batch = self.reader.batch(self.local_batch)
+        self.feed(batch[0], batch[1])
+        self.graph.train_step(mode, allreduce=self._allreduce(), use_graph=use_graph)
+        res = {"global_step": self.global_step, "train_op": mode}
+        if fetch_losses if fetch_losses is not None else (step % cfg.summary_freq == 0):
+            L = self.graph.losses()                                            # device -> host read
+            res["loss_recover"], res["loss_generator"] = L['recover'], L['generator']
+        return res
+
+    def train(self, config):
+        """adversarial_learner.py:312-420."""
+        self.config = config
+        self.build_train_graph()
+        self.min_val_iou = -1.0e12
+        if self.rank == 0:
+            print("Number of params: {}".format(self.graph.param_count()))
+            print("-------------------------------------")
+            print("Training {} Recover and {} Generator".format(config.iters_rec, config.iters_gen))
+            print("-------------------------------------")
+        for step in count(start=1):
+            start_time = time.time()
+            results = self.step()
+            if step % config.summary_freq == 0 and self.rank == 0:
+                train_epoch = math.ceil(step / self.train_steps_per_epoch)
+                train_step = step - (train_epoch - 1) * self.train_steps_per_epoch
+                print("Epoch: [%2d] [%5d/%5d] time: %4.4f/it loss_generator: %4.4f loss_recover %4.4f"
+                      % (train_epoch, train_step, self.train_steps_per_epoch, time.time() - start_time,
+                         results["loss_generator"], results["loss_recover"]))
+            if step % self.train_steps_per_epoch == 0:
+                train_epoch = int(step / self.train_steps_per_epoch)
+                self.epoch_end_callback(None, None, train_epoch)
+                if train_epoch == self.config.max_epochs:
+                    if self.rank == 0:
+                        print("-------------------------------")
+                        print("Training completed successfully")
+                        print("-------------------------------")
+                    break
+
+    def epoch_end_callback(self, sess, sv, epoch_num):
+        """adversarial_learner.py:422-448: validation IoU, save best / every save_freq epochs."""
+        validation_iou = 0.0
+        for _ in range(self.val_steps_per_epoch):
+            img1, img2, gt, _ = self.reader.batch(self.local_batch)
+            self.feed(img1, img2)
+            self.graph.forward()
+            masks = self.graph.mask.cpu().numpy()
+            gtr = torch.nn.functional.interpolate(gt.permute(0, 3, 1, 2), size=masks.shape[1:3], mode='nearest').permute(0, 2, 3, 1).numpy()
+            validation_iou += float(np.sum(compute_all_IoU(masks, gtr)))
+        d = _dist()
+        if d is not None and self.world > 1:
+            t = torch.tensor([validation_iou], device=self.device)
+            d.all_reduce(t)
+            validation_iou = float(t)
+        validation_iou /= self.val_steps_per_epoch * self.config.batch_size
+        if self.rank == 0:
+            print("Epoch [{}] Validation IoU: {}".format(epoch_num, validation_iou))
+        if validation_iou > self.min_val_iou:
+            self.save(sess, self.config.checkpoint_dir, 'best')
+            self.min_val_iou = validation_iou
+        if epoch_num % self.config.save_freq == 0:
+            self.save(sess, self.config.checkpoint_dir, epoch_num)
+
+    # ------------------------------------------------------------------------------------------------ inference
+    def build_test_graph(self):
+        """adversarial_learner.py:450-523: PWC-Net -> resize -> generator -> recover (forward only)."""
+        cfg = self.config
+        self._init_dist()
+        self.local_batch = cfg.batch_size
+        self.load_training_data()
+        self.graph = CISGraph(cfg.img_height, cfg.img_width, self.local_batch, device=self.device, flow_normalizer=cfg.flow_normalizer,
+                              cbn=cfg.cbn, epsilon=cfg.epsilon, with_pwc=True, train=False)
+        self.test_samples = self.reader.val_samples
+        self.test_iterator = self.reader
+
+    def build_aug_test_graph(self):
+        """adversarial_learner.py:525-592: multi-crop ensemble, batch 1 per crop (the four crops are batched here)."""
+        self.test_crops = [0.85, 0.9, 0.95, 1.0]
+        print("Evaluating the following crops {}".format(self.test_crops))
+        cfg = self.config
+        self._init_dist()
+        self.local_batch = len(self.test_crops)
+        self.load_training_data()
+        self.graph = CISGraph(cfg.img_height, cfg.img_width, self.local_batch, device=self.device, flow_normalizer=cfg.flow_normalizer,
+                              with_pwc=True, train=False)
+        self.test_samples = self.reader.val_samples
+        self.test_iterator = self.reader
+
+    def setup_inference(self, config, aug_test=False):
+        """adversarial_learner.py:594-604."""
+        self.config = config
+        self.aug_test = aug_test
+        if self.aug_test:
+            self.build_aug_test_graph()
+        else:
+            self.build_test_graph()
+
+    def restore(self, ckpt_file):
+        """test_generator.py:45-58: restores ALL trainables (incl. PWC-Net) from one checkpoint."""
+        if ckpt_file.startswith('synthetic'):
+            p = {}
+            p.update(params_init.init_generator())
+            p.update(params_init.init_recover())
+            p.update(params_init.init_pwcnet(self.graph.pwc_store.entries))
+        elif ckpt_file and os.path.isfile(ckpt_file):
+            st = torch.load(ckpt_file, map_location='cpu')
+            p = st.get('params', st)
+        else:
+            raise IOError("Checkpoint file not found")                         # test_generator.py:58
+        self.graph.load_params(p)
+
+    def inference(self, sess=None, batch=None):
+        """adversarial_learner.py:606-623 -> dict with the reference's keys (numpy arrays)."""
+        g = self.graph
+        if batch is None:
+            batch = self.reader.batch(self.local_batch)
+        img1, img2, gt, names = batch
+        if self.aug_test:
+            # crops [0.85,0.9,0.95,1.0] of ONE frame pair, each resized back to 384x640 (davis2016_data_utils.py:328-354)
+            from ..data.crops import central_crops
+            img1, img2, gt = central_crops(img1[:1], img2[:1], gt[:1], self.test_crops)
+        self.feed(img1, img2)
+        g.forward()
+        H, W = g.H, g.W
+        gtr = torch.nn.functional.interpolate(gt.permute(0, 3, 1, 2), size=(H, W), mode='nearest').permute(0, 2, 3, 1).numpy()
+        masks = g.mask.cpu().numpy()
+        if self.aug_test:
+            outs = {'pred_masks': {}, 'gt_masks': {}, 'img_1s': {}}
+            image = g.image.cpu().numpy()
+            for i, c in enumerate(self.test_crops):
+                outs['pred_masks'][c], outs['gt_masks'][c], outs['img_1s'][c] = masks[i], gtr[i], image[i]
+            return {'outs': outs, 'img_fname': np.array(names[0].encode())}
+        return {'gen_masks': masks, 'pred_flow': g.pred[:g.B].cpu().numpy(), 'input_image': g.image.cpu().numpy(),
+                'gt_flow': g.flow.cpu().numpy(), 'gt_masks': gtr, 'img_fname': np.array([n.encode() for n in names])}

@@ -1,0 +1,227 @@
+"""bench.py - frame-pairs/sec of the adversarial train step at 256x448 (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]/[2]): DAVIS2016-shaped adversarial training, 4 frame pairs per GPU, PWC-Net at 384x640
+in the loop, generator + inpainter alternating 1 recover : 3 generator steps (common_flags.py:19-21), synthetic frames and
+seeded random-init weights of the reference architecture.  One "step" = one alternating train step on one batch.
+`value`: steps with the batch already resident in HBM.  `e2e`: the same steps through AdversarialLearner.step() fed from
+pinned host memory (H2D inside the timed region) with a D2H read of the losses every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'frame-pairs/sec adversarial train step 256x448'
+H, W, BPG = 256, 448, 4
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows for n, v in zip(names, r[3:7]) if v.lower().startswith('active')})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference(steps, warmup, batch=1, threads=None):
+    """The reference graph restated on torch-CPU (oracle/; the genuine TF1.13 path is not installable here), all host
+    threads, identical step schedule (PWC-Net fwd @384x640 -> resize -> generator -> 3x recover -> losses -> backward -> clip
+    -> TF-Adam) on a bounded sample: `batch` frame pair(s) per step."""
+    from oracle import params as OP, losses as OL
+    from unsupervised_detection_b200.data.synthetic import SyntheticReader
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    p = OP.make_params(seed=8964)
+    opt = OL.TFAdam()
+    rd = SyntheticReader(384, 640, seed=8964)
+    img1, img2, _, _ = rd.batch(batch, pinned=False)
+    cfg = dict(batch_size=batch)
+    times = []
+    for s in range(1, warmup + steps + 1):
+        t0 = time.time()
+        OL.train_step(p, opt, s, img1, img2, H, W, cfg)
+        if s > warmup:
+            times.append(time.time() - t0)
+    tot = sum(times)
+    return batch * len(times) / tot, threads, tot / len(times) * 1e3
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 4)), min(args.warmup, 1)
+    v, threads, ms = cpu_reference(steps, warmup)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'frame-pairs/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'adversarial train step 256x448, PWC-Net 384x640 in loop, 1 rec : 3 gen', 'global_batch': 1,
+                       'note': 'CPU restatement of the reference graph (TF1.13 not installable); bounded sample: 1 frame pair per step'},
+            'cpu_baseline': {'value': v, 'unit': 'frame-pairs/s', 'cores': threads, 'kind': 'port',
+                             'sample': '%d step(s) x 1 frame pair, schedule starting at step %d' % (steps, warmup + 1)},
+            'e2e': {'value': v, 'unit': 'frame-pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------- our arm
+def conv_roofline(graph, reps=5):
+    """Dominant kernel = the tcgen05 implicit-GEMM conv (cis_conv_igemm): algorithmic FLOPs of every conv launch of one
+    1R:3G cycle / CUDA-event time of those launches replayed back to back on the launching stream."""
+    import ctypes
+    st = torch.cuda.current_stream()
+    total_fl, total_ms, n = 0.0, 0.0, 0
+    for plan, weight in ((graph.fwd, 4), (graph.bwd['R'], 1), (graph.bwd['G'], 3)):
+        ops = [(fn, a) for fn, a, name, _ in plan.ops if name == 'cis_conv_igemm']
+        fl = sum(f for _, _, name, f in plan.ops if name == 'cis_conv_igemm')   # algorithmic 2*MACs on real channels
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for fn, a in ops:
+            fn(*a, st.cuda_stream)
+        torch.cuda.synchronize()
+        e0.record(st)
+        for _ in range(reps):
+            for fn, a in ops:
+                fn(*a, st.cuda_stream)
+        e1.record(st)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        total_fl += weight * fl
+        total_ms += weight * ms
+        n += weight * len(ops)
+    return total_fl / 4, total_ms / 4, n / 4.0
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from unsupervised_detection_b200.common_flags import Config
+    from unsupervised_detection_b200.models.adversarial_learner import AdversarialLearner
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    cfg = Config(img_height=H, img_width=W, batch_size=BPG * world, dataset='SYNTHETIC', flow_ckpt='synthetic', summary_freq=10 ** 9)
+    L = AdversarialLearner()
+    L.config = cfg
+    L.build_train_graph()
+    rank, dev = L.rank, L.device
+    g = L.graph
+    pool = [L.reader.batch(BPG) for _ in range(2)]
+    K, Wm = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    # ---- device-resident arm
+    L.feed(pool[0][0], pool[0][1])
+    cnt = [0]
+
+    def dev_step(_):
+        cnt[0] += 1
+        g.train_step('R' if (cnt[0] % (cfg.iters_rec + cfg.iters_gen)) < cfg.iters_rec else 'G', allreduce=ar, use_graph=True)
+    ar = L._allreduce()
+    for i in range(Wm):
+        dev_step(i)
+    smp = ClockSampler(L.local_rank)
+    smp.start()
+    ms_dev = timed(dev_step, K)
+    # ---- end-to-end arm through the public API: pinned host batch -> H2D -> step -> D2H losses
+    for i in range(Wm):
+        L.step(pool[i % 2], fetch_losses=True)
+    ms_e2e = timed(lambda i: L.step(pool[i % 2], fetch_losses=True), K)
+    smp.stop_flag = True
+    smp.join(timeout=2)
+    gb = BPG * world
+    value = gb * K / (ms_dev / 1e3)
+    e2e = gb * K / (ms_e2e / 1e3)
+    launches = sum(g.launches_per_step('R' if (i % 4) == 3 else 'G') for i in range(K))
+    if rank != 0:
+        return
+    pk, src = peaks()
+    fl, ms_conv, nconv = conv_roofline(g)
+    ach = fl / (ms_conv * 1e-3) / 1e12
+    try:
+        cv, cores, cms = cpu_reference(2, 0) if not args.no_cpu else (None, 0, 0)
+    except Exception as e:  # the CPU leg must never take the GPU number down
+        cv, cores, cms = None, 0, 0
+    line = {'metric': METRIC, 'value': value, 'unit': 'frame-pairs/s', 'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': ms_dev / K,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+            'config': {'workload': 'DAVIS2016-shaped adversarial train 256x448, batch 4/GPU, PWC-Net 384x640 in loop, 1 rec : 3 gen (configs[1])',
+                       'global_batch': gb, 'parallelism': 'dp%d' % world, 'l2': 'per-step working set (activations) exceeds the 126 MB L2',
+                       'cuda_graph': True},
+            'e2e': {'value': e2e, 'unit': 'frame-pairs/s', 'h2d_bytes_per_step': 2 * BPG * 384 * 640 * 3 * 4, 'd2h_bytes_per_step': 32,
+                    'ms_per_step': ms_e2e / K},
+            'gpu_launches': launches,
+            'clocks': smp.summary(),
+            'roofline': {'bound': 'tensor', 'kernel': 'cis::conv_igemm_kernel (all conv launches of a 1R:3G cycle, per step)',
+                         'achieved': ach, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s', 'frac': ach / pk['bf16_tflops_sustained'],
+                         'peak_source': src + ' bf16_tflops_sustained', 'traffic': None, 'algorithmic_gflop_per_step': fl / 1e9,
+                         'conv_ms_per_step': ms_conv, 'conv_launches_per_step': nconv},
+            'cpu_baseline': {'value': cv, 'unit': 'frame-pairs/s', 'cores': cores, 'kind': 'port',
+                             'sample': '2 steps (generator, generator) x 1 frame pair of the same workload, %.0f ms/step' % cms}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=4)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

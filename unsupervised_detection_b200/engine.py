@@ -31,19 +31,19 @@ class Plan(object):
         self.ops = []
         self.keep = []  # ctypes structs / tensors that must outlive the plan
 
-    def add(self, fname, *args):
+    def add(self, fname, *args, flops=0.0):
         fn = getattr(_lib.load(), fname)
-        self.ops.append((fn, args, fname))
+        self.ops.append((fn, args, fname, flops))
 
     def add_py(self, fn, label='py'):
-        self.ops.append((None, fn, label))
+        self.ops.append((None, fn, label, 0.0))
 
     def zero(self, t):
         self.add_py(t.zero_, 'zero')
 
     def run(self, stream=None):
         st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
-        for fn, args, name in self.ops:
+        for fn, args, name, _ in self.ops:
             if fn is None:
                 args()
             else:
@@ -52,7 +52,7 @@ class Plan(object):
                     _lib.check(rc, name)
 
     def count(self):
-        return sum(1 for fn, _, _ in self.ops if fn is not None)
+        return sum(1 for op in self.ops if op[0] is not None)
 
     def extend(self, other):
         self.ops += other.ops
@@ -419,7 +419,7 @@ class Builder(object):
         d.mode = mode
         plan.keep.append(d)
         plan.keep += [srcs, out, outf, addf, post_add, layer]
-        plan.add('cis_conv_igemm', C.byref(d))
+        plan.add('cis_conv_igemm', C.byref(d), flops=2.0 * N * OH * OW * layer.k * layer.k * layer.cin * layer.cout)
         if layer.tag:
             self.tape.append(lambda bp, m, L=layer, S=list(srcs), O=out, P=post_add: self._conv_bwd(bp, m, L, S, O, P))
         return out
@@ -455,7 +455,7 @@ class Builder(object):
             ntile = -(-layer.K_pad // 128)
             w.splits = max(1, min(nkb // 4 if nkb >= 4 else 1, max(1, (2 * 148) // ntile)))
             bp.keep.append(w)
-            bp.add('cis_conv_wgrad', C.byref(w))
+            bp.add('cis_conv_wgrad', C.byref(w), flops=2.0 * npix * layer.k * layer.k * layer.cin * layer.cout)
             layer.wgrad_modes = getattr(layer, 'wgrad_modes', set()) | {mode}
             bp.add('cis_colsum', G.ptr, G.pitch, G.c_off, npix, layer.cout,
                    (layer.db_eff.data_ptr() if layer.bn else layer.store.ptr(layer.bkey, 'grad')))
@@ -491,7 +491,7 @@ class Builder(object):
             if acc:
                 d.add_pre, d.add_pre_pitch, d.add_pre_coff = tgt.ptr, tgt.pitch, tgt.c_off
             bp.keep.append(d)
-            bp.add('cis_conv_igemm', C.byref(d))
+            bp.add('cis_conv_igemm', C.byref(d), flops=2.0 * nb * oh * ow * len(pk['taps']) * layer.cin * layer.cout)
         if single:
             srcs[0].grad_written[mode] = True
         else:
@@ -530,7 +530,7 @@ class Builder(object):
                 d.outf, d.outf_pitch, d.outf_coff, d.outf_ch = outf.data_ptr(), outf.shape[-1], 0, layer.cout
             plan.keep.append(d)
             plan.keep += [src, out, outf, layer]
-            plan.add('cis_conv_igemm', C.byref(d))
+            plan.add('cis_conv_igemm', C.byref(d), flops=2.0 * N * H * W * len(pk['taps']) * layer.cin * layer.cout)
         return out
 
     # ---- resampling ops

@@ -1,0 +1,92 @@
+"""The reference-facing surface on the GPU: AdversarialLearner.step()/inference() through host buffers, and
+size-independent properties at BASELINE's full size (256x448, batch 4)."""
+import numpy as np
+import pytest
+import torch
+
+from unsupervised_detection_b200.common_flags import Config
+from unsupervised_detection_b200.models.adversarial_learner import AdversarialLearner
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def learner():
+    L = AdversarialLearner()
+    L.config = Config(img_height=256, img_width=448, batch_size=4, dataset='SYNTHETIC', flow_ckpt='synthetic', summary_freq=2)
+    L.build_train_graph()
+    return L
+
+
+def test_flow_ckpt_is_mandatory():
+    L = AdversarialLearner()
+    L.config = Config(img_height=64, img_width=64, batch_size=1, dataset='SYNTHETIC', flow_ckpt='')
+    with pytest.raises(IOError):
+        L.build_train_graph()                       # adversarial_learner.py:343
+
+
+def test_step_api_full_size(learner):
+    L = learner
+    assert L.graph.param_count() == 18918722       # "Number of params" (adversarial_learner.py:338)
+    batch = L.reader.batch(4)
+    outs = [L.step(batch) for _ in range(4)]
+    assert [o['train_op'] for o in outs] == ['G', 'G', 'G', 'R']
+    assert outs[-1]['global_step'] == 1
+    assert 'loss_recover' in outs[1] and np.isfinite(outs[1]['loss_recover']) and np.isfinite(outs[1]['loss_generator'])
+    m = L.graph.mask
+    assert float(m.min()) > 0.0 and float(m.max()) < 1.0 and torch.isfinite(m).all()
+    assert all(torch.isfinite(v).all() for v in L.graph.export_params().values())
+
+
+def test_forward_is_deterministic_and_batch_independent(learner):
+    """Samples are independent in the forward (per-sample flow normalisation, BN without batch statistics): swapping two
+    samples of the batch swaps their masks bit-exactly; repeated runs are bit-identical."""
+    L = learner
+    g = L.graph
+    b = L.reader.batch(4)
+    L.feed(b[0], b[1])
+    g.forward()
+    m1 = g.mask.clone()
+    g.forward()
+    assert torch.equal(m1, g.mask)
+    perm = [1, 0, 2, 3]
+    L.feed(b[0][perm], b[1][perm])
+    g.forward()
+    assert torch.equal(m1[perm], g.mask)
+
+
+def test_data_parallel_split_equals_full_batch(learner):
+    """local-mean gradients of the batch halves summed == global-batch gradient (emulated on one GPU by running
+    the two halves through a batch-2 graph with global_batch=4)."""
+    from unsupervised_detection_b200.step_graph import CISGraph
+    L = learner
+    g4 = L.graph
+    b = L.reader.batch(4)
+    L.feed(b[0], b[1])
+    g4.forward()
+    g4.bwd['R'].run()
+    full = g4.rec_store.grad.clone()
+    g2 = CISGraph(256, 448, 2, global_batch=4)
+    g2.load_params({k: v for k, v in g4.export_params().items()})
+    acc = torch.zeros_like(g2.rec_store.grad)
+    for h in range(2):
+        g2.img1.copy_(b[0][2 * h:2 * h + 2])
+        g2.img2.copy_(b[1][2 * h:2 * h + 2])
+        g2.forward()
+        g2.bwd['R'].run()
+        acc += g2.rec_store.grad
+    torch.cuda.synchronize()
+    cos = float(torch.dot(acc, full) / (acc.norm() * full.norm()))
+    assert cos > 0.9999 and abs(float(acc.norm() / full.norm()) - 1) < 1e-3
+
+
+def test_inference_keys(learner):
+    L = AdversarialLearner()
+    L.setup_inference(Config(img_height=128, img_width=224, batch_size=1, dataset='SYNTHETIC'), aug_test=False)
+    L.restore('synthetic')
+    r = L.inference(None)
+    assert set(r) == {'gen_masks', 'pred_flow', 'input_image', 'gt_flow', 'gt_masks', 'img_fname'}    # adversarial_learner.py:617-619
+    assert r['gen_masks'].shape == (1, 128, 224, 1) and r['pred_flow'].shape == (1, 128, 224, 2)
+    from unsupervised_detection_b200.models.utils.general_utils import compute_IoU
+    iou, ann = compute_IoU(r['gt_masks'][0], r['gen_masks'][0])
+    assert 0.0 <= iou <= 1.0

@@ -34,7 +34,7 @@ def test_conv_engine(case):
     assert r['fwd_err'] <= tol(r['fwd_ref']), r
     if 'dx_err' in r:
         assert r['dx_err'] <= tol(r['dx_ref']), r
-        assert r['dw_err'] <= 2 ** -9 * r['dw_ref'] + 1e-3, r
-        assert r['db_err'] <= 2 ** -9 * r['db_ref'] + 1e-3, r
+        assert r['dw_err'] <= 2 ** -7 * r['dw_ref'] + 1e-3, r   # g*act' is stored in bf16 before the wgrad GEMM
+        assert r['db_err'] <= 2 ** -7 * r['db_ref'] + 1e-3, r
     if 'dgamma_err' in r:
         assert r['dgamma_err'] <= 2 ** -6 * r['dgamma_ref'] + 1e-2, r

@@ -66,6 +66,14 @@ typedef struct {
   const void* add_post; /* bf16, added after the activation (generator skips, nets.py:29,32,33) */
   int32_t add_post_pitch, add_post_coff;
   int32_t mode;      /* 0 normal; 1: outf[pix] = sigmoid((l0 - l1)/10)  (nets.py:38-41) */
+  /* halo-resident variant (stride-1 gathers only): the CTA tile is MT stacked 16x8-pixel blocks of dilation phase (a,b);
+   * the (16*MT+ey) x (8+ex) input halo of a 64-channel chunk is staged ONCE in shared memory and all taps read it through
+   * shifted UMMA descriptors.  dh/dw then hold tap offsets >= 0 relative to the halo origin, in units of `dil` pixels. */
+  int32_t halo;      /* 0: generic per-tap gather kernel, 1: halo-resident kernel */
+  int32_t dil;       /* dilation = phase period (1 for undilated) */
+  int32_t MT;        /* 1..4 stacked M tiles (MT*BN <= 512 TMEM columns) */
+  int32_t hoy, hox;  /* halo origin relative to the tile origin (phase units, <= 0) */
+  int32_t ey, ex;    /* halo extent beyond the tile (max tap offset) */
 } CisConv;
 
 /* Weight gradient of the same convolution: dWp[co][(t,c)] += sum_rows g[row][co] * A[row][(t,c)]  (fp32, split-K atomics).

@@ -24,6 +24,14 @@ CASES = [
     dict(N=1, H=12, W=20, cins=[16], cout=32, k=5, stride=2, act=ACT_LEAKY),
     dict(N=2, H=6, W=10, cins=[196], cout=196, k=3, act=ACT_LEAKY, alpha=0.1, backward=False),
     dict(N=1, H=20, W=20, cins=[16], cout=2, k=3),
+    # larger maps: exercise the halo-resident kernel with several stacked M tiles, ragged tiles and dilation phases
+    dict(N=2, H=70, W=44, cins=[128], cout=128, k=3, act=ACT_ELU, bn=True),
+    dict(N=4, H=96, W=160, cins=[64, 40], cout=128, k=3, act=ACT_LEAKY, alpha=0.1, backward=False),
+    dict(N=1, H=50, W=36, cins=[128], cout=128, k=3, dil=2, act=ACT_ELU, bn=True),
+    dict(N=1, H=64, W=112, cins=[128], cout=96, k=3, dil=8, act=ACT_LEAKY, backward=False),
+    dict(N=3, H=40, W=56, cins=[16, 16, 16, 2], cout=2, k=5),
+    dict(N=3, H=33, W=57, cins=[32, 32, 32, 2], cout=16, k=4, act=ACT_LEAKY),
+    dict(N=2, H=40, W=48, cins=[5], cout=32, k=5, act=ACT_ELU, bn=True),
 ]
 
 

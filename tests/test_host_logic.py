@@ -39,7 +39,23 @@ def test_cabi_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert sorted(declared) == sorted(_lib.EXPORTS)
     assert lib.cis_version() >= 100
-    assert C.sizeof(_lib.CisConv) == 496 and C.sizeof(_lib.CisWgrad) == 376   # must match the C structs (gcc-checked at build)
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    import shutil
+    import subprocess
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    src = tmp_path / 'sz.c'
+    src.write_text('#include "%s"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%%zu %%zu %%zu %%zu %%zu %%zu\\n", sizeof(CisConv), '
+                   'sizeof(CisWgrad), offsetof(CisConv, src), offsetof(CisConv, mode), offsetof(CisConv, ex), offsetof(CisWgrad, splits));return 0;}\n'
+                   % os.path.join(ROOT, 'include', 'cis_b200.h'))
+    exe = tmp_path / 'sz'
+    subprocess.check_call(['gcc', str(src), '-o', str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    exp = [C.sizeof(_lib.CisConv), C.sizeof(_lib.CisWgrad), _lib.CisConv.src.offset, _lib.CisConv.mode.offset, _lib.CisConv.ex.offset,
+           _lib.CisWgrad.splits.offset]
+    assert got == exp
 
 
 def test_bad_descriptor_is_rejected_without_a_gpu():

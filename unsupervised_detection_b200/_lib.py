@@ -29,7 +29,9 @@ class CisConv(C.Structure):
                 ('add_pre', C.c_void_p), ('add_pre_pitch', C.c_int32), ('add_pre_coff', C.c_int32),
                 ('addf_pre', C.c_void_p), ('addf_pitch', C.c_int32), ('addf_coff', C.c_int32),
                 ('add_post', C.c_void_p), ('add_post_pitch', C.c_int32), ('add_post_coff', C.c_int32),
-                ('mode', C.c_int32)]
+                ('mode', C.c_int32),
+                ('halo', C.c_int32), ('dil', C.c_int32), ('MT', C.c_int32), ('hoy', C.c_int32), ('hox', C.c_int32),
+                ('ey', C.c_int32), ('ex', C.c_int32)]
 
 
 class CisWgrad(C.Structure):

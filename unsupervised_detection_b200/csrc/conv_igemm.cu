@@ -28,6 +28,74 @@ struct SrcS {
   int pitch, c_off, chunks, n_mod;
 };
 
+
+// One 16-column chunk of the fused epilogue: bias -> (+bf16 accumulate | +fp32 residual) -> activation -> (+skip) -> stores.
+__device__ __forceinline__ void epi_chunk(const CisConv& p, float (&v)[16], const int cg, const size_t dpix) {
+  if (p.bias) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] += __ldg(p.bias + cg + e);
+  }
+  if (p.add_pre && cg < p.out_ch) {
+    const uint4* a = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.add_pre) + dpix * p.add_pre_pitch +
+                                                    p.add_pre_coff + cg);
+    const int nv = (p.out_ch - cg >= 16) ? 2 : 1;
+    for (int h2 = 0; h2 < nv; ++h2) {
+      const uint4 u = __ldg(a + h2);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[h2 * 8 + 2 * e] += bf16lo(w4[e]);
+        v[h2 * 8 + 2 * e + 1] += bf16hi(w4[e]);
+      }
+    }
+  }
+  if (p.addf_pre) {
+    for (int e = 0; e < 16 && cg + e < p.outf_ch; ++e) v[e] += __ldg(p.addf_pre + dpix * p.addf_pitch + p.addf_coff + cg + e);
+  }
+  if (p.act == CIS_ACT_ELU) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.f ? v[e] : expm1f(v[e]);
+  } else if (p.act == CIS_ACT_LEAKY) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * p.alpha;
+  }
+  if (p.add_post && cg < p.out_ch) {
+    const uint4* a = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.add_post) + dpix * p.add_post_pitch +
+                                                    p.add_post_coff + cg);
+    const int nv = (p.out_ch - cg >= 16) ? 2 : 1;
+    for (int h2 = 0; h2 < nv; ++h2) {
+      const uint4 u = __ldg(a + h2);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[h2 * 8 + 2 * e] += bf16lo(w4[e]);
+        v[h2 * 8 + 2 * e + 1] += bf16hi(w4[e]);
+      }
+    }
+  }
+  if (p.mode == 1) {
+    if (cg == 0) p.outf[dpix] = 1.f / (1.f + __expf(-(v[0] - v[1]) * 0.1f));
+    return;
+  }
+  if (p.out && cg < p.out_ch) {
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + dpix * p.out_pitch + p.out_coff + cg;
+    if (((p.out_ch | p.out_coff | p.out_pitch) & 7) == 0) {
+      uint4 u0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+      *reinterpret_cast<uint4*>(o) = u0;
+      if (p.out_ch - cg >= 16) {
+        uint4 u1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+        *reinterpret_cast<uint4*>(o + 8) = u1;
+      }
+    } else {
+      for (int e = 0; e < 16 && cg + e < p.out_ch; ++e) o[e] = __float2bfloat16(v[e]);
+    }
+  }
+  if (p.outf && cg < p.outf_ch) {
+    float* o = p.outf + dpix * p.outf_pitch + p.outf_coff + cg;
+    for (int e = 0; e < 16 && cg + e < p.outf_ch; ++e) o[e] = v[e];
+  }
+}
+
 template <int BN>
 struct FwdCfg {
   static constexpr int kStages = (BN == 128) ? 3 : 4;
@@ -184,70 +252,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
       float v[16];
       tmem_ld16(t_row + c0, v);
       if (!valid) continue;
-      const int cg = cbase + c0;  // global output channel of v[0]
-      if (p.bias) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] += __ldg(p.bias + cg + e);
-      }
-      if (p.add_pre && cg < p.out_ch) {
-        const uint4* a = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.add_pre) +
-                                                        dpix * p.add_pre_pitch + p.add_pre_coff + cg);
-        const int nv = (p.out_ch - cg >= 16) ? 2 : 1;
-        for (int h2 = 0; h2 < nv; ++h2) {
-          const uint4 u = __ldg(a + h2);
-          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            v[h2 * 8 + 2 * e] += bf16lo(w4[e]);
-            v[h2 * 8 + 2 * e + 1] += bf16hi(w4[e]);
-          }
-        }
-      }
-      if (p.addf_pre) {
-        for (int e = 0; e < 16 && cg + e < p.outf_ch; ++e) v[e] += __ldg(p.addf_pre + dpix * p.addf_pitch + p.addf_coff + cg + e);
-      }
-      if (p.act == CIS_ACT_ELU) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.f ? v[e] : expm1f(v[e]);
-      } else if (p.act == CIS_ACT_LEAKY) {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * p.alpha;
-      }
-      if (p.add_post && cg < p.out_ch) {
-        const uint4* a = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.add_post) +
-                                                        dpix * p.add_post_pitch + p.add_post_coff + cg);
-        const int nv = (p.out_ch - cg >= 16) ? 2 : 1;
-        for (int h2 = 0; h2 < nv; ++h2) {
-          const uint4 u = __ldg(a + h2);
-          const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            v[h2 * 8 + 2 * e] += bf16lo(w4[e]);
-            v[h2 * 8 + 2 * e + 1] += bf16hi(w4[e]);
-          }
-        }
-      }
-      if (p.mode == 1) {
-        if (cg == 0) p.outf[dpix] = 1.f / (1.f + __expf(-(v[0] - v[1]) * 0.1f));
-        continue;
-      }
-      if (p.out && cg < p.out_ch) {
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + dpix * p.out_pitch + p.out_coff + cg;
-        if (((p.out_ch | p.out_coff | p.out_pitch) & 7) == 0) {
-          uint4 u0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-          *reinterpret_cast<uint4*>(o) = u0;
-          if (p.out_ch - cg >= 16) {
-            uint4 u1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-            *reinterpret_cast<uint4*>(o + 8) = u1;
-          }
-        } else {
-          for (int e = 0; e < 16 && cg + e < p.out_ch; ++e) o[e] = __float2bfloat16(v[e]);
-        }
-      }
-      if (p.outf && cg < p.outf_ch) {
-        float* o = p.outf + dpix * p.outf_pitch + p.outf_coff + cg;
-        for (int e = 0; e < 16 && cg + e < p.outf_ch; ++e) o[e] = v[e];
-      }
+      epi_chunk(p, v, cbase + c0, dpix);
     }
   } else {
     // ------------------------------------------------------------------ MMA issuer (warp 4)
@@ -275,6 +280,217 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   if (warp == 4) tmem_dealloc<Cfg::kTmemCols>(tmem);
+}
+
+
+// ======================================================================================================= halo-resident conv
+// Stride-1 gathers (forward convs incl. dilated ones, stride-1 data gradients, parity launches of stride-2 data gradients and
+// of the 4x4 s2 transposed convs).  The CTA owns MT stacked tiles of 16x8 output pixels of one dilation phase; per 64-channel
+// chunk the (16*MT+ey) x (8+ex) input halo is copied ONCE into shared memory (SWIZZLE_128B rows of 128 B = one pixel x 64 ch)
+// and every tap (dy,dx) reads it in place: A descriptor start = halo + ((16*m+dy)*Wh + dx)*128, SBO = Wh*128.  The hardware
+// applies the 128B swizzle on absolute shared-memory address bits (tools/umma_probe.cu), so 128-byte-granular starts and a
+// non-1024 SBO are legal with base_offset = 0.  im2col traffic drops from k*k x to ~1.3 x and the packed weights of a
+// (tap, chunk) are reused by the MT tiles.
+static constexpr int kHaloBStages = 3;
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_constant__ CisConv p, const int halo_stage_bytes) {
+  constexpr int BS = kHaloBStages;
+  constexpr int kBStage = BN * 128;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[2 * 2 + 2 * BS + 1];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_dh[CIS_MAX_TAPS], s_dw[CIS_MAX_TAPS];
+  __shared__ SrcS s_src[CIS_MAX_SRC];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int MT = p.MT, d = p.dil;
+  const int Wh = 8 + p.ex, Hh = 16 * MT + p.ey, HP = Wh * Hh;
+  const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t h_base = tile_base;                                // 2 halo stages
+  const uint32_t b_base = tile_base + 2 * halo_stage_bytes;         // BS weight stages
+  int* pixtab = reinterpret_cast<int*>(smem_raw + (b_base + BS * kBStage - smem_u32(smem_raw)));
+  const uint32_t bar_hfull = smem_u32(&bars[0]), bar_hempty = smem_u32(&bars[2]);
+  const uint32_t bar_bfull = smem_u32(&bars[4]), bar_bempty = smem_u32(&bars[4 + BS]);
+  const uint32_t bar_accum = smem_u32(&bars[4 + 2 * BS]);
+
+  // ---- tile decode: blockIdx.x -> (tx, ty, phase, n)
+  const int Hp0 = (p.OH + d - 1) / d, Wp0 = (p.OW + d - 1) / d;
+  const int tiles_x = (Wp0 + 7) / 8, tiles_y = (Hp0 + 16 * MT - 1) / (16 * MT);
+  int bid = blockIdx.x;
+  const int tx = bid % tiles_x; bid /= tiles_x;
+  const int ty = bid % tiles_y; bid /= tiles_y;
+  const int ph = bid % (d * d);
+  const int n = bid / (d * d);
+  const int pa = ph / d, pb = ph % d;
+  const int ny = blockIdx.y;
+  int m_chunks = 0;
+  for (int i = 0; i < p.nsrc; ++i) m_chunks += p.src[i].chunks;
+  const int nchunks = (m_chunks + 7) / 8;  // 64-channel chunks
+  const int cin8 = m_chunks * 8;
+  const uint32_t ncols = (MT * BN <= 32) ? 32u : (MT * BN <= 64) ? 64u : (MT * BN <= 128) ? 128u : (MT * BN <= 256) ? 256u : 512u;
+
+  if (tid < p.ntaps) {
+    s_dh[tid] = p.dh[tid];
+    s_dw[tid] = p.dw[tid];
+  }
+  if (tid < p.nsrc) {
+    s_src[tid].ptr = reinterpret_cast<const __nv_bfloat16*>(p.src[tid].ptr);
+    s_src[tid].pitch = p.src[tid].pitch;
+    s_src[tid].c_off = p.src[tid].c_off;
+    s_src[tid].chunks = p.src[tid].chunks;
+    s_src[tid].n_mod = p.src[tid].n_mod;
+  }
+  for (int q = tid; q < HP; q += kThreads) {
+    const int hy = q / Wh, hx = q - hy * Wh;
+    const int gy = ty * 16 * MT + hy + p.hoy, gx = tx * 8 + hx + p.hox;
+    const int y = pa + d * gy, x = pb + d * gx;
+    pixtab[q] = (gy >= 0 && gx >= 0 && y < p.H && x < p.W) ? (y * p.W + x) : -1;
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(bar_hfull + 8 * s, kProducerThreads);
+        mbar_init(bar_hempty + 8 * s, 1);
+      }
+      for (int s = 0; s < BS; ++s) {
+        mbar_init(bar_bfull + 8 * s, kProducerThreads);
+        mbar_init(bar_bempty + 8 * s, 1);
+      }
+      mbar_init(bar_accum, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_dyn(smem_u32(&tmem_slot), ncols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers
+    const int j = tid & 7, pl = tid >> 3;
+    // cp.async groups complete in order; a group's "full" arrival is issued two commits later (kLag = 2 in flight), which is
+    // deadlock-free because every wait-for-empty below depends only on groups that are >= 2 commits old (BS = 3 stages).
+    uint32_t pend0 = 0, pend1 = 0;
+    int npend = 0;
+    auto push = [&](uint32_t bar) {
+      cp_async_commit();
+      if (npend == 2) {
+        cp_async_wait<2>();
+        fence_proxy_async();
+        mbar_arrive(pend0);
+        pend0 = pend1;
+        pend1 = bar;
+      } else {
+        if (npend == 0) pend0 = bar; else pend1 = bar;
+        ++npend;
+      }
+    };
+    const __nv_bfloat16* wbase = reinterpret_cast<const __nv_bfloat16*>(p.wpack) + (size_t)(ny * BN + pl) * p.K_pad + j * 8;
+    int it = 0;
+    for (int cc = 0; cc < nchunks; ++cc) {
+      const int hs = cc & 1;
+      mbar_wait(bar_hempty + 8 * hs, (uint32_t)(((cc >> 1) & 1) ^ 1));
+      const int rem = m_chunks - cc * 8;                 // valid 16-byte chunks in this 64-channel chunk
+      const int nk16 = rem >= 8 ? 4 : (rem + 1) / 2;     // K=16 MMA groups actually issued
+      const bool need = j < 2 * nk16;
+      const bool cvalid = j < rem;
+      int c = cc * 8 + j, si = 0;
+      if (cvalid) {
+        while (si < p.nsrc - 1 && c >= s_src[si].chunks) {
+          c -= s_src[si].chunks;
+          ++si;
+        }
+      } else {
+        c = 0;
+      }
+      const int nmod = s_src[si].n_mod, pitch = s_src[si].pitch;
+      const int ne = nmod ? (n % nmod) : n;
+      const __nv_bfloat16* sp = s_src[si].ptr;
+      const __nv_bfloat16* sb = sp + (size_t)ne * p.H * p.W * pitch + s_src[si].c_off + c * 8;
+      if (need) {
+        const uint32_t hdst = h_base + hs * halo_stage_bytes;
+        for (int q = pl; q < HP; q += 16) {
+          const int off = pixtab[q];
+          const bool ok = cvalid && off >= 0;
+          cp_async16(hdst + q * 128 + ((j ^ (q & 7)) << 4), ok ? (const void*)(sb + (size_t)off * pitch) : (const void*)sp, ok ? 16u : 0u);
+        }
+      }
+      push(bar_hfull + 8 * hs);
+      for (int t = 0; t < p.ntaps; ++t, ++it) {
+        const int bs = it % BS;
+        mbar_wait(bar_bempty + 8 * bs, (uint32_t)(((it / BS) & 1) ^ 1));
+        if (need) {
+          const uint32_t bdst = b_base + bs * kBStage + pl * 128 + ((j ^ (pl & 7)) << 4);
+          const __nv_bfloat16* wsrc = wbase + (size_t)t * cin8 + cc * 64;
+#pragma unroll
+          for (int i = 0; i < BN / 16; ++i) cp_async16(bdst + i * 16 * 128, wsrc + (size_t)i * 16 * p.K_pad, 16u);
+        }
+        push(bar_bfull + 8 * bs);
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    if (npend > 0) mbar_arrive(pend0);
+    if (npend > 1) mbar_arrive(pend1);
+
+    // ------------------------------------------------------------------ epilogue
+    mbar_wait(bar_accum, 0);
+    tc_fence_after();
+    const int r = warp * 32 + lane;
+    const int cbase = ny * BN;
+    for (int m = 0; m < MT; ++m) {
+      const int gy = ty * 16 * MT + 16 * m + (r >> 3), gx = tx * 8 + (r & 7);
+      const int oy = pa + d * gy, ox = pb + d * gx;
+      const bool valid = oy < p.OH && ox < p.OW;
+      const size_t dpix = valid ? ((size_t)(n * p.DH + oy * p.osh + p.oa) * p.DW + ox * p.osw + p.ob) : 0;
+      const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16) + m * BN;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        float v[16];
+        tmem_ld16(t_row + c0, v);
+        if (!valid) continue;
+        epi_chunk(p, v, cbase + c0, dpix);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+    int it = 0;
+    for (int cc = 0; cc < nchunks; ++cc) {
+      const int hs = cc & 1;
+      const int rem = m_chunks - cc * 8;
+      const int nk16 = rem >= 8 ? 4 : (rem + 1) / 2;
+      mbar_wait(bar_hfull + 8 * hs, (uint32_t)((cc >> 1) & 1));
+      const uint32_t hsrc = h_base + hs * halo_stage_bytes;
+      for (int t = 0; t < p.ntaps; ++t, ++it) {
+        const int bs = it % BS;
+        mbar_wait(bar_bfull + 8 * bs, (uint32_t)((it / BS) & 1));
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t b_addr = b_base + bs * kBStage;
+          const uint32_t tap_off = (uint32_t)((s_dh[t] * Wh + s_dw[t]) * 128);
+          for (int m = 0; m < MT; ++m) {
+            const uint32_t a_addr = hsrc + (uint32_t)(16 * m * Wh * 128) + tap_off;
+            for (int k = 0; k < nk16; ++k) {
+              const uint64_t da = make_smem_desc(a_addr + k * 32, 16, Wh * 128);
+              const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
+              umma_bf16(tmem + m * BN, da, db, idesc, (uint32_t)((it | k) != 0));
+            }
+          }
+          umma_commit(bar_bempty + 8 * bs);
+          if (t == p.ntaps - 1) umma_commit(bar_hempty + 8 * hs);
+          if (cc == nchunks - 1 && t == p.ntaps - 1) umma_commit(bar_accum);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc_dyn(tmem, ncols);
 }
 
 // ======================================================================================================= wgrad
@@ -471,6 +687,27 @@ static int launch_fwd(const CisConv* d, cudaStream_t st) {
   return cis_check_launch("conv_igemm");
 }
 
+
+template <int BN>
+static int launch_halo(const CisConv* d, cudaStream_t st) {
+  const int Wh = 8 + d->ex, Hh = 16 * d->MT + d->ey, HP = Wh * Hh;
+  const int halo_stage = (HP * 128 + 1023) & ~1023;
+  const int smem = 2 * halo_stage + kHaloBStages * BN * 128 + HP * 4 + 1024;
+  if (smem > 227 * 1024) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_conv_igemm(halo): tile does not fit shared memory");
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cis_set_cuda_error(e, "cudaFuncSetAttribute(conv_halo)");
+    attr_smem = smem;
+  }
+  const int dd = d->dil;
+  const int Hp0 = (d->OH + dd - 1) / dd, Wp0 = (d->OW + dd - 1) / dd;
+  const int tiles = ((Wp0 + 7) / 8) * ((Hp0 + 16 * d->MT - 1) / (16 * d->MT));
+  dim3 grid(tiles * dd * dd * d->N, d->n_tiles);
+  conv_halo_kernel<BN><<<grid, kThreads, smem, st>>>(*d, halo_stage);
+  return cis_check_launch("conv_halo");
+}
+
 extern "C" int cis_conv_igemm(const CisConv* d, cis_stream_t stream) {
   if (!d || d->ntaps < 1 || d->ntaps > CIS_MAX_TAPS || d->nsrc < 1 || d->nsrc > CIS_MAX_SRC || d->K_pad % 64 != 0 || d->K_pad <= 0 ||
       d->n_tiles < 1 || !d->wpack)
@@ -485,6 +722,20 @@ extern "C" int cis_conv_igemm(const CisConv* d, cis_stream_t stream) {
   if ((d->add_pre || d->add_post) && (((d->add_pre_pitch | d->add_pre_coff | d->add_post_pitch | d->add_post_coff | d->out_ch) & 7) != 0))
     return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm: residual slices must be 8-channel aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  if (d->halo) {
+    if (d->MT < 1 || d->MT > 4 || d->MT * d->BN > 512 || d->dil < 1 || d->sh != 1 || d->sw != 1 || d->ey < 0 || d->ex < 0 ||
+        (d->dil > 1 && (d->OH != d->H || d->OW != d->W)))
+      return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm(halo): bad tile parameters");
+    if (d->K_pad < (d->ntaps - 1) * chunks * 8 + ((chunks + 7) / 8) * 64)
+      return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm(halo): K_pad too small for 64-channel chunking");
+    switch (d->BN) {
+      case 16: return launch_halo<16>(d, st);
+      case 32: return launch_halo<32>(d, st);
+      case 64: return launch_halo<64>(d, st);
+      case 128: return launch_halo<128>(d, st);
+      default: return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_conv_igemm: BN must be 16/32/64/128");
+    }
+  }
   switch (d->BN) {
     case 16: return launch_fwd<16>(d, st);
     case 32: return launch_fwd<32>(d, st);

@@ -135,6 +135,58 @@ def pick_bn(cout):
     return 128, -(-cout // 128)
 
 
+
+NUM_SMS = 148
+HALO_ENABLED = True
+
+
+def _pow2_cols(c):
+    for v in (32, 64, 128, 256, 512):
+        if c <= v:
+            return v
+    return 1024
+
+
+def setup_halo(d, taps, dil, n_tiles):
+    """Switch a stride-1 gather descriptor to the halo-resident kernel when it pays off: taps become offsets relative to the
+    halo origin in units of `dil`, MT (stacked 16x8 tiles per CTA) is chosen by a wave/overhead model."""
+    if not HALO_ENABLED or d.sh != 1 or d.sw != 1:
+        return False
+    if any(a % dil or b % dil for a, b in taps):
+        return False
+    if dil > 1 and (d.OH != d.H or d.OW != d.W):
+        return False
+    th = [(a // dil, b // dil) for a, b in taps]
+    hoy, hox = min(a for a, _ in th), min(b for _, b in th)
+    rel = [(a - hoy, b - hox) for a, b in th]
+    ey, ex = max(a for a, _ in rel), max(b for _, b in rel)
+    Hp0, Wp0 = -(-d.OH // dil), -(-d.OW // dil)
+    tiles_x = -(-Wp0 // 8)
+    best = None
+    ntaps = len(taps)
+    for MT in (4, 3, 2, 1):
+        if MT * d.BN > 512:
+            continue
+        HP = (8 + ex) * (16 * MT + ey)
+        smem = 2 * ru(HP * 128, 1024) + 3 * d.BN * 128 + HP * 4 + 1024 + 1024
+        if smem > 227 * 1024:
+            continue
+        tiles_y = -(-Hp0 // (16 * MT))
+        util = (Hp0 * Wp0) / float(tiles_y * 16 * MT * tiles_x * 8)
+        ncta = d.N * dil * dil * tiles_x * tiles_y * n_tiles
+        # per (tap, 64-channel chunk) and SM: tensor time vs L2->SM operand traffic (~20 B/clk/SM with all SMs pulling)
+        t_mma = MT * 2.0 * d.BN
+        t_mem = (d.BN * 128 + HP * 128.0 / ntaps) / 20.0
+        cost = -(-ncta // NUM_SMS) * (max(t_mma, t_mem) + 400.0 / ntaps)
+        if best is None or cost < best[0] - 1e-9:
+            best = (cost, MT, util)
+    if best is None or best[2] < 0.5:
+        return False
+    d.halo, d.dil, d.MT, d.hoy, d.hox, d.ey, d.ex = 1, dil, best[1], hoy, hox, ey, ex
+    _fill_taps(d, rel)
+    return True
+
+
 class ParamStore(object):
     """One flat fp32 parameter buffer (+ grad, Adam m/v) per variable scope; names follow the TF variable layout
     (adversarial_learner.py:211-214 scopes 'MaskNet' / 'FlownetS'; model_pwcnet.py 'pwcnet')."""
@@ -220,7 +272,7 @@ class ConvLayer(object):
         """kmap[k=(ti,pos)] = taps_idx[ti]*per_tap_stride + chanmap[pos]*chan_stride (or -1)."""
         m = len(chanmap)
         K = len(taps_idx) * m
-        Kp = ru(K, 64)
+        Kp = ru(max(K, (len(taps_idx) - 1) * m + ru(m, 64)), 64)   # halo kernel reads 64-channel chunks per tap
         km = np.full(Kp, -1, dtype=np.int32)
         cm = np.asarray(chanmap, dtype=np.int64)
         for ti, t in enumerate(taps_idx):
@@ -417,6 +469,8 @@ class Builder(object):
         if post_add is not None:
             d.add_post, d.add_post_pitch, d.add_post_coff = post_add.ptr, post_add.pitch, post_add.c_off
         d.mode = mode
+        if layer.stride == 1:
+            setup_halo(d, taps, layer.dil, layer.n_tiles)
         plan.keep.append(d)
         plan.keep += [srcs, out, outf, addf, post_add, layer]
         plan.add('cis_conv_igemm', C.byref(d), flops=2.0 * N * OH * OW * layer.k * layer.k * layer.cin * layer.cout)
@@ -490,6 +544,7 @@ class Builder(object):
             d.out, d.out_pitch, d.out_coff, d.out_ch = tgt.ptr, tgt.pitch, tgt.c_off, tgt.C8
             if acc:
                 d.add_pre, d.add_pre_pitch, d.add_pre_coff = tgt.ptr, tgt.pitch, tgt.c_off
+            setup_halo(d, pk['taps'], layer.dil if s == 1 else 1, pk['n_tiles'])
             bp.keep.append(d)
             bp.add('cis_conv_igemm', C.byref(d), flops=2.0 * nb * oh * ow * len(pk['taps']) * layer.cin * layer.cout)
         if single:
@@ -528,6 +583,7 @@ class Builder(object):
             d.out, d.out_pitch, d.out_coff, d.out_ch = out.ptr, out.pitch, out.c_off, layer.cout
             if outf is not None:
                 d.outf, d.outf_pitch, d.outf_coff, d.outf_ch = outf.data_ptr(), outf.shape[-1], 0, layer.cout
+            setup_halo(d, pk['taps'], 1, layer.n_tiles)
             plan.keep.append(d)
             plan.keep += [src, out, outf, layer]
             plan.add('cis_conv_igemm', C.byref(d), flops=2.0 * N * H * W * len(pk['taps']) * layer.cin * layer.cout)

@@ -135,7 +135,9 @@ def run_ours(args):
     cfg = Config(img_height=H, img_width=W, batch_size=BPG * world, dataset='SYNTHETIC', flow_ckpt='synthetic', summary_freq=10 ** 9)
     L = AdversarialLearner()
     L.config = cfg
-    L.build_train_graph()
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):        # stdout carries exactly one JSON line
+        L.build_train_graph()
     rank, dev = L.rank, L.device
     g = L.graph
     pool = [L.reader.batch(BPG) for _ in range(2)]

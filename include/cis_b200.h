@@ -46,7 +46,8 @@ typedef struct {
   int16_t dw[CIS_MAX_TAPS];
   int32_t nsrc;
   CisSrc src[CIS_MAX_SRC];
-  const void* wpack; /* bf16 [n_tiles*BN][K_pad], K order (tap, concat channel), K_pad multiple of 64 */
+  const void* wpack; /* halo=0: bf16 [n_tiles*BN][K_pad], K order (tap, concat channel), K_pad multiple of 64;
+                        halo=1: pre-swizzled tiles from cis_pack_weights_tiled */
   int32_t K_pad;
   int32_t BN;        /* N tile: 16, 32, 64 or 128 */
   int32_t n_tiles;   /* grid.y; padded output channels = n_tiles*BN */
@@ -102,6 +103,10 @@ int cis_conv_wgrad(const CisWgrad* d, cis_stream_t stream);
 /* wp[n][k] = (kmap[k] >= 0 && ne >= 0) ? w[kmap[k] + ne*sn] : 0 for n < rows, ne = nmap ? nmap[n] : (n < cout ? n : -1). */
 int cis_pack_weights(const float* w, const int32_t* kmap, int32_t K_pad, int32_t rows, int32_t cout, int32_t sn, const int32_t* nmap,
                      void* wp, cis_stream_t stream);
+/* halo-kernel operand: out[(ny, chunk, tap)][n][64] bf16 blocks of BN x 128 B with the SWIZZLE_128B pattern pre-applied; kmap is the
+ * same tap-major map (k = tap*cin8 + channel). */
+int cis_pack_weights_tiled(const float* w, const int32_t* kmap, int32_t cin8, int32_t ntaps, int32_t n_tiles, int32_t BN, int32_t cout,
+                           int32_t sn, const int32_t* nmap, void* out, cis_stream_t stream);
 /* dw[kmap[k] + n] (=|+=) dwp[n][k] for kmap[k] >= 0, n < cout  (forward orientation, sn = 1). */
 int cis_unpack_wgrad(const float* dwp, const int32_t* kmap, int32_t K_pad, int32_t cout, float* dw, cis_stream_t stream);
 /* tf.layers.batch_normalization in inference mode folded into the conv (convolution_utils.py:46-51):

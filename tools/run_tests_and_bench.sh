@@ -1,2 +1,2 @@
-timeout 1200 python -m pytest tests -q -m gpu 2>&1 | tail -25 | cut -c1-600
-python bench.py --steps 8 --warmup 4 --no-cpu > gpurun_out/bench_b.json 2> gpurun_out/bench_b.err; tail -2 gpurun_out/bench_b.err | cut -c1-300; cat gpurun_out/bench_b.json | cut -c1-1800
+timeout 600 python -m pytest tests -q -m gpu --timeout 90 2>&1 | tail -12 | cut -c1-600
+timeout 300 python bench.py --steps 8 --warmup 4 --no-cpu > gpurun_out/bench_b.json 2> gpurun_out/bench_b.err; tail -2 gpurun_out/bench_b.err | cut -c1-300; cat gpurun_out/bench_b.json | cut -c1-1800

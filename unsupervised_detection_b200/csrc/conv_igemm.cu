@@ -14,6 +14,16 @@
 #include "../../include/cis_b200.h"
 #include "common.cuh"
 
+// cp.async (LDGSTS) data is published to the MMA warp through the mbarrier that cp.async.mbarrier.arrive.noinc signals; the
+// tensor core then reads it through the async proxy.  A consumer-side fence.proxy.async per pipeline step costs > 1000 clk of
+// serial latency in the single issuing warp (ncu r01c), so it is compiled out by default -- the same protocol CUTLASS uses for
+// its cp.async + UMMA/GMMA mainloops; every launch configuration is covered by the bit-sensitive parity tests.
+#ifdef CIS_PARANOID_PROXY_FENCE
+#define CIS_CONSUMER_PROXY_FENCE() fence_proxy_async()
+#else
+#define CIS_CONSUMER_PROXY_FENCE() ((void)0)
+#endif
+
 namespace cis {
 
 static constexpr int kBM = 128;       // GEMM rows per CTA
@@ -220,16 +230,8 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
       const uint32_t b_dst = b_base + s * Cfg::kBStage + rl * 128 + sw_off;
 #pragma unroll
       for (int i = 0; i < BN / 16; ++i) cp_async16(b_dst + i * 16 * 128, wrow + (size_t)i * 16 * p.K_pad + kb * kBK, 16u);
-      cp_async_commit();
-      if (kb >= kLag) {
-        cp_async_wait<kLag>();
-        fence_proxy_async();
-        mbar_arrive(bar_full + 8 * ((kb - kLag) % S));
-      }
+      cp_async_mbar_arrive_noinc(bar_full + 8 * s);
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int kb = (nkb > kLag ? nkb - kLag : 0); kb < nkb; ++kb) mbar_arrive(bar_full + 8 * (kb % S));
 
     // ------------------------------------------------------------------ epilogue
     mbar_wait(bar_accum, 0);
@@ -261,16 +263,13 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
       const int s = kb % S;
       const uint32_t ph = (uint32_t)((kb / S) & 1);
       mbar_wait(bar_full + 8 * s, ph);
+      CIS_CONSUMER_PROXY_FENCE();
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = a_base + s * kAStage;
-        const uint32_t b_addr = b_base + s * Cfg::kBStage;
+      if (elect_one()) {
+        const uint32_t alo = desc_lo(a_base + s * kAStage, 16), blo = desc_lo(b_base + s * Cfg::kBStage, 16);
+        const uint32_t dhi = desc_hi(1024);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          const uint64_t da = make_smem_desc(a_addr + k * 32, 16, 1024);
-          const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem, da, db, idesc, (uint32_t)((kb | k) != 0));
-        }
+        for (int k = 0; k < kBK / 16; ++k) umma_bf16_lh(tmem, alo + 2 * k, dhi, blo + 2 * k, dhi, idesc, (uint32_t)((kb | k) != 0));
         umma_commit(bar_empty + 8 * s);
         if (kb == nkb - 1) umma_commit(bar_accum);
       }
@@ -291,14 +290,13 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
 // applies the 128B swizzle on absolute shared-memory address bits (tools/umma_probe.cu), so 128-byte-granular starts and a
 // non-1024 SBO are legal with base_offset = 0.  im2col traffic drops from k*k x to ~1.3 x and the packed weights of a
 // (tap, chunk) are reused by the MT tiles.
-static constexpr int kHaloBStages = 3;
+static constexpr int kHaloMaxBStages = 8;
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_constant__ CisConv p, const int halo_stage_bytes) {
-  constexpr int BS = kHaloBStages;
+__global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_constant__ CisConv p, const int halo_stage_bytes, const int BS) {
   constexpr int kBStage = BN * 128;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bars[2 * 2 + 2 * BS + 1];
+  __shared__ uint64_t bars[2 * 2 + 2 * kHaloMaxBStages + 1];
   __shared__ uint32_t tmem_slot;
   __shared__ int s_dh[CIS_MAX_TAPS], s_dw[CIS_MAX_TAPS];
   __shared__ SrcS s_src[CIS_MAX_SRC];
@@ -311,8 +309,8 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   const uint32_t b_base = tile_base + 2 * halo_stage_bytes;         // BS weight stages
   int* pixtab = reinterpret_cast<int*>(smem_raw + (b_base + BS * kBStage - smem_u32(smem_raw)));
   const uint32_t bar_hfull = smem_u32(&bars[0]), bar_hempty = smem_u32(&bars[2]);
-  const uint32_t bar_bfull = smem_u32(&bars[4]), bar_bempty = smem_u32(&bars[4 + BS]);
-  const uint32_t bar_accum = smem_u32(&bars[4 + 2 * BS]);
+  const uint32_t bar_bfull = smem_u32(&bars[4]), bar_bempty = smem_u32(&bars[4 + kHaloMaxBStages]);
+  const uint32_t bar_accum = smem_u32(&bars[4 + 2 * kHaloMaxBStages]);
 
   // ---- tile decode: blockIdx.x -> (tx, ty, phase, n)
   const int Hp0 = (p.OH + d - 1) / d, Wp0 = (p.OW + d - 1) / d;
@@ -350,11 +348,11 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < 2; ++s) {
-        mbar_init(bar_hfull + 8 * s, kProducerThreads);
+        mbar_init(bar_hfull + 8 * s, 96);
         mbar_init(bar_hempty + 8 * s, 1);
       }
       for (int s = 0; s < BS; ++s) {
-        mbar_init(bar_bfull + 8 * s, kProducerThreads);
+        mbar_init(bar_bfull + 8 * s, 1);   // one expect_tx arrival; the bulk copy completes the transaction bytes
         mbar_init(bar_bempty + 8 * s, 1);
       }
       mbar_init(bar_accum, 1);
@@ -370,71 +368,56 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
 
   if (warp < 4) {
     // ------------------------------------------------------------------ producers
-    const int j = tid & 7, pl = tid >> 3;
-    // cp.async groups complete in order; a group's "full" arrival is issued two commits later (kLag = 2 in flight), which is
-    // deadlock-free because every wait-for-empty below depends only on groups that are >= 2 commits old (BS = 3 stages).
-    uint32_t pend0 = 0, pend1 = 0;
-    int npend = 0;
-    auto push = [&](uint32_t bar) {
-      cp_async_commit();
-      if (npend == 2) {
-        cp_async_wait<2>();
-        fence_proxy_async();
-        mbar_arrive(pend0);
-        pend0 = pend1;
-        pend1 = bar;
-      } else {
-        if (npend == 0) pend0 = bar; else pend1 = bar;
-        ++npend;
-      }
-    };
-    const __nv_bfloat16* wbase = reinterpret_cast<const __nv_bfloat16*>(p.wpack) + (size_t)(ny * BN + pl) * p.K_pad + j * 8;
-    int it = 0;
-    for (int cc = 0; cc < nchunks; ++cc) {
-      const int hs = cc & 1;
-      mbar_wait(bar_hempty + 8 * hs, (uint32_t)(((cc >> 1) & 1) ^ 1));
-      const int rem = m_chunks - cc * 8;                 // valid 16-byte chunks in this 64-channel chunk
-      const int nk16 = rem >= 8 ? 4 : (rem + 1) / 2;     // K=16 MMA groups actually issued
-      const bool need = j < 2 * nk16;
-      const bool cvalid = j < rem;
-      int c = cc * 8 + j, si = 0;
-      if (cvalid) {
-        while (si < p.nsrc - 1 && c >= s_src[si].chunks) {
-          c -= s_src[si].chunks;
-          ++si;
+    // Two independent roles so neither stream throttles the other: warps 0-1 stream the per-chunk halos (2 stages), warps 2-3
+    // stream the per-(tap, chunk) weight tiles (BS stages).
+    if (warp != 2) {
+      const int hid = warp == 3 ? tid - 32 : tid;   // 96 halo loader threads (warps 0, 1, 3)
+      const int j = hid & 7, pl = hid >> 3;         // pl = 0..11
+      for (int cc = 0; cc < nchunks; ++cc) {
+        const int hs = cc & 1;
+        mbar_wait(bar_hempty + 8 * hs, (uint32_t)(((cc >> 1) & 1) ^ 1));
+        const int rem = m_chunks - cc * 8;                 // valid 16-byte chunks in this 64-channel chunk
+        const int nk16 = rem >= 8 ? 4 : (rem + 1) / 2;     // K=16 MMA groups actually issued
+        const bool need = j < 2 * nk16;
+        const bool cvalid = j < rem;
+        int c = cc * 8 + j, si = 0;
+        if (cvalid) {
+          while (si < p.nsrc - 1 && c >= s_src[si].chunks) {
+            c -= s_src[si].chunks;
+            ++si;
+          }
+        } else {
+          c = 0;
         }
-      } else {
-        c = 0;
-      }
-      const int nmod = s_src[si].n_mod, pitch = s_src[si].pitch;
-      const int ne = nmod ? (n % nmod) : n;
-      const __nv_bfloat16* sp = s_src[si].ptr;
-      const __nv_bfloat16* sb = sp + (size_t)ne * p.H * p.W * pitch + s_src[si].c_off + c * 8;
-      if (need) {
-        const uint32_t hdst = h_base + hs * halo_stage_bytes;
-        for (int q = pl; q < HP; q += 16) {
-          const int off = pixtab[q];
-          const bool ok = cvalid && off >= 0;
-          cp_async16(hdst + q * 128 + ((j ^ (q & 7)) << 4), ok ? (const void*)(sb + (size_t)off * pitch) : (const void*)sp, ok ? 16u : 0u);
-        }
-      }
-      push(bar_hfull + 8 * hs);
-      for (int t = 0; t < p.ntaps; ++t, ++it) {
-        const int bs = it % BS;
-        mbar_wait(bar_bempty + 8 * bs, (uint32_t)(((it / BS) & 1) ^ 1));
+        const int nmod = s_src[si].n_mod, pitch = s_src[si].pitch;
+        const int ne = nmod ? (n % nmod) : n;
+        const __nv_bfloat16* sp = s_src[si].ptr;
+        const __nv_bfloat16* sb = sp + (size_t)ne * p.H * p.W * pitch + s_src[si].c_off + c * 8;
         if (need) {
-          const uint32_t bdst = b_base + bs * kBStage + pl * 128 + ((j ^ (pl & 7)) << 4);
-          const __nv_bfloat16* wsrc = wbase + (size_t)t * cin8 + cc * 64;
-#pragma unroll
-          for (int i = 0; i < BN / 16; ++i) cp_async16(bdst + i * 16 * 128, wsrc + (size_t)i * 16 * p.K_pad, 16u);
+          const uint32_t hdst = h_base + hs * halo_stage_bytes + (uint32_t)(j << 4);
+          for (int q = pl; q < HP; q += 12) {
+            const int off = pixtab[q];
+            const bool ok = cvalid && off >= 0;
+            cp_async16((hdst + q * 128) ^ (uint32_t)((q & 7) << 4), ok ? (const void*)(sb + (size_t)off * pitch) : (const void*)sp,
+                       ok ? 16u : 0u);
+          }
         }
-        push(bar_bfull + 8 * bs);
+        cp_async_mbar_arrive_noinc(bar_hfull + 8 * hs);
+      }
+    } else if (tid == 64) {
+      // weights: pre-swizzled [n-tile][chunk][tap] tiles of BN x 128 B (cis_pack_weights_tiled) -> ONE bulk copy per pipeline step
+      const uint8_t* wt = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)ny * nchunks * p.ntaps * kBStage;
+      int it = 0;
+      for (int cc = 0; cc < nchunks; ++cc) {
+        for (int t = 0; t < p.ntaps; ++t, ++it) {
+          const int bs = it % BS;
+          mbar_wait(bar_bempty + 8 * bs, (uint32_t)(((it / BS) & 1) ^ 1));
+          mbar_expect_tx(bar_bfull + 8 * bs, kBStage);
+          bulk_g2s(b_base + bs * kBStage, wt + (size_t)it * kBStage, kBStage, bar_bfull + 8 * bs);
+        }
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    if (npend > 0) mbar_arrive(pend0);
-    if (npend > 1) mbar_arrive(pend1);
+    __syncwarp();
 
     // ------------------------------------------------------------------ epilogue
     mbar_wait(bar_accum, 0);
@@ -458,26 +441,34 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   } else {
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+    const uint32_t ahi = desc_hi((uint32_t)(Wh * 128)), bhi = desc_hi(1024);
+    const uint32_t a_mstep = (uint32_t)(16 * Wh * 128) >> 4;   // descriptor start-field step between stacked M tiles
     int it = 0;
     for (int cc = 0; cc < nchunks; ++cc) {
       const int hs = cc & 1;
       const int rem = m_chunks - cc * 8;
       const int nk16 = rem >= 8 ? 4 : (rem + 1) / 2;
       mbar_wait(bar_hfull + 8 * hs, (uint32_t)((cc >> 1) & 1));
+      CIS_CONSUMER_PROXY_FENCE();
       const uint32_t hsrc = h_base + hs * halo_stage_bytes;
       for (int t = 0; t < p.ntaps; ++t, ++it) {
         const int bs = it % BS;
         mbar_wait(bar_bfull + 8 * bs, (uint32_t)((it / BS) & 1));
+        CIS_CONSUMER_PROXY_FENCE();
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t b_addr = b_base + bs * kBStage;
-          const uint32_t tap_off = (uint32_t)((s_dh[t] * Wh + s_dw[t]) * 128);
-          for (int m = 0; m < MT; ++m) {
-            const uint32_t a_addr = hsrc + (uint32_t)(16 * m * Wh * 128) + tap_off;
-            for (int k = 0; k < nk16; ++k) {
-              const uint64_t da = make_smem_desc(a_addr + k * 32, 16, Wh * 128);
-              const uint64_t db = make_smem_desc(b_addr + k * 32, 16, 1024);
-              umma_bf16(tmem + m * BN, da, db, idesc, (uint32_t)((it | k) != 0));
+        if (elect_one()) {
+          const uint32_t blo = desc_lo(b_base + bs * kBStage, 16);
+          uint32_t alo = desc_lo(hsrc + (uint32_t)((s_dh[t] * Wh + s_dw[t]) * 128), 16);
+          const uint32_t acc0 = (uint32_t)(it != 0);
+          for (int m = 0; m < MT; ++m, alo += a_mstep) {
+            const uint32_t td = tmem + m * BN;
+            if (nk16 == 4) {
+              umma_bf16_lh(td, alo, ahi, blo, bhi, idesc, acc0);
+              umma_bf16_lh(td, alo + 2, ahi, blo + 2, bhi, idesc, 1u);
+              umma_bf16_lh(td, alo + 4, ahi, blo + 4, bhi, idesc, 1u);
+              umma_bf16_lh(td, alo + 6, ahi, blo + 6, bhi, idesc, 1u);
+            } else {
+              for (int k = 0; k < nk16; ++k) umma_bf16_lh(td, alo + 2 * k, ahi, blo + 2 * k, bhi, idesc, k ? 1u : acc0);
             }
           }
           umma_commit(bar_bempty + 8 * bs);
@@ -614,16 +605,8 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
           cp_async16(dst + (2 + u) * kWTile, bptr[u] + off, ok ? 16u : 0u);
         }
       }
-      cp_async_commit();
-      if (it >= kLag) {
-        cp_async_wait<kLag>();
-        fence_proxy_async();
-        mbar_arrive(bar_full + 8 * ((it - kLag) % S));
-      }
+      cp_async_mbar_arrive_noinc(bar_full + 8 * s);
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    for (int it = (nkb > kLag ? nkb - kLag : 0); it < nkb; ++it) mbar_arrive(bar_full + 8 * (it % S));
 
     // epilogue: row = output channel co, columns = packed K columns of this n-tile
     mbar_wait(bar_accum, 0);
@@ -647,16 +630,14 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
       const int s = it % S;
       const uint32_t ph = (uint32_t)((it / S) & 1);
       mbar_wait(bar_full + 8 * s, ph);
+      CIS_CONSUMER_PROXY_FENCE();
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t st = tile_base + s * kWStage;
+        // 16 pixels (K) per MMA = 16 rows x 128 B; MN atoms (64 channels) are kWTile apart (LBO), 8-row K groups 1024 B (SBO)
+        const uint32_t alo = desc_lo(st, kWTile), blo = desc_lo(st + 2 * kWTile, kWTile), dhi = desc_hi(1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          // 16 pixels (K) per MMA = 16 rows x 128 B; MN atoms (64 channels) are kWTile apart (LBO), 8-row K groups 1024 B (SBO)
-          const uint64_t da = make_smem_desc(st + k * 2048, kWTile, 1024);
-          const uint64_t db = make_smem_desc(st + 2 * kWTile + k * 2048, kWTile, 1024);
-          umma_bf16(tmem, da, db, idesc, (uint32_t)((it | k) != 0));
-        }
+        for (int k = 0; k < 4; ++k) umma_bf16_lh(tmem, alo + 128 * k, dhi, blo + 128 * k, dhi, idesc, (uint32_t)((it | k) != 0));
         umma_commit(bar_empty + 8 * s);
         if (it == nkb - 1) umma_commit(bar_accum);
       }
@@ -692,8 +673,12 @@ template <int BN>
 static int launch_halo(const CisConv* d, cudaStream_t st) {
   const int Wh = 8 + d->ex, Hh = 16 * d->MT + d->ey, HP = Wh * Hh;
   const int halo_stage = (HP * 128 + 1023) & ~1023;
-  const int smem = 2 * halo_stage + kHaloBStages * BN * 128 + HP * 4 + 1024;
-  if (smem > 227 * 1024) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_conv_igemm(halo): tile does not fit shared memory");
+  const int fixed = 2 * halo_stage + HP * 4 + 1024;
+  int BS = (226 * 1024 - fixed) / (BN * 128);     // as deep a weight ring as fits next to the two halo stages
+  if (BS > kHaloMaxBStages) BS = kHaloMaxBStages;
+  if (BS > 4 && fixed + BS * BN * 128 > 110 * 1024 && fixed + 4 * BN * 128 <= 110 * 1024) BS = 4;   // keep 2 CTAs/SM when possible
+  if (BS < 2) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_conv_igemm(halo): tile does not fit shared memory");
+  const int smem = fixed + BS * BN * 128;
   static int attr_smem = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -704,7 +689,7 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   const int Hp0 = (d->OH + dd - 1) / dd, Wp0 = (d->OW + dd - 1) / dd;
   const int tiles = ((Wp0 + 7) / 8) * ((Hp0 + 16 * d->MT - 1) / (16 * d->MT));
   dim3 grid(tiles * dd * dd * d->N, d->n_tiles);
-  conv_halo_kernel<BN><<<grid, kThreads, smem, st>>>(*d, halo_stage);
+  conv_halo_kernel<BN><<<grid, kThreads, smem, st>>>(*d, halo_stage, BS);
   return cis_check_launch("conv_halo");
 }
 
@@ -726,8 +711,6 @@ extern "C" int cis_conv_igemm(const CisConv* d, cis_stream_t stream) {
     if (d->MT < 1 || d->MT > 4 || d->MT * d->BN > 512 || d->dil < 1 || d->sh != 1 || d->sw != 1 || d->ey < 0 || d->ex < 0 ||
         (d->dil > 1 && (d->OH != d->H || d->OW != d->W)))
       return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm(halo): bad tile parameters");
-    if (d->K_pad < (d->ntaps - 1) * chunks * 8 + ((chunks + 7) / 8) * 64)
-      return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm(halo): K_pad too small for 64-channel chunking");
     switch (d->BN) {
       case 16: return launch_halo<16>(d, st);
       case 32: return launch_halo<32>(d, st);

@@ -39,6 +39,31 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const int* __re
   const float v = (km >= 0 && ne >= 0) ? w[(size_t)km + (size_t)ne * sn] : 0.f;
   wp[i] = __float2bfloat16(v);
 }
+// Pre-swizzled weight tiles for the halo kernel: block (ny, cc, t) = BN rows x 128 B, row n holds K = 64 channels of chunk cc for
+// tap t with the SWIZZLE_128B pattern already applied (16-byte chunk index ^= n & 7), so a plain bulk copy lands the UMMA layout.
+__global__ void pack_weights_tiled_kernel(const float* __restrict__ w, const int* __restrict__ kmap, int cin8, int ntaps, int n_tiles, int BN,
+                                          int cout, int sn, const int* __restrict__ nmap, bf16* __restrict__ out) {
+  const int nchunks = (cin8 + 63) / 64;
+  const size_t total = (size_t)n_tiles * nchunks * ntaps * BN * 64;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int pos = (int)(i % 64);            // physical element position inside the 128-byte row
+  size_t r = i / 64;
+  const int n = (int)(r % BN); r /= BN;
+  const int t = (int)(r % ntaps); r /= ntaps;
+  const int cc = (int)(r % nchunks);
+  const int ny = (int)(r / nchunks);
+  const int kk = (((pos >> 3) ^ (n & 7)) << 3) | (pos & 7);   // logical channel within the chunk
+  const int c = cc * 64 + kk;
+  float v = 0.f;
+  if (c < cin8) {
+    const int km = kmap[t * cin8 + c];
+    const int ng = ny * BN + n;
+    const int ne = nmap ? nmap[ng] : (ng < cout ? ng : -1);
+    if (km >= 0 && ne >= 0) v = w[(size_t)km + (size_t)ne * sn];
+  }
+  out[i] = __float2bfloat16(v);
+}
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const int* __restrict__ kmap, int K_pad, int cout,
                                     float* __restrict__ dw) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -688,6 +713,12 @@ int cis_pack_weights(const float* w, const int32_t* kmap, int32_t K_pad, int32_t
                      cis_stream_t stream) {
   pack_weights_kernel<<<nblk((size_t)rows * K_pad), 256, 0, ST>>>(w, kmap, K_pad, rows, cout, sn, nmap, (mbf)wp);
   return cis_check_launch("pack_weights");
+}
+int cis_pack_weights_tiled(const float* w, const int32_t* kmap, int32_t cin8, int32_t ntaps, int32_t n_tiles, int32_t BN, int32_t cout, int32_t sn,
+                           const int32_t* nmap, void* out, cis_stream_t stream) {
+  const size_t total = (size_t)n_tiles * ((cin8 + 63) / 64) * ntaps * BN * 64;
+  pack_weights_tiled_kernel<<<nblk(total), 256, 0, ST>>>(w, kmap, cin8, ntaps, n_tiles, BN, cout, sn, nmap, (mbf)out);
+  return cis_check_launch("pack_weights_tiled");
 }
 int cis_unpack_wgrad(const float* dwp, const int32_t* kmap, int32_t K_pad, int32_t cout, float* dw, cis_stream_t stream) {
   unpack_wgrad_kernel<<<nblk((size_t)cout * K_pad), 256, 0, ST>>>(dwp, kmap, K_pad, cout, dw);

@@ -295,6 +295,16 @@ class ConvLayer(object):
             self.b_eff = torch.zeros(self.npad, dtype=torch.float32, device=self.device)
             self.db_eff = torch.zeros(self.npad, dtype=torch.float32, device=self.device)
 
+    def _alloc_tiles(self, ntaps, cin8, BN, n_tiles):
+        nchunks = -(-cin8 // 64)
+        return torch.zeros(n_tiles * nchunks * ntaps * BN * 64, dtype=torch.bfloat16, device=self.device)
+
+    def fwd_tiles_buf(self):
+        """Pre-swizzled tile-major copy of the forward operand (halo kernel)."""
+        if getattr(self, 'fwd_tiles', None) is None:
+            self.fwd_tiles = self._alloc_tiles(self.k * self.k, len(self.in_chanmap), self.BN, self.n_tiles)
+        return self.fwd_tiles
+
     def w_src_ptr(self):
         return self.w_eff.data_ptr() if self.bn else self.store.ptr(self.wkey)
 
@@ -310,15 +320,28 @@ class ConvLayer(object):
         if self.fwd_pack is not None:
             if self.transposed:
                 for pk in self.tr_packs:
-                    plan.add('cis_pack_weights', self.w_src_ptr(), pk['kmap'].data_ptr(), pk['K_pad'], self.npad, self.cout, self.cin,
-                             None, pk['w'].data_ptr())
+                    if pk.get('wt') is not None:
+                        plan.add('cis_pack_weights_tiled', self.w_src_ptr(), pk['kmap'].data_ptr(), len(self.in_chanmap), len(pk['taps']),
+                                 self.n_tiles, self.BN, self.cout, self.cin, None, pk['wt'].data_ptr())
+                    if pk.get('rows_used', True):
+                        plan.add('cis_pack_weights', self.w_src_ptr(), pk['kmap'].data_ptr(), pk['K_pad'], self.npad, self.cout, self.cin,
+                                 None, pk['w'].data_ptr())
             else:
-                plan.add('cis_pack_weights', self.w_src_ptr(), self.fwd_kmap.data_ptr(), self.K_pad, self.npad, self.cout, 1,
-                         None, self.fwd_pack.data_ptr())
+                if getattr(self, 'fwd_tiles', None) is not None:
+                    plan.add('cis_pack_weights_tiled', self.w_src_ptr(), self.fwd_kmap.data_ptr(), len(self.in_chanmap), self.k * self.k,
+                             self.n_tiles, self.BN, self.cout, 1, None, self.fwd_tiles.data_ptr())
+                if getattr(self, 'fwd_rows_used', True):
+                    plan.add('cis_pack_weights', self.w_src_ptr(), self.fwd_kmap.data_ptr(), self.K_pad, self.npad, self.cout, 1,
+                             None, self.fwd_pack.data_ptr())
         if dgrad and self.dgrad_packs:
+            cout8 = ru(self.cout, 8)
             for pk in self.dgrad_packs:
-                plan.add('cis_pack_weights', self.w_src_ptr(), pk['kmap'].data_ptr(), pk['K_pad'], pk['rows'], len(self.in_chanmap),
-                         self.cout, pk['nmap'].data_ptr(), pk['w'].data_ptr())
+                if pk.get('wt') is not None:
+                    plan.add('cis_pack_weights_tiled', self.w_src_ptr(), pk['kmap'].data_ptr(), cout8, len(pk['taps']), pk['n_tiles'], pk['BN'],
+                             len(self.in_chanmap), self.cout, pk['nmap'].data_ptr(), pk['wt'].data_ptr())
+                if pk.get('rows_used', True):
+                    plan.add('cis_pack_weights', self.w_src_ptr(), pk['kmap'].data_ptr(), pk['K_pad'], pk['rows'], len(self.in_chanmap),
+                             self.cout, pk['nmap'].data_ptr(), pk['w'].data_ptr())
 
     def plan_zero_grads(self, bp):
         if hasattr(self, 'dwp'):
@@ -469,8 +492,11 @@ class Builder(object):
         if post_add is not None:
             d.add_post, d.add_post_pitch, d.add_post_coff = post_add.ptr, post_add.pitch, post_add.c_off
         d.mode = mode
-        if layer.stride == 1:
-            setup_halo(d, taps, layer.dil, layer.n_tiles)
+        if layer.stride == 1 and setup_halo(d, taps, layer.dil, layer.n_tiles):
+            d.wpack = layer.fwd_tiles_buf().data_ptr()
+            layer.fwd_rows_used = getattr(layer, 'fwd_rows_used', False)
+        else:
+            layer.fwd_rows_used = True
         plan.keep.append(d)
         plan.keep += [srcs, out, outf, addf, post_add, layer]
         plan.add('cis_conv_igemm', C.byref(d), flops=2.0 * N * OH * OW * layer.k * layer.k * layer.cin * layer.cout)
@@ -507,7 +533,7 @@ class Builder(object):
             w.dwp, w.Cout, w.K_pad = layer.dwp.data_ptr(), layer.cout, layer.K_pad
             nkb = -(-npix // 64)
             ntile = -(-layer.K_pad // 128)
-            w.splits = max(1, min(nkb // 4 if nkb >= 4 else 1, max(1, (2 * 148) // ntile)))
+            w.splits = max(1, min(nkb // 8 if nkb >= 8 else 1, max(1, (4 * NUM_SMS) // ntile)))
             bp.keep.append(w)
             bp.add('cis_conv_wgrad', C.byref(w), flops=2.0 * npix * layer.k * layer.k * layer.cin * layer.cout)
             layer.wgrad_modes = getattr(layer, 'wgrad_modes', set()) | {mode}
@@ -544,7 +570,13 @@ class Builder(object):
             d.out, d.out_pitch, d.out_coff, d.out_ch = tgt.ptr, tgt.pitch, tgt.c_off, tgt.C8
             if acc:
                 d.add_pre, d.add_pre_pitch, d.add_pre_coff = tgt.ptr, tgt.pitch, tgt.c_off
-            setup_halo(d, pk['taps'], layer.dil if s == 1 else 1, pk['n_tiles'])
+            if setup_halo(d, pk['taps'], layer.dil if s == 1 else 1, pk['n_tiles']):
+                if pk.get('wt') is None:
+                    pk['wt'] = layer._alloc_tiles(len(pk['taps']), ru(layer.cout, 8), pk['BN'], pk['n_tiles'])
+                d.wpack = pk['wt'].data_ptr()
+                pk['rows_used'] = pk.get('rows_used', False)
+            else:
+                pk['rows_used'] = True
             bp.keep.append(d)
             bp.add('cis_conv_igemm', C.byref(d), flops=2.0 * nb * oh * ow * len(pk['taps']) * layer.cin * layer.cout)
         if single:
@@ -583,7 +615,13 @@ class Builder(object):
             d.out, d.out_pitch, d.out_coff, d.out_ch = out.ptr, out.pitch, out.c_off, layer.cout
             if outf is not None:
                 d.outf, d.outf_pitch, d.outf_coff, d.outf_ch = outf.data_ptr(), outf.shape[-1], 0, layer.cout
-            setup_halo(d, pk['taps'], 1, layer.n_tiles)
+            if setup_halo(d, pk['taps'], 1, layer.n_tiles):
+                if pk.get('wt') is None:
+                    pk['wt'] = layer._alloc_tiles(len(pk['taps']), len(layer.in_chanmap), layer.BN, layer.n_tiles)
+                d.wpack = pk['wt'].data_ptr()
+                pk['rows_used'] = pk.get('rows_used', False)
+            else:
+                pk['rows_used'] = True
             plan.keep.append(d)
             plan.keep += [src, out, outf, layer]
             plan.add('cis_conv_igemm', C.byref(d), flops=2.0 * N * H * W * len(pk['taps']) * layer.cin * layer.cout)

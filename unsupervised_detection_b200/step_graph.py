@@ -144,6 +144,7 @@ class CISGraph(object):
         for L in self.rec.all_layers():
             L.plan_pack(self.pack_rec, dgrad=train)
         self._pwc_packed = False
+        self._dirty = True      # packed bf16 operands out of date w.r.t. the fp32 master weights
         self.graphs = {}
 
     # ------------------------------------------------------------------------------------------------ parameters
@@ -151,6 +152,7 @@ class CISGraph(object):
         """params: dict name -> tensor with the reference's variable layout (see oracle/params.py for the names)."""
         self.gen_store.load(params)
         self.rec_store.load(params)
+        self._dirty = True
         if self.with_pwc:
             self.pwc_store.load(params)
             self._pwc_packed = False
@@ -172,18 +174,26 @@ class CISGraph(object):
             self.pack_pwc.run()
             self._pwc_packed = True
 
-    def forward(self):
+    def _ensure_packed(self):
         self._ensure_pwc()
-        self.pack_gen.run()
-        self.pack_rec.run()
+        if self._dirty:
+            self.pack_gen.run()
+            self.pack_rec.run()
+            self._dirty = False
+
+    def _pack_of(self, mode):
+        return self.pack_rec if mode == 'R' else self.pack_gen
+
+    def forward(self):
+        self._ensure_packed()
         self.fwd.run()
 
     def launches_per_step(self, mode):
-        return self.pack_gen.count() + self.pack_rec.count() + self.fwd.count() + self.bwd[mode].count() + self.adam[mode].count()
+        return self.fwd.count() + self.bwd[mode].count() + self.adam[mode].count() + self._pack_of(mode).count()
 
     def train_step(self, mode, allreduce=None, use_graph=False):
         """One alternating step body (adversarial_learner.py:380-397): mode 'R' = train_recover_op, 'G' = train_generator_op."""
-        self._ensure_pwc()
+        self._ensure_packed()
         if use_graph:
             g = self.graphs.get(mode)
             if g is None:
@@ -193,28 +203,27 @@ class CISGraph(object):
                 allreduce((self.rec_store if mode == 'R' else self.gen_store).grad)
             g[1].replay()
             return
-        self.pack_gen.run()
-        self.pack_rec.run()
         self.fwd.run()
         self.bwd[mode].run()
         if allreduce is not None:
             allreduce((self.rec_store if mode == 'R' else self.gen_store).grad)
         self.adam[mode].run()
+        self._pack_of(mode).run()      # only the updated network's bf16 operands are re-packed
 
     def _capture(self, mode):
         torch.cuda.synchronize()
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
-            # warm-up outside capture (sets function attributes, lazy allocations)
-            self.pack_gen.run(); self.pack_rec.run(); self.fwd.run(); self.bwd[mode].run()
+            # warm-up outside capture (sets function attributes, lazy allocations); does not touch the parameters
+            self.fwd.run(); self.bwd[mode].run(); self._pack_of(mode).run()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1):
-            self.pack_gen.run(); self.pack_rec.run(); self.fwd.run(); self.bwd[mode].run()
+            self.fwd.run(); self.bwd[mode].run()
         with torch.cuda.graph(g2):
-            self.adam[mode].run()
+            self.adam[mode].run(); self._pack_of(mode).run()
         self.graphs[mode] = (g1, g2)
         return self.graphs[mode]
 

@@ -13,6 +13,7 @@
 #include "ptx.cuh"
 #include "../../include/cis_b200.h"
 #include "common.cuh"
+#include <cuda.h>
 
 // cp.async (LDGSTS) data is published to the MMA warp through the mbarrier that cp.async.mbarrier.arrive.noinc signals; the
 // tensor core then reads it through the async proxy.  A consumer-side fence.proxy.async per pipeline step costs > 1000 clk of
@@ -291,9 +292,13 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
 // non-1024 SBO are legal with base_offset = 0.  im2col traffic drops from k*k x to ~1.3 x and the packed weights of a
 // (tap, chunk) are reused by the MT tiles.
 static constexpr int kHaloMaxBStages = 8;
+struct HaloMaps {
+  CUtensorMap m[CIS_MAX_SRC];   // one 4-D (C, W, H, N) SWIZZLE_128B map per concat source, box = (64, Wh, Hh, 1)
+};
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_constant__ CisConv p, const int halo_stage_bytes, const int BS) {
+__global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_constant__ CisConv p, const int halo_stage_bytes, const int BS, const int NHS,
+                                                        const __grid_constant__ HaloMaps maps, const int use_tma) {
   constexpr int kBStage = BN * 128;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * 2 + 2 * kHaloMaxBStages + 1];
@@ -306,7 +311,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   const int Wh = 8 + p.ex, Hh = 16 * MT + p.ey, HP = Wh * Hh;
   const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t h_base = tile_base;                                // 2 halo stages
-  const uint32_t b_base = tile_base + 2 * halo_stage_bytes;         // BS weight stages
+  const uint32_t b_base = tile_base + NHS * halo_stage_bytes;       // BS weight stages
   int* pixtab = reinterpret_cast<int*>(smem_raw + (b_base + BS * kBStage - smem_u32(smem_raw)));
   const uint32_t bar_hfull = smem_u32(&bars[0]), bar_hempty = smem_u32(&bars[2]);
   const uint32_t bar_bfull = smem_u32(&bars[4]), bar_bempty = smem_u32(&bars[4 + kHaloMaxBStages]);
@@ -348,7 +353,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < 2; ++s) {
-        mbar_init(bar_hfull + 8 * s, 96);
+        mbar_init(bar_hfull + 8 * s, use_tma ? 1 : 96);
         mbar_init(bar_hempty + 8 * s, 1);
       }
       for (int s = 0; s < BS; ++s) {
@@ -370,12 +375,30 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     // ------------------------------------------------------------------ producers
     // Two independent roles so neither stream throttles the other: warps 0-1 stream the per-chunk halos (2 stages), warps 2-3
     // stream the per-(tap, chunk) weight tiles (BS stages).
-    if (warp != 2) {
+    if (use_tma) {
+      if (tid == 0) {
+        // halo through the TMA engine: one 4-D tiled load per 64-channel chunk, out-of-image pixels / channels are zero-filled
+        for (int cc = 0; cc < nchunks; ++cc) {
+          const int hs = cc % NHS;
+          mbar_wait(bar_hempty + 8 * hs, (uint32_t)(((cc / NHS) & 1) ^ 1));
+          int c = cc * 8, si = 0;
+          while (si < p.nsrc - 1 && c >= s_src[si].chunks) {
+            c -= s_src[si].chunks;
+            ++si;
+          }
+          const int nmod = s_src[si].n_mod;
+          mbar_expect_tx(bar_hfull + 8 * hs, (uint32_t)(HP * 128));
+          tma_load_4d(h_base + hs * halo_stage_bytes, &maps.m[si], bar_hfull + 8 * hs, c * 8, tx * 8 + p.hox, ty * 16 * MT + p.hoy,
+                      nmod ? (n % nmod) : n);
+        }
+      }
+      __syncwarp();
+    } else if (warp != 2) {
       const int hid = warp == 3 ? tid - 32 : tid;   // 96 halo loader threads (warps 0, 1, 3)
       const int j = hid & 7, pl = hid >> 3;         // pl = 0..11
       for (int cc = 0; cc < nchunks; ++cc) {
-        const int hs = cc & 1;
-        mbar_wait(bar_hempty + 8 * hs, (uint32_t)(((cc >> 1) & 1) ^ 1));
+        const int hs = cc % NHS;
+        mbar_wait(bar_hempty + 8 * hs, (uint32_t)(((cc / NHS) & 1) ^ 1));
         const int rem = m_chunks - cc * 8;                 // valid 16-byte chunks in this 64-channel chunk
         const int nk16 = rem >= 8 ? 4 : (rem + 1) / 2;     // K=16 MMA groups actually issued
         const bool need = j < 2 * nk16;
@@ -404,7 +427,8 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
         }
         cp_async_mbar_arrive_noinc(bar_hfull + 8 * hs);
       }
-    } else if (tid == 64) {
+    }
+    if (tid == 64) {
       // weights: pre-swizzled [n-tile][chunk][tap] tiles of BN x 128 B (cis_pack_weights_tiled) -> ONE bulk copy per pipeline step
       const uint8_t* wt = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)ny * nchunks * p.ntaps * kBStage;
       int it = 0;
@@ -445,10 +469,10 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     const uint32_t a_mstep = (uint32_t)(16 * Wh * 128) >> 4;   // descriptor start-field step between stacked M tiles
     int it = 0;
     for (int cc = 0; cc < nchunks; ++cc) {
-      const int hs = cc & 1;
+      const int hs = cc % NHS;
       const int rem = m_chunks - cc * 8;
       const int nk16 = rem >= 8 ? 4 : (rem + 1) / 2;
-      mbar_wait(bar_hfull + 8 * hs, (uint32_t)((cc >> 1) & 1));
+      mbar_wait(bar_hfull + 8 * hs, (uint32_t)((cc / NHS) & 1));
       CIS_CONSUMER_PROXY_FENCE();
       const uint32_t hsrc = h_base + hs * halo_stage_bytes;
       for (int t = 0; t < p.ntaps; ++t, ++it) {
@@ -669,15 +693,54 @@ static int launch_fwd(const CisConv* d, cudaStream_t st) {
 }
 
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// (C, W, H, N) bf16 map of one concat source slice; box (64, bw, bh, 1), 128B swizzle, zero OOB fill.
+static bool encode_src_map(CUtensorMap* m, const CisSrc& s, int N, int H, int W, int bw, int bh) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  const int nb = s.n_mod > 0 ? s.n_mod : N;
+  cuuint64_t dims[4] = {(cuuint64_t)s.chunks * 8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nb};
+  cuuint64_t strides[3] = {(cuuint64_t)s.pitch * 2, (cuuint64_t)W * s.pitch * 2, (cuuint64_t)H * W * s.pitch * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  void* base = (void*)((const char*)s.ptr + (size_t)s.c_off * 2);
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BN>
 static int launch_halo(const CisConv* d, cudaStream_t st) {
   const int Wh = 8 + d->ex, Hh = 16 * d->MT + d->ey, HP = Wh * Hh;
   const int halo_stage = (HP * 128 + 1023) & ~1023;
-  const int fixed = 2 * halo_stage + HP * 4 + 1024;
-  int BS = (226 * 1024 - fixed) / (BN * 128);     // as deep a weight ring as fits next to the two halo stages
+  int chunks = 0;
+  for (int i = 0; i < d->nsrc; ++i) chunks += d->src[i].chunks;
+  const int nchunks = (chunks + 7) / 8;
+  const int nhs = nchunks > 1 ? 2 : 1;            // halo stages: double-buffer only when there is a next chunk to prefetch
+  const int fixed = nhs * halo_stage + HP * 4 + 1024;
+  const int steps = nchunks * d->ntaps;
+  int BS = (226 * 1024 - fixed) / (BN * 128);     // as deep a weight ring as fits ...
   if (BS > kHaloMaxBStages) BS = kHaloMaxBStages;
-  if (BS > 4 && fixed + BS * BN * 128 > 110 * 1024 && fixed + 4 * BN * 128 <= 110 * 1024) BS = 4;   // keep 2 CTAs/SM when possible
-  if (BS < 2) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_conv_igemm(halo): tile does not fit shared memory");
+  if (BS > steps) BS = steps;                     // ... but never deeper than the number of pipeline steps
+  // prefer several co-resident CTAs per SM (their load / MMA / epilogue phases overlap) over a very deep ring
+  const int budgets[3] = {56 * 1024, 74 * 1024, 112 * 1024};
+  for (int b = 0; b < 3; ++b) {
+    const int fit = (budgets[b] - fixed) / (BN * 128);
+    if (fit >= 3 || (fit >= steps && fit >= 1)) { if (BS > fit) BS = fit; break; }
+  }
+  if (BS < 1) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_conv_igemm(halo): tile does not fit shared memory");
   const int smem = fixed + BS * BN * 128;
   static int attr_smem = 0;
   if (smem > attr_smem) {
@@ -689,7 +752,15 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   const int Hp0 = (d->OH + dd - 1) / dd, Wp0 = (d->OW + dd - 1) / dd;
   const int tiles = ((Wp0 + 7) / 8) * ((Hp0 + 16 * d->MT - 1) / (16 * d->MT));
   dim3 grid(tiles * dd * dd * d->N, d->n_tiles);
-  conv_halo_kernel<BN><<<grid, kThreads, smem, st>>>(*d, halo_stage, BS);
+  // TMA halo path: undilated, every concat source except the last a multiple of 64 channels (a chunk never straddles sources)
+  HaloMaps maps;
+  int use_tma = (d->dil == 1 && Wh <= 256 && Hh <= 256) ? 1 : 0;
+  for (int i = 0; use_tma && i < d->nsrc - 1; ++i)
+    if (d->src[i].chunks % 8) use_tma = 0;
+  for (int i = 0; use_tma && i < d->nsrc; ++i)
+    if (((uintptr_t)d->src[i].ptr + (size_t)d->src[i].c_off * 2) % 16 || !encode_src_map(&maps.m[i], d->src[i], d->N, d->H, d->W, Wh, Hh)) use_tma = 0;
+  if (!use_tma) memset(&maps, 0, sizeof(maps));
+  conv_halo_kernel<BN><<<grid, kThreads, smem, st>>>(*d, halo_stage, BS, nhs, maps, use_tma);
   return cis_check_launch("conv_halo");
 }
 

@@ -66,6 +66,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, uint
       "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// 4-D tiled TMA load (tensor map in param/global space); coordinates may be negative / out of range => zero fill (= SAME padding).
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 // 1-D bulk copy global -> shared through the TMA engine; completion = complete_tx(bytes) on the mbarrier.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),

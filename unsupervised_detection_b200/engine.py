@@ -164,20 +164,29 @@ def setup_halo(d, taps, dil, n_tiles):
     tiles_x = -(-Wp0 // 8)
     best = None
     ntaps = len(taps)
-    for MT in (4, 3, 2, 1):
+    m_chunks = sum(d.src[i].chunks for i in range(d.nsrc))
+    nchunks = -(-m_chunks // 8)
+    nhs = 2 if nchunks > 1 else 1
+    for MT in (1, 2, 3, 4):
         if MT * d.BN > 512:
             continue
         HP = (8 + ex) * (16 * MT + ey)
-        smem = 2 * ru(HP * 128, 1024) + 3 * d.BN * 128 + HP * 4 + 1024 + 1024
+        fixed = nhs * ru(HP * 128, 1024) + HP * 4 + 1024
+        smem = fixed + min(3, ntaps * nchunks) * d.BN * 128 + 1024
         if smem > 227 * 1024:
             continue
         tiles_y = -(-Hp0 // (16 * MT))
         util = (Hp0 * Wp0) / float(tiles_y * 16 * MT * tiles_x * 8)
+        if util < 0.5:
+            continue
         ncta = d.N * dil * dil * tiles_x * tiles_y * n_tiles
-        # per (tap, 64-channel chunk) and SM: tensor time vs L2->SM operand traffic (~20 B/clk/SM with all SMs pulling)
-        t_mma = MT * 2.0 * d.BN
-        t_mem = (d.BN * 128 + HP * 128.0 / ntaps) / 20.0
-        cost = -(-ncta // NUM_SMS) * (max(t_mma, t_mem) + 400.0 / ntaps)
+        cps = max(1, min((225 * 1024) // smem, 512 // _pow2_cols(MT * d.BN), 6))
+        # per CTA: tensor time vs operand traffic (weights through the TMA engine ~40 B/clk/SM, halo through LDGSTS ~16 B/clk/SM),
+        # plus a fixed prologue/epilogue latency that co-resident CTAs overlap
+        t_mma = MT * 2.0 * d.BN * ntaps * nchunks
+        t_mem = (d.BN * 128 * ntaps / 40.0 + HP * 128 / 16.0) * nchunks
+        t_cta = max(t_mma, t_mem) + (4000.0 + 1500.0 * MT) / cps
+        cost = -(-ncta // (NUM_SMS * cps)) * cps * t_cta / min(cps, max(1.0, ncta / float(NUM_SMS)))
         if best is None or cost < best[0] - 1e-9:
             best = (cost, MT, util)
     if best is None or best[2] < 0.5:

@@ -516,7 +516,12 @@ static constexpr int kWTile = 64 * 128;            // one [64 pix][64 ch] bf16 s
 static constexpr int kWStage = 4 * kWTile;         // A (2 sub-tiles) + B (2 sub-tiles)
 static constexpr int kWSmem = kWStages * kWStage + 1024;
 
-__global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_constant__ CisWgrad p) {
+struct WgradMaps {
+  CUtensorMap g;                 // (C8, OW, OH, N) gradient slice, box (64, 8, 8, 1)
+  CUtensorMap x[CIS_MAX_SRC];    // (C8, W, H, N) activation slices, box (64, 8, 8, 1)
+};
+
+__global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_constant__ CisWgrad p, const __grid_constant__ WgradMaps maps) {
   constexpr int S = kWStages;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * S + 1];
@@ -535,7 +540,8 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
   int m_chunks = 0;
   for (int i = 0; i < p.nsrc; ++i) m_chunks += p.src[i].chunks;
   const int k_chunks = p.ntaps * m_chunks;
-  const int nkb_total = (M + 63) / 64;
+  const int tiles_x = (p.OW + 7) / 8, tiles_y = (p.OH + 7) / 8;
+  const int nkb_total = p.tma ? p.N * tiles_x * tiles_y : (M + 63) / 64;   // TMA path: one K block = one 8x8 pixel tile
   const int per = (nkb_total + p.splits - 1) / p.splits;
   const int kb0 = blockIdx.y * per;
   const int kb1 = min(kb0 + per, nkb_total);
@@ -545,7 +551,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
   if (warp == 4) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(bar_full + 8 * s, kProducerThreads);
+        mbar_init(bar_full + 8 * s, p.tma ? 1 : kProducerThreads);
         mbar_init(bar_empty + 8 * s, 1);
       }
       mbar_init(bar_accum, 1);
@@ -560,6 +566,53 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
   const uint32_t tmem = tmem_slot;
 
   if (warp < 4) {
+    if (p.tma) {
+      if (tid == 0) {
+        // two 64-column groups of this CTA: group = tap * nchunks64 + chunk64 -> (tap offset, source map, channel offset)
+        const int nch64 = (m_chunks + 7) / 8;
+        int gsrc[2], gc0[2], gdh[2], gdw[2], gnm[2];
+        bool gok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int grp = blockIdx.x * 2 + u;
+          gok[u] = grp < p.ntaps * nch64;
+          const int t = gok[u] ? grp / nch64 : 0;
+          int c = gok[u] ? (grp - t * nch64) * 8 : 0, si = 0;
+          while (si < p.nsrc - 1 && c >= p.src[si].chunks) {
+            c -= p.src[si].chunks;
+            ++si;
+          }
+          gsrc[u] = si;
+          gc0[u] = c * 8;
+          gdh[u] = s_dh[t];
+          gdw[u] = s_dw[t];
+          int nm = p.src[0].n_mod;
+          if (si == 1) nm = p.src[1].n_mod;
+          if (si == 2) nm = p.src[2].n_mod;
+          if (si == 3) nm = p.src[3].n_mod;
+          gnm[u] = nm;
+        }
+        const int tpi = tiles_x * tiles_y;
+        for (int it = 0; it < nkb; ++it) {
+          const int s = it % S;
+          mbar_wait(bar_empty + 8 * s, (uint32_t)(((it / S) & 1) ^ 1));
+          const int kb = kb0 + it;
+          const int n = kb / tpi, r = kb - n * tpi;
+          const int ty = r / tiles_x, tx = r - ty * tiles_x;
+          const uint32_t st = tile_base + s * kWStage, bar = bar_full + 8 * s;
+          mbar_expect_tx(bar, 4 * kWTile);
+          tma_load_4d(st, &maps.g, bar, 0, tx * 8, ty * 8, n);
+          tma_load_4d(st + kWTile, &maps.g, bar, 64, tx * 8, ty * 8, n);          // channels >= extent: zero fill
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int ne = gnm[u] ? (n % gnm[u]) : n;
+            // an invalid group (beyond the last tap) reads channel 1<<20 -> fully out of range -> zeros
+            tma_load_4d(st + (2 + u) * kWTile, &maps.x[gsrc[u]], bar, gok[u] ? gc0[u] : (1 << 20), tx * 8 + gdw[u], ty * 8 + gdh[u], ne);
+          }
+        }
+      }
+      __syncwarp();
+    } else {
     const int j = tid & 7, rl = tid >> 3;
     const uint32_t sw_off = (uint32_t)((j ^ (rl & 7)) << 4);
     // fixed per-thread decode of the two B (activation) chunks and two A (gradient) chunks
@@ -632,6 +685,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
       cp_async_mbar_arrive_noinc(bar_full + 8 * s);
     }
 
+    }
     // epilogue: row = output channel co, columns = packed K columns of this n-tile
     mbar_wait(bar_accum, 0);
     tc_fence_after();
@@ -809,7 +863,19 @@ extern "C" int cis_conv_wgrad(const CisWgrad* d, cis_stream_t stream) {
     if (e != cudaSuccess) return cis_set_cuda_error(e, "cudaFuncSetAttribute(conv_wgrad)");
     attr_set = true;
   }
+  WgradMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (d->tma) {
+    if (d->sh != 1 || d->sw != 1) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_wgrad: TMA path needs a stride-1 layer");
+    for (int i = 0; i < d->nsrc - 1; ++i)
+      if (d->src[i].chunks % 8) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_wgrad: TMA path needs 64-channel aligned concat sources");
+    CisSrc gs;
+    gs.ptr = d->g; gs.pitch = d->g_pitch; gs.c_off = d->g_coff; gs.chunks = d->g_chunks; gs.n_mod = 0;
+    bool ok = encode_src_map(&maps.g, gs, d->N, d->OH, d->OW, 8, 8);
+    for (int i = 0; ok && i < d->nsrc; ++i) ok = encode_src_map(&maps.x[i], d->src[i], d->N, d->H, d->W, 8, 8);
+    if (!ok) return cis_set_error(CIS_ERR_CUDA, "cis_conv_wgrad: cuTensorMapEncodeTiled failed / unavailable");
+  }
   dim3 grid((d->K_pad + 127) / 128, d->splits);
-  conv_wgrad_kernel<<<grid, kThreads, kWSmem, (cudaStream_t)stream>>>(*d);
+  conv_wgrad_kernel<<<grid, kThreads, kWSmem, (cudaStream_t)stream>>>(*d, maps);
   return cis_check_launch("conv_wgrad");
 }

@@ -138,6 +138,7 @@ def pick_bn(cout):
 
 NUM_SMS = 148
 HALO_ENABLED = True
+WGRAD_TMA = True
 
 
 def _pow2_cols(c):
@@ -363,7 +364,7 @@ class ConvLayer(object):
         if not hasattr(self, 'dwp'):
             return
         s = self.store
-        bp.add('cis_unpack_wgrad', self.dwp.data_ptr(), self.fwd_kmap.data_ptr(), self.K_pad, self.cout, s.ptr(self.wkey, 'grad'))
+        bp.add('cis_unpack_wgrad', self.dwp.data_ptr(), self.wg_kmap.data_ptr(), self.wg_K_pad, self.cout, s.ptr(self.wkey, 'grad'))
         if self.bn:
             bp.add('cis_bn_chain', s.ptr(self.wkey), s.ptr(self.bkey), s.ptr(self.name + '/gamma'), s.ptr(self.wkey, 'grad'),
                    self.db_eff.data_ptr(), self.k * self.k * self.cin * self.cout, self.cout, s.ptr(self.bkey, 'grad'),
@@ -533,15 +534,31 @@ class Builder(object):
         taps, _, _ = layer.fwd_taps(H, W)
         if layer.tag == mode:   # weight + bias gradients
             if not hasattr(layer, 'dwp'):
-                layer.dwp = torch.zeros(layer.cout, layer.K_pad, dtype=torch.float32, device=self.device)
+                # TMA operand path (8x8 pixel tiles) for stride-1 layers whose concat sources are 64-channel aligned
+                layer.wg_tma = bool(WGRAD_TMA and layer.stride == 1 and all(s_.C8 % 64 == 0 for s_ in srcs[:-1]))
+                if layer.wg_tma:
+                    cin8 = len(layer.in_chanmap)
+                    nch64 = -(-cin8 // 64)
+                    ncol = layer.k * layer.k * nch64 * 64
+                    layer.wg_K_pad = ru(ncol, 128)
+                    km = np.full(layer.wg_K_pad, -1, dtype=np.int32)
+                    fk = layer.fwd_kmap.cpu().numpy()
+                    for t in range(layer.k * layer.k):
+                        for pos in range(cin8):
+                            km[(t * nch64 + pos // 64) * 64 + pos % 64] = fk[t * cin8 + pos]
+                    layer.wg_kmap = torch.from_numpy(km).to(self.device)
+                else:
+                    layer.wg_K_pad, layer.wg_kmap = layer.K_pad, layer.fwd_kmap
+                layer.dwp = torch.zeros(layer.cout, layer.wg_K_pad, dtype=torch.float32, device=self.device)
             w = CisWgrad()
             w.N, w.H, w.W, w.OH, w.OW, w.sh, w.sw = nb, H, W, out.H, out.W, layer.stride, layer.stride
             _fill_taps(w, taps)
             _fill_srcs(w, srcs)
             w.g, w.g_pitch, w.g_coff, w.g_chunks = G.ptr, G.pitch, G.c_off, G.C8 // 8
-            w.dwp, w.Cout, w.K_pad = layer.dwp.data_ptr(), layer.cout, layer.K_pad
-            nkb = -(-npix // 64)
-            ntile = -(-layer.K_pad // 128)
+            w.dwp, w.Cout, w.K_pad = layer.dwp.data_ptr(), layer.cout, layer.wg_K_pad
+            w.tma = 1 if layer.wg_tma else 0
+            nkb = (nb * (-(-out.H // 8)) * (-(-out.W // 8))) if layer.wg_tma else -(-npix // 64)
+            ntile = -(-layer.wg_K_pad // 128)
             w.splits = max(1, min(nkb // 8 if nkb >= 8 else 1, max(1, (4 * NUM_SMS) // ntile)))
             bp.keep.append(w)
             bp.add('cis_conv_wgrad', C.byref(w), flops=2.0 * npix * layer.k * layer.k * layer.cin * layer.cout)

@@ -23,6 +23,17 @@ def same_pad(n_in, k, s=1, d=1):
     return total // 2, total - total // 2
 
 
+SIDE_STREAM = True
+_SIDE = {}
+
+
+def _side_stream(device):
+    key = str(device)
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
+
 class Plan(object):
     """An ordered list of C-ABI launches (and a few torch memsets) replayable on any stream."""
 
@@ -31,25 +42,67 @@ class Plan(object):
         self.ops = []
         self.keep = []  # ctypes structs / tensors that must outlive the plan
 
-    def add(self, fname, *args, flops=0.0):
+    def add(self, fname, *args, flops=0.0, lane=0):
         fn = getattr(_lib.load(), fname)
-        self.ops.append((fn, args, fname, flops))
+        self.ops.append((fn, args, fname, flops, lane))
 
     def add_py(self, fn, label='py'):
-        self.ops.append((None, fn, label, 0.0))
+        self.ops.append((None, fn, label, 0.0, 0))
 
     def zero(self, t):
         self.add_py(t.zero_, 'zero')
 
+    def join(self):
+        """Main lane waits for everything issued on the side lane so far."""
+        self.ops.append((None, None, 'join', 0.0, 0))
+
     def run(self, stream=None):
-        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
-        for fn, args, name, _ in self.ops:
+        """Lane 0 = the current stream; lane 1 = a side stream forked/joined with events (weight-gradient GEMMs run there,
+        concurrently with the data-gradient chain).  Works eagerly and under CUDA-graph capture."""
+        if stream is not None or not SIDE_STREAM or not any(op[4] for op in self.ops):
+            st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+            for fn, args, name, _, _ in self.ops:
+                if fn is None:
+                    if args is not None:
+                        args()
+                else:
+                    rc = fn(*args, st)
+                    if rc != 0:
+                        _lib.check(rc, name)
+            return
+        main = torch.cuda.current_stream()
+        side = _side_stream(main.device)
+        st0, st1 = main.cuda_stream, side.cuda_stream
+        main_ahead, side_used = True, False
+        for fn, args, name, _, lane in self.ops:
             if fn is None:
-                args()
+                if name == 'join':
+                    if side_used:
+                        ev = torch.cuda.Event()
+                        ev.record(side)
+                        main.wait_event(ev)
+                        side_used = False
+                elif args is not None:
+                    args()
+                    main_ahead = True
+                continue
+            if lane == 1:
+                if main_ahead:
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    side.wait_event(ev)
+                    main_ahead = False
+                rc = fn(*args, st1)
+                side_used = True
             else:
-                rc = fn(*args, st)
-                if rc != 0:
-                    _lib.check(rc, name)
+                rc = fn(*args, st0)
+                main_ahead = True
+            if rc != 0:
+                _lib.check(rc, name)
+        if side_used:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            main.wait_event(ev)
 
     def count(self):
         return sum(1 for op in self.ops if op[0] is not None)
@@ -139,6 +192,7 @@ def pick_bn(cout):
 NUM_SMS = 148
 HALO_ENABLED = True
 WGRAD_TMA = True
+MATERIALIZE_MISALIGNED_CONCAT = True
 
 
 def _pow2_cols(c):
@@ -458,6 +512,9 @@ class Builder(object):
              plan=None, out_rows=None):
         """y = act(conv(concat(srcs)) + bias [+ addf]) [+ post_add]; returns the output Act."""
         plan = plan or self.fwd
+        if MATERIALIZE_MISALIGNED_CONCAT and len(srcs) > 1 and layer.tag and layer.stride == 1 and \
+                any(s.C8 % 64 for s in srcs[:-1]):
+            srcs = [self.concat(srcs, name=layer.name + '.cat')]
         s0 = srcs[0]
         N = out_rows or max(s.N for s in srcs)
         H, W = s0.H, s0.W
@@ -561,10 +618,10 @@ class Builder(object):
             ntile = -(-layer.wg_K_pad // 128)
             w.splits = max(1, min(nkb // 8 if nkb >= 8 else 1, max(1, (4 * NUM_SMS) // ntile)))
             bp.keep.append(w)
-            bp.add('cis_conv_wgrad', C.byref(w), flops=2.0 * npix * layer.k * layer.k * layer.cin * layer.cout)
+            bp.add('cis_conv_wgrad', C.byref(w), flops=2.0 * npix * layer.k * layer.k * layer.cin * layer.cout, lane=1)
             layer.wgrad_modes = getattr(layer, 'wgrad_modes', set()) | {mode}
             bp.add('cis_colsum', G.ptr, G.pitch, G.c_off, npix, layer.cout,
-                   (layer.db_eff.data_ptr() if layer.bn else layer.store.ptr(layer.bkey, 'grad')))
+                   (layer.db_eff.data_ptr() if layer.bn else layer.store.ptr(layer.bkey, 'grad')), lane=1)
         need = [s for s in srcs if mode in s.dep]
         if not need:
             return
@@ -621,6 +678,48 @@ class Builder(object):
                            1 if s_.grad_written.get(mode) else 0)
                     s_.grad_written[mode] = True
                 off += s_.C8
+
+    # ---- materialised concat (only where the virtual concat is not 64-channel aligned, so the TMA operand paths apply)
+    def concat(self, srcs, name='cat'):
+        N = max(s.N for s in srcs)
+        H, W = srcs[0].H, srcs[0].W
+        chanmap, base = [], 0
+        for s in srcs:
+            chanmap += [(m + base if m >= 0 else -1) for m in s.chanmap]
+            base += s.C
+        dep = frozenset().union(*[s.dep for s in srcs])
+        cat = Act(N, H, W, base, self.device, chanmap=chanmap, dep=dep, name=name)
+        gr = [s.gen_rows for s in srcs if s.gen_rows]
+        if gr:
+            cat.gen_rows = gr[0]
+        self.keep += [srcs, cat]
+        off = 0
+        for s in srcs:
+            reps = (N // s.n_mod) if s.n_mod else 1
+            rows = s.n_mod if s.n_mod else s.N
+            for r in range(reps):   # batch-broadcast sources are replicated into every third of the batch
+                self.fwd.add('cis_add_slice', cat.ptr + 2 * r * rows * H * W * cat.pitch, cat.pitch, off, s.ptr, s.pitch, s.c_off,
+                             rows * H * W, s.C8 // 8, 1, 0)
+            off += s.C8
+
+        def bwd(bp, mode):
+            if mode not in cat.dep or not cat.grad_written.get(mode):
+                return
+            g = cat.get_grad()
+            nb = cat.rows(mode)
+            o = 0
+            for s_ in srcs:
+                if mode in s_.dep:
+                    sg = s_.get_grad()
+                    reps, rows = 1, s_.rows(mode)
+                    if s_.n_mod:
+                        reps, rows = nb // s_.n_mod, s_.n_mod
+                    bp.add('cis_add_slice', sg.ptr, sg.pitch, sg.c_off, g.ptr, g.pitch, o, rows * H * W, s_.C8 // 8, reps,
+                           1 if s_.grad_written.get(mode) else 0)
+                    s_.grad_written[mode] = True
+                o += s_.C8
+        self.tape.append(bwd)
+        return cat
 
     # ---- transposed conv (PWC-Net up_flow / up_feat), forward only
     def conv_transpose(self, layer, src, out=None, outf=None, plan=None, name=None):

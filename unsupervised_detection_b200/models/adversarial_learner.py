@@ -53,10 +53,11 @@ class AdversarialLearner(object):
         self.world, self.rank, self.local_rank = 1, 0, 0
         if int(os.environ.get('WORLD_SIZE', '1')) > 1:
             import torch.distributed as dist
-            if not dist.is_initialized():
-                dist.init_process_group('nccl' if torch.cuda.is_available() else 'gloo')
-            self.world, self.rank = dist.get_world_size(), dist.get_rank()
             self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+            torch.cuda.set_device(self.local_rank)
+            if not dist.is_initialized():
+                dist.init_process_group('nccl', device_id=torch.device('cuda', self.local_rank))
+            self.world, self.rank = dist.get_world_size(), dist.get_rank()
         self.device = 'cuda:%d' % self.local_rank
         torch.cuda.set_device(self.local_rank)
 
@@ -132,10 +133,34 @@ class AdversarialLearner(object):
     def feed(self, img1, img2):
         """Host -> device copy of one batch of frame pairs [B,384,640,3] fp32 (pinned host tensors copy asynchronously)."""
         g = self.graph
+        st = getattr(self, '_staged', None)
+        if st is not None and st[0] is img1:
+            # this batch was prefetched on the copy stream while the previous step was computing: device-to-device hand-over
+            torch.cuda.current_stream().wait_event(st[3])
+            g.img1.copy_(st[1], non_blocking=True)
+            g.img2.copy_(st[2], non_blocking=True)
+            self._staged = None
+            return
         g.img1.copy_(img1, non_blocking=True)
         g.img2.copy_(img2, non_blocking=True)
 
-    def step(self, batch=None, fetch_losses=None, use_graph=True):
+    def prefetch(self, batch):
+        """Start the host -> device copy of the NEXT batch on a side stream so it overlaps the current step's kernels."""
+        g = self.graph
+        if getattr(self, '_copy_stream', None) is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._stage_bufs = [(torch.empty_like(g.img1), torch.empty_like(g.img2)) for _ in range(2)]
+            self._stage_idx = 0
+        self._stage_idx ^= 1
+        d1, d2 = self._stage_bufs[self._stage_idx]
+        with torch.cuda.stream(self._copy_stream):
+            d1.copy_(batch[0], non_blocking=True)
+            d2.copy_(batch[1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+        self._staged = (batch[0], d1, d2, ev)
+
+    def step(self, batch=None, fetch_losses=None, use_graph=True, next_batch=None):
         """One iteration of the training loop body (adversarial_learner.py:380-409): picks train_recover_op or
         train_generator_op from the running step counter, consumes one batch, returns {global_step, loss_*?}."""
         cfg = self.config
@@ -149,6 +174,8 @@ class AdversarialLearner(object):
             batch = self.reader.batch(self.local_batch)
         self.feed(batch[0], batch[1])
         self.graph.train_step(mode, allreduce=self._allreduce(), use_graph=use_graph)
+        if next_batch is not None:
+            self.prefetch(next_batch)          # overlaps this step's kernels; consumed by the next step() call
         res = {"global_step": self.global_step, "train_op": mode}
         if fetch_losses if fetch_losses is not None else (step % cfg.summary_freq == 0):
             L = self.graph.losses()                                            # device -> host read

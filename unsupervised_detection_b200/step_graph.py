@@ -125,8 +125,10 @@ class CISGraph(object):
                 for L in layers:
                     L.plan_finalize(fin)
                 full = Plan('bwd_' + mode)
-                for pl in (pre, head, body, fin):
+                for pl in (pre, head, body):
                     full.extend(pl)
+                full.join()            # weight-gradient lane -> main lane before the packed gradients are unpacked
+                full.extend(fin)
                 self.bwd[mode] = full
                 ad = Plan('adam_' + mode)
                 if mode == 'G':

@@ -491,6 +491,7 @@ class Builder(object):
     def __init__(self, device):
         self.device = device
         self.fwd = Plan('fwd')
+        self.lane = 0        # lane given to forward launches (1 = side stream, see Plan.run)
         self.tape = []       # backward closures in forward order
         self.keep = []       # every buffer referenced by raw pointer from a descriptor must outlive the plans
 
@@ -566,7 +567,7 @@ class Builder(object):
             layer.fwd_rows_used = True
         plan.keep.append(d)
         plan.keep += [srcs, out, outf, addf, post_add, layer]
-        plan.add('cis_conv_igemm', C.byref(d), flops=2.0 * N * OH * OW * layer.k * layer.k * layer.cin * layer.cout)
+        plan.add('cis_conv_igemm', C.byref(d), flops=2.0 * N * OH * OW * layer.k * layer.k * layer.cin * layer.cout, lane=self.lane)
         if layer.tag:
             self.tape.append(lambda bp, m, L=layer, S=list(srcs), O=out, P=post_add: self._conv_bwd(bp, m, L, S, O, P))
         return out

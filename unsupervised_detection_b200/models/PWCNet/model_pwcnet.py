@@ -81,6 +81,7 @@ class ModelPWCNet(object):
         # ---- feature pyramids (shared weights; frame 1 features land inside the level buffers)
         c1, c2 = [None], [None]
         for pyr, x, first in ((c1, img1_8, True), (c2, img2_8, False)):
+            B.lane = 0 if first else 1       # the two pyramids are independent: frame 2 runs on the side stream
             for l in range(1, PYR_LVLS + 1):
                 f = NUM_CHANN[l]
                 x = B.conv(self.L['featpyr/conv%da' % l], [x])
@@ -90,6 +91,8 @@ class ModelPWCNet(object):
                     out = Act(N, hs[l][0], hs[l][1], f, dev, buf=E[l], c_off=C1_OFF, name='c1_%d' % l)
                 x = B.conv(self.L['featpyr/conv%db' % l], [x], out=out)
                 pyr.append(x)
+        B.lane = 0
+        P.join()
         self.c1, self.c2 = c1, c2
         B.hold((c1, c2, E))
         up_flow_f32 = None

@@ -90,11 +90,29 @@ class RecoverNet(object):
     def all_layers(self):
         return list(self.layers.values())
 
+    def build_a_encoder(self, B, img8):
+        """The image encoder depends only on the image: it can be issued early, on the side stream, concurrently with the
+        generator (its results are first needed by the decoder concats)."""
+        L = self.layers
+        d = {}
+        x = B.conv(L['aconv1'], [img8]); d['1'] = x
+        x = B.conv(L['aconv2'], [x]); d['2'] = x
+        x = B.conv(L['aconv3'], [x])
+        x = B.conv(L['aconv31'], [x]); d['31'] = x
+        x = B.conv(L['aconv4'], [x])
+        x = B.conv(L['aconv41'], [x]); d['41'] = x
+        x = B.conv(L['aconv5'], [x])
+        x = B.conv(L['aconv51'], [x]); d['51'] = x
+        x = B.conv(L['aconv6'], [x]); d['6'] = x
+        self.a_feats = d
+        return d
+
     def build(self, B, img8, flow_in, flow1_out, ncalls=3):
         """img8: Act [B,H,W,8] (image, 3 real channels); flow_in: Act [ncalls*B,H,W,8] = [flow_masked(2), ones, 1-mask] per call
         (nets.py:50-53); flow1_out: fp32 [ncalls*B,h1,w1,2] receives `flow1` (the final x2 resize is fused into the loss)."""
         L = self.layers
         nB = img8.N
+        self._enc = None
 
         def enc(pre, x):
             d = {}
@@ -108,7 +126,7 @@ class RecoverNet(object):
             x = B.conv(L[pre + 'conv51'], [x]); d['51'] = x
             x = B.conv(L[pre + 'conv6'], [x]); d['6'] = x
             return d
-        a = enc('a', img8)
+        a = self.a_feats if getattr(self, 'a_feats', None) is not None else enc('a', img8)
         b = enc('b', flow_in)
         if ncalls > 1:
             a = {k: v.alias(nB) for k, v in a.items()}

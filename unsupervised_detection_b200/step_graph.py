@@ -67,6 +67,9 @@ class CISGraph(object):
         P.add('cis_pack_generator_input', self.image.data_ptr(), self.flow.data_ptr(), self.stats.data_ptr(), B, hw, self.gen_in.ptr)
         P.add('cis_pack_f32_to_bf16', self.image.data_ptr(), B * hw, 3, 0.0, self.img8.ptr, 8, 0)
         self.mask = f32(B, H, W, 1)
+        bld.lane = 1
+        self.rec.build_a_encoder(bld, self.img8)        # side stream, overlaps the generator
+        bld.lane = 0
         self.gen.build(bld, self.gen_in, self.mask)
         # mask (x) flow -> recover inputs for the 3 calls (adversarial_learner.py:107-131)
         self.rec_in = Act(3 * B, H, W, 4, device, name='rec_in', dep={'G'})
@@ -87,6 +90,7 @@ class CISGraph(object):
         h1, w1 = -(-H // 2), -(-W // 2)
         self.h1, self.w1 = h1, w1
         self.flow1 = f32(3 * B, h1, w1, 2)
+        P.join()
         self.rec.build(bld, self.img8, self.rec_in, self.flow1)
         # ---- losses (adversarial_learner.py:141-204)
         self.sums = torch.zeros(B, 5, dtype=torch.float64, device=device)

@@ -789,8 +789,8 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   if (BS > kHaloMaxBStages) BS = kHaloMaxBStages;
   if (BS > steps) BS = steps;                     // ... but never deeper than the number of pipeline steps
   // prefer several co-resident CTAs per SM (their load / MMA / epilogue phases overlap) over a very deep ring
-  const int budgets[3] = {56 * 1024, 74 * 1024, 112 * 1024};
-  for (int b = 0; b < 3; ++b) {
+  const int budgets[5] = {36 * 1024, 44 * 1024, 56 * 1024, 74 * 1024, 112 * 1024};
+  for (int b = 0; b < 5; ++b) {
     const int fit = (budgets[b] - fixed) / (BN * 128);
     if (fit >= 3 || (fit >= steps && fit >= 1)) { if (BS > fit) BS = fit; break; }
   }

@@ -75,6 +75,12 @@ typedef struct {
   int32_t MT;        /* 1..4 stacked M tiles (MT*BN <= 512 TMEM columns) */
   int32_t hoy, hox;  /* halo origin relative to the tile origin (phase units, <= 0) */
   int32_t ey, ex;    /* halo extent beyond the tile (max tap offset) */
+  /* split-K for launches that would otherwise occupy a handful of SMs: grid.z = splits CTAs share one output tile; each writes
+   * its partial fp32 tile to a private slice of sk_scratch, the last CTA to arrive (ticket in sk_counters) sums the slices in a
+   * fixed order (deterministic), applies the epilogue and resets the ticket. */
+  int32_t splits;        /* 0/1 = off */
+  float* sk_scratch;     /* >= tiles * splits * 128 * BN floats (tiles = grid.x * grid.y * MT); need not be initialised */
+  int32_t* sk_counters;  /* zero-initialised, >= grid.x * grid.y ints */
 } CisConv;
 
 /* Weight gradient of the same convolution: dWp[co][(t,c)] += sum_rows g[row][co] * A[row][(t,c)]  (fp32, split-K atomics).

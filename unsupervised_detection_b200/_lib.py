@@ -31,7 +31,8 @@ class CisConv(C.Structure):
                 ('add_post', C.c_void_p), ('add_post_pitch', C.c_int32), ('add_post_coff', C.c_int32),
                 ('mode', C.c_int32),
                 ('halo', C.c_int32), ('dil', C.c_int32), ('MT', C.c_int32), ('hoy', C.c_int32), ('hox', C.c_int32),
-                ('ey', C.c_int32), ('ex', C.c_int32)]
+                ('ey', C.c_int32), ('ex', C.c_int32),
+                ('splits', C.c_int32), ('sk_scratch', C.c_void_p), ('sk_counters', C.c_void_p)]
 
 
 class CisWgrad(C.Structure):

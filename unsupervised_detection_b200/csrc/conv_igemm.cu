@@ -107,6 +107,173 @@ __device__ __forceinline__ void epi_chunk(const CisConv& p, float (&v)[16], cons
   }
 }
 
+
+
+// Latency-batched epilogue for NC x 16 accumulator columns of one row: residual loads are issued first, then all TMEM loads,
+// ONE wait, then the arithmetic and the stores (the per-chunk version paid a full TMEM + global-load round trip per 16 columns).
+template <int NC>
+__device__ __forceinline__ void epi_group(const CisConv& p, const uint32_t taddr, const int cg0, const size_t dpix, const bool valid,
+                                          const float* __restrict__ sbias) {
+  // one residual operand per launch: add_pre (gradient accumulation, before the activation) or add_post (skip, after it)
+  uint4 rres[NC][2];
+  const bool is_pre = p.add_pre != nullptr;
+  const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(is_pre ? p.add_pre : p.add_post);
+  const bool has_res = valid && rp != nullptr;
+  const size_t roff = has_res ? (dpix * (is_pre ? p.add_pre_pitch : p.add_post_pitch) + (is_pre ? p.add_pre_coff : p.add_post_coff)) : 0;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int cg = cg0 + 16 * c;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      rres[c][h] = make_uint4(0, 0, 0, 0);
+      if (has_res && cg + 8 * h < p.out_ch) rres[c][h] = __ldg(reinterpret_cast<const uint4*>(rp + roff + cg) + h);
+    }
+  }
+  uint32_t raw[NC][16];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) tmem_ld16_nowait(taddr + 16 * c, raw[c]);
+  tmem_ld_wait();
+  if (!valid) return;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int cg = cg0 + 16 * c;
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[c][e]);
+    if (p.bias) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] += sbias[cg - cg0 + e + (cg0 & 127)];
+    }
+    if (is_pre) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t w4[4] = {rres[c][h].x, rres[c][h].y, rres[c][h].z, rres[c][h].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[h * 8 + 2 * e] += bf16lo(w4[e]);
+          v[h * 8 + 2 * e + 1] += bf16hi(w4[e]);
+        }
+      }
+    }
+    if (p.addf_pre) {
+      for (int e = 0; e < 16 && cg + e < p.outf_ch; ++e) v[e] += __ldg(p.addf_pre + dpix * p.addf_pitch + p.addf_coff + cg + e);
+    }
+    if (p.act == CIS_ACT_ELU) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.f ? v[e] : expm1f(v[e]);
+    } else if (p.act == CIS_ACT_LEAKY) {
+#pragma unroll
+      for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * p.alpha;
+    }
+    if (!is_pre) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t w4[4] = {rres[c][h].x, rres[c][h].y, rres[c][h].z, rres[c][h].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          v[h * 8 + 2 * e] += bf16lo(w4[e]);
+          v[h * 8 + 2 * e + 1] += bf16hi(w4[e]);
+        }
+      }
+    }
+    if (p.mode == 1) {
+      if (cg == 0) p.outf[dpix] = 1.f / (1.f + __expf(-(v[0] - v[1]) * 0.1f));
+      continue;
+    }
+    if (p.out && cg < p.out_ch) {
+      __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + dpix * p.out_pitch + p.out_coff + cg;
+      if (((p.out_ch | p.out_coff | p.out_pitch) & 7) == 0) {
+        *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        if (p.out_ch - cg >= 16)
+          *reinterpret_cast<uint4*>(o + 8) =
+              make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+      } else {
+        for (int e = 0; e < 16 && cg + e < p.out_ch; ++e) o[e] = __float2bfloat16(v[e]);
+      }
+    }
+    if (p.outf && cg < p.outf_ch) {
+      float* o = p.outf + dpix * p.outf_pitch + p.outf_coff + cg;
+      for (int e = 0; e < 16 && cg + e < p.outf_ch; ++e) o[e] = v[e];
+    }
+  }
+}
+// all BN columns of one row, in groups of at most 64 columns (register budget)
+template <int BN>
+__device__ __forceinline__ void epi_row(const CisConv& p, const uint32_t t_row, const int cbase, const size_t dpix, const bool valid,
+                                        const float* __restrict__ sbias) {
+  if constexpr (BN >= 32) {
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) epi_group<2>(p, t_row + c0, cbase + c0, dpix, valid, sbias);
+  } else {
+    epi_group<1>(p, t_row, cbase, dpix, valid, sbias);
+  }
+}
+
+// ---- split-K fix-up (single launch): every CTA of a tile adds its partial accumulator to a zero-initialised fp32 scratch tile,
+// takes a ticket, and the last one reads the full sums back (re-zeroing scratch and ticket for the next launch).
+__device__ __forceinline__ void named_bar_sync_128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ float ld_cg(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+template <int BN>
+__device__ __forceinline__ void splitk_store_partial(float* slice, uint32_t t_row, int row) {
+  // slice = this split's private [128][BN] fp32 tile: plain 16-byte stores, no atomics, fixed summation order later
+#pragma unroll 1
+  for (int c0 = 0; c0 < BN; c0 += 16) {
+    float v[16];
+    tmem_ld16(t_row + c0, v);
+    float4* o = reinterpret_cast<float4*>(slice + (size_t)row * BN + c0);
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+    o[2] = make_float4(v[8], v[9], v[10], v[11]);
+    o[3] = make_float4(v[12], v[13], v[14], v[15]);
+  }
+}
+// sum of the nsplit private slices of one tile for (row, c0..c0+15); loads are plain L2 loads (__ldcg) issued in batches of
+// 4 slices x 4 float4 so their latencies overlap (a volatile-asm version serialised ~150 round trips per thread: ncu r01d)
+template <int BN>
+__device__ __forceinline__ void splitk_reduce16(const float* tile0, int nsplit, int row, int c0, float* v) {
+#pragma unroll
+  for (int e = 0; e < 16; ++e) v[e] = 0.f;
+  const float4* q0 = reinterpret_cast<const float4*>(tile0 + (size_t)row * BN + c0);
+  const size_t zstride = (size_t)kBM * BN / 4;
+  int z = 0;
+  for (; z + 4 <= nsplit; z += 4) {
+    float4 t[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int h = 0; h < 4; ++h) t[u][h] = __ldcg(q0 + (size_t)(z + u) * zstride + h);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        v[4 * h] += t[u][h].x; v[4 * h + 1] += t[u][h].y; v[4 * h + 2] += t[u][h].z; v[4 * h + 3] += t[u][h].w;
+      }
+  }
+  for (; z < nsplit; ++z) {
+    float4 t[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) t[h] = __ldcg(q0 + (size_t)z * zstride + h);
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      v[4 * h] += t[h].x; v[4 * h + 1] += t[h].y; v[4 * h + 2] += t[h].z; v[4 * h + 3] += t[h].w;
+    }
+  }
+}
+// returns true for the last-arriving CTA of the tile (uniform over the 128 epilogue threads)
+__device__ __forceinline__ bool splitk_ticket(int* counter, int splits, int tid, int* s_flag) {
+  __threadfence();
+  named_bar_sync_128();
+  if (tid == 0) *s_flag = (atomicAdd(counter, 1) == splits - 1) ? 1 : 0;
+  named_bar_sync_128();
+  const bool last = *s_flag != 0;
+  if (last) __threadfence();
+  return last;
+}
+
 template <int BN>
 struct FwdCfg {
   static constexpr int kStages = (BN == 128) ? 3 : 4;
@@ -141,8 +308,15 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
     return s;
   }();
   const int k_chunks = p.ntaps * m_chunks;
-  const int nkb = p.K_pad / kBK;
+  const int nkb_all = p.K_pad / kBK;
+  const int nsplit = p.splits > 1 ? p.splits : 1;
+  const int kper = (nkb_all + nsplit - 1) / nsplit;
+  const int kb_lo = blockIdx.z * kper;
+  const int nkb = min(kper, nkb_all - kb_lo);     // host guarantees nkb >= 1 for every split
   const int ny = blockIdx.y;
+  __shared__ int s_flag;
+  __shared__ float s_bias[BN];
+  if (tid < BN) s_bias[tid] = p.bias ? p.bias[ny * BN + tid] : 0.f;
 
   if (tid < p.ntaps) {
     s_dh[tid] = p.dh[tid];
@@ -201,7 +375,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
       const uint32_t ph = (uint32_t)((kb / S) & 1);
       mbar_wait(bar_empty + 8 * s, ph ^ 1u);
       // ---- A: decode this thread's K chunk -> (tap, source, channel chunk)
-      const int q = kb * 8 + j;
+      const int q = (kb_lo + kb) * 8 + j;
       const bool kvalid = q < k_chunks;
       int t = 0, c = 0;
       if (kvalid) {
@@ -230,7 +404,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
       // ---- B: packed weights, rows rl + 16 i
       const uint32_t b_dst = b_base + s * Cfg::kBStage + rl * 128 + sw_off;
 #pragma unroll
-      for (int i = 0; i < BN / 16; ++i) cp_async16(b_dst + i * 16 * 128, wrow + (size_t)i * 16 * p.K_pad + kb * kBK, 16u);
+      for (int i = 0; i < BN / 16; ++i) cp_async16(b_dst + i * 16 * 128, wrow + (size_t)i * 16 * p.K_pad + (kb_lo + kb) * kBK, 16u);
       cp_async_mbar_arrive_noinc(bar_full + 8 * s);
     }
 
@@ -250,12 +424,21 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
     }
     const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
     const int cbase = ny * BN;
+    if (nsplit > 1) {
+      const int tile_id = blockIdx.x * gridDim.y + ny;
+      float* tile0 = p.sk_scratch + (size_t)tile_id * nsplit * kBM * BN;
+      splitk_store_partial<BN>(tile0 + (size_t)blockIdx.z * kBM * BN, t_row, row);
+      if (splitk_ticket(p.sk_counters + tile_id, nsplit, tid, &s_flag)) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      float v[16];
-      tmem_ld16(t_row + c0, v);
-      if (!valid) continue;
-      epi_chunk(p, v, cbase + c0, dpix);
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          float v[16];
+          splitk_reduce16<BN>(tile0, nsplit, row, c0, v);
+          if (valid) epi_chunk(p, v, cbase + c0, dpix);
+        }
+        if (tid == 0) p.sk_counters[tile_id] = 0;
+      }
+    } else {
+      epi_row<BN>(p, t_row, cbase, dpix, valid, s_bias);
     }
   } else {
     // ------------------------------------------------------------------ MMA issuer (warp 4)
@@ -329,8 +512,15 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   const int ny = blockIdx.y;
   int m_chunks = 0;
   for (int i = 0; i < p.nsrc; ++i) m_chunks += p.src[i].chunks;
-  const int nchunks = (m_chunks + 7) / 8;  // 64-channel chunks
+  const int nchunks_all = (m_chunks + 7) / 8;  // 64-channel chunks
+  const int nsplit = p.splits > 1 ? p.splits : 1;
+  const int cper = (nchunks_all + nsplit - 1) / nsplit;
+  const int cc_lo = blockIdx.z * cper;
+  const int nchunks = min(cper, nchunks_all - cc_lo);   // chunks handled by this CTA (host guarantees >= 1)
   const int cin8 = m_chunks * 8;
+  __shared__ int s_flag;
+  __shared__ float s_bias[BN];
+  if (tid < BN) s_bias[tid] = p.bias ? p.bias[ny * BN + tid] : 0.f;
   const uint32_t ncols = (MT * BN <= 32) ? 32u : (MT * BN <= 64) ? 64u : (MT * BN <= 128) ? 128u : (MT * BN <= 256) ? 256u : 512u;
 
   if (tid < p.ntaps) {
@@ -381,7 +571,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
         for (int cc = 0; cc < nchunks; ++cc) {
           const int hs = cc % NHS;
           mbar_wait(bar_hempty + 8 * hs, (uint32_t)(((cc / NHS) & 1) ^ 1));
-          int c = cc * 8, si = 0;
+          int c = (cc_lo + cc) * 8, si = 0;
           while (si < p.nsrc - 1 && c >= s_src[si].chunks) {
             c -= s_src[si].chunks;
             ++si;
@@ -399,11 +589,11 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
       for (int cc = 0; cc < nchunks; ++cc) {
         const int hs = cc % NHS;
         mbar_wait(bar_hempty + 8 * hs, (uint32_t)(((cc / NHS) & 1) ^ 1));
-        const int rem = m_chunks - cc * 8;                 // valid 16-byte chunks in this 64-channel chunk
+        const int rem = m_chunks - (cc_lo + cc) * 8;       // valid 16-byte chunks in this 64-channel chunk
         const int nk16 = rem >= 8 ? 4 : (rem + 1) / 2;     // K=16 MMA groups actually issued
         const bool need = j < 2 * nk16;
         const bool cvalid = j < rem;
-        int c = cc * 8 + j, si = 0;
+        int c = (cc_lo + cc) * 8 + j, si = 0;
         if (cvalid) {
           while (si < p.nsrc - 1 && c >= s_src[si].chunks) {
             c -= s_src[si].chunks;
@@ -430,7 +620,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     }
     if (tid == 64) {
       // weights: pre-swizzled [n-tile][chunk][tap] tiles of BN x 128 B (cis_pack_weights_tiled) -> ONE bulk copy per pipeline step
-      const uint8_t* wt = reinterpret_cast<const uint8_t*>(p.wpack) + (size_t)ny * nchunks * p.ntaps * kBStage;
+      const uint8_t* wt = reinterpret_cast<const uint8_t*>(p.wpack) + ((size_t)ny * nchunks_all + cc_lo) * p.ntaps * kBStage;
       int it = 0;
       for (int cc = 0; cc < nchunks; ++cc) {
         for (int t = 0; t < p.ntaps; ++t, ++it) {
@@ -448,19 +638,39 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     tc_fence_after();
     const int r = warp * 32 + lane;
     const int cbase = ny * BN;
-    for (int m = 0; m < MT; ++m) {
-      const int gy = ty * 16 * MT + 16 * m + (r >> 3), gx = tx * 8 + (r & 7);
-      const int oy = pa + d * gy, ox = pb + d * gx;
-      const bool valid = oy < p.OH && ox < p.OW;
-      const size_t dpix = valid ? ((size_t)(n * p.DH + oy * p.osh + p.oa) * p.DW + ox * p.osw + p.ob) : 0;
-      const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16) + m * BN;
+    const int tile_id = blockIdx.x * gridDim.y + ny;
+    bool last = true;
+    if (nsplit > 1) {
+      for (int m = 0; m < MT; ++m)
+        splitk_store_partial<BN>(p.sk_scratch + (((size_t)tile_id * MT + m) * nsplit + blockIdx.z) * kBM * BN,
+                                 tmem + ((uint32_t)(warp * 32) << 16) + m * BN, r);
+      last = splitk_ticket(p.sk_counters + tile_id, nsplit, tid, &s_flag);
+    }
+    if (last) {
+      for (int m = 0; m < MT; ++m) {
+        const int gy = ty * 16 * MT + 16 * m + (r >> 3), gx = tx * 8 + (r & 7);
+        const int oy = pa + d * gy, ox = pb + d * gx;
+        const bool valid = oy < p.OH && ox < p.OW;
+        const size_t dpix = valid ? ((size_t)(n * p.DH + oy * p.osh + p.oa) * p.DW + ox * p.osw + p.ob) : 0;
+        const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16) + m * BN;
+        const float* tile0 = nsplit > 1 ? p.sk_scratch + ((size_t)tile_id * MT + m) * nsplit * kBM * BN : nullptr;
+        if (nsplit <= 1) {
+          epi_row<BN>(p, t_row, cbase, dpix, valid, s_bias);
+          continue;
+        }
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 16) {
-        float v[16];
-        tmem_ld16(t_row + c0, v);
-        if (!valid) continue;
-        epi_chunk(p, v, cbase + c0, dpix);
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          float v[16];
+          if (nsplit > 1) {
+            splitk_reduce16<BN>(tile0, nsplit, r, c0, v);
+          } else {
+            tmem_ld16(t_row + c0, v);
+          }
+          if (!valid) continue;
+          epi_chunk(p, v, cbase + c0, dpix);
+        }
       }
+      if (nsplit > 1 && tid == 0) p.sk_counters[tile_id] = 0;
     }
   } else {
     // ------------------------------------------------------------------ MMA issuer
@@ -470,7 +680,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     int it = 0;
     for (int cc = 0; cc < nchunks; ++cc) {
       const int hs = cc % NHS;
-      const int rem = m_chunks - cc * 8;
+      const int rem = m_chunks - (cc_lo + cc) * 8;
       const int nk16 = rem >= 8 ? 4 : (rem + 1) / 2;
       mbar_wait(bar_hfull + 8 * hs, (uint32_t)((cc / NHS) & 1));
       CIS_CONSUMER_PROXY_FENCE();
@@ -741,7 +951,12 @@ static int launch_fwd(const CisConv* d, cudaStream_t st) {
     attr_set = true;
   }
   const int M = d->N * d->OH * d->OW;
-  dim3 grid((M + kBM - 1) / kBM, d->n_tiles);
+  int splits = d->splits > 1 ? d->splits : 1;
+  if (splits > 1) {
+    const int nkb = d->K_pad / kBK, per = (nkb + splits - 1) / splits;
+    if (!d->sk_scratch || !d->sk_counters || (splits - 1) * per >= nkb) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm: bad split-K setup");
+  }
+  dim3 grid((M + kBM - 1) / kBM, d->n_tiles, splits);
   conv_igemm_kernel<BN><<<grid, kThreads, Cfg::kSmem, st>>>(*d);
   return cis_check_launch("conv_igemm");
 }
@@ -782,9 +997,9 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   int chunks = 0;
   for (int i = 0; i < d->nsrc; ++i) chunks += d->src[i].chunks;
   const int nchunks = (chunks + 7) / 8;
-  const int nhs = nchunks > 1 ? 2 : 1;            // halo stages: double-buffer only when there is a next chunk to prefetch
+  const int steps = ((nchunks + (d->splits > 1 ? d->splits : 1) - 1) / (d->splits > 1 ? d->splits : 1)) * d->ntaps;
+  const int nhs = steps > d->ntaps ? 2 : 1;         // halo stages: double-buffer only when there is a next chunk to prefetch
   const int fixed = nhs * halo_stage + HP * 4 + 1024;
-  const int steps = nchunks * d->ntaps;
   int BS = (226 * 1024 - fixed) / (BN * 128);     // as deep a weight ring as fits ...
   if (BS > kHaloMaxBStages) BS = kHaloMaxBStages;
   if (BS > steps) BS = steps;                     // ... but never deeper than the number of pipeline steps
@@ -805,7 +1020,12 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   const int dd = d->dil;
   const int Hp0 = (d->OH + dd - 1) / dd, Wp0 = (d->OW + dd - 1) / dd;
   const int tiles = ((Wp0 + 7) / 8) * ((Hp0 + 16 * d->MT - 1) / (16 * d->MT));
-  dim3 grid(tiles * dd * dd * d->N, d->n_tiles);
+  int splits = d->splits > 1 ? d->splits : 1;
+  if (splits > 1) {
+    const int per = (nchunks + splits - 1) / splits;
+    if (!d->sk_scratch || !d->sk_counters || (splits - 1) * per >= nchunks) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm(halo): bad split-K setup");
+  }
+  dim3 grid(tiles * dd * dd * d->N, d->n_tiles, splits);
   // TMA halo path: undilated, every concat source except the last a multiple of 64 channels (a chunk never straddles sources)
   HaloMaps maps;
   int use_tma = (d->dil == 1 && Wh <= 256 && Hh <= 256) ? 1 : 0;

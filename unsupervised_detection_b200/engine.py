@@ -202,6 +202,36 @@ def _pow2_cols(c):
     return 1024
 
 
+SPLITK = False   # measured r01: per-CTA fixed latencies dominate the low-resolution layers; splitting K made them slower
+
+
+def setup_splitk(d, device, keep):
+    """Launches whose grid would cover well under the 148 SMs (low-resolution pyramid levels) split their K loop over grid.z;
+    see CisConv.splits.  Scratch and ticket buffers are per launch (launches on different lanes may overlap)."""
+    if not SPLITK:
+        return
+    m_chunks = sum(d.src[i].chunks for i in range(d.nsrc))
+    if d.halo:
+        Hp0, Wp0 = -(-d.OH // d.dil), -(-d.OW // d.dil)
+        tiles = (-(-Wp0 // 8)) * (-(-Hp0 // (16 * d.MT))) * d.dil * d.dil * d.N
+        ncta, units, min_units, mt = tiles * d.n_tiles, -(-m_chunks // 8), 1, d.MT
+    else:
+        ncta, units, min_units, mt = (-(-(d.N * d.OH * d.OW) // 128)) * d.n_tiles, d.K_pad // 64, 4, 1
+    if ncta >= 100:
+        return
+    splits = min(units // min_units, -(-2 * NUM_SMS // ncta))
+    if splits < 2:
+        return
+    per = -(-units // splits)
+    splits = -(-units // per)
+    if splits < 2:
+        return
+    sc = torch.empty(ncta * mt * splits * 128 * d.BN, dtype=torch.float32, device=device)
+    ct = torch.zeros(ncta, dtype=torch.int32, device=device)
+    keep += [sc, ct]
+    d.splits, d.sk_scratch, d.sk_counters = splits, sc.data_ptr(), ct.data_ptr()
+
+
 def setup_halo(d, taps, dil, n_tiles):
     """Switch a stride-1 gather descriptor to the halo-resident kernel when it pays off: taps become offsets relative to the
     halo origin in units of `dil`, MT (stacked 16x8 tiles per CTA) is chosen by a wave/overhead model."""
@@ -565,6 +595,7 @@ class Builder(object):
             layer.fwd_rows_used = getattr(layer, 'fwd_rows_used', False)
         else:
             layer.fwd_rows_used = True
+        setup_splitk(d, self.device, plan.keep)
         plan.keep.append(d)
         plan.keep += [srcs, out, outf, addf, post_add, layer]
         plan.add('cis_conv_igemm', C.byref(d), flops=2.0 * N * OH * OW * layer.k * layer.k * layer.cin * layer.cout, lane=self.lane)
@@ -661,6 +692,7 @@ class Builder(object):
                 pk['rows_used'] = pk.get('rows_used', False)
             else:
                 pk['rows_used'] = True
+            setup_splitk(d, self.device, bp.keep)
             bp.keep.append(d)
             bp.add('cis_conv_igemm', C.byref(d), flops=2.0 * nb * oh * ow * len(pk['taps']) * layer.cin * layer.cout)
         if single:
@@ -748,6 +780,7 @@ class Builder(object):
                 pk['rows_used'] = pk.get('rows_used', False)
             else:
                 pk['rows_used'] = True
+            setup_splitk(d, self.device, plan.keep)
             plan.keep.append(d)
             plan.keep += [src, out, outf, layer]
             plan.add('cis_conv_igemm', C.byref(d), flops=2.0 * N * H * W * len(pk['taps']) * layer.cin * layer.cout)

@@ -624,7 +624,8 @@ class Builder(object):
         if layer.tag == mode:   # weight + bias gradients
             if not hasattr(layer, 'dwp'):
                 # TMA operand path (8x8 pixel tiles) for stride-1 layers whose concat sources are 64-channel aligned
-                layer.wg_tma = bool(WGRAD_TMA and layer.stride == 1 and all(s_.C8 % 64 == 0 for s_ in srcs[:-1]))
+                layer.wg_tma = bool(WGRAD_TMA and layer.stride == 1 and len(layer.in_chanmap) >= 32 and
+                                    all(s_.C8 % 64 == 0 for s_ in srcs[:-1]))   # thin inputs: per-tap 64-channel padding would waste the loads
                 if layer.wg_tma:
                     cin8 = len(layer.in_chanmap)
                     nch64 = -(-cin8 // 64)

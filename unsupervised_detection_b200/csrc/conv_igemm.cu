@@ -14,6 +14,8 @@
 #include "../../include/cis_b200.h"
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 // cp.async (LDGSTS) data is published to the MMA warp through the mbarrier that cp.async.mbarrier.arrive.noinc signals; the
 // tensor core then reads it through the async proxy.  A consumer-side fence.proxy.async per pipeline step costs > 1000 clk of
@@ -718,6 +720,175 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   if (warp == 4) tmem_dealloc_dyn(tmem, ncols);
 }
 
+
+// ======================================================================================================= persistent halo conv
+// Same math as conv_halo_kernel (TMA halo path only), restructured as a persistent, fully warp-specialised pipeline so the
+// per-tile latency chain (halo fetch -> MMAs -> TMEM read-back -> stores) of one tile overlaps the next tiles:
+//   warp 0: halo TMA producer | warp 1: weight-tile bulk-copy producer | warp 2: MMA issuer | warp 3: TMEM owner
+//   warps 4-7: epilogue (TMEM lane quarter = warp % 4), two accumulator stages in TMEM (full/empty mbarriers).
+// Every role walks the same static work list  w = blockIdx.x, blockIdx.x + gridDim.x, ...  of output tiles.
+static constexpr int kPThreads = 256;
+
+template <int BN>
+__global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __grid_constant__ CisConv p, const int halo_stage_bytes,
+                                                                       const int BS, const int NHS, const int AS,
+                                                                       const __grid_constant__ HaloMaps maps) {
+  constexpr int kBStage = BN * 128;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[2 * 3 + 2 * kHaloMaxBStages + 4];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_dh[CIS_MAX_TAPS], s_dw[CIS_MAX_TAPS];
+  __shared__ float s_bias[BN];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int MT = p.MT;
+  const int Wh = 8 + p.ex, Hh = 16 * MT + p.ey, HP = Wh * Hh;
+  const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t h_base = tile_base, b_base = tile_base + NHS * halo_stage_bytes;
+  const uint32_t bar_hfull = smem_u32(&bars[0]), bar_hempty = smem_u32(&bars[3]);
+  const uint32_t bar_bfull = smem_u32(&bars[6]), bar_bempty = smem_u32(&bars[6 + kHaloMaxBStages]);
+  const uint32_t bar_tfull = smem_u32(&bars[6 + 2 * kHaloMaxBStages]), bar_tempty = smem_u32(&bars[8 + 2 * kHaloMaxBStages]);
+
+  const int tiles_x = (p.OW + 7) / 8, tiles_y = (p.OH + 16 * MT - 1) / (16 * MT);
+  const int total = tiles_x * tiles_y * p.N;
+  int m_chunks = 0;
+  for (int i = 0; i < p.nsrc; ++i) m_chunks += p.src[i].chunks;
+  const int nchunks = (m_chunks + 7) / 8;
+  const uint32_t acc_cols = (uint32_t)(MT * BN);
+  const uint32_t want = acc_cols * AS;
+  const uint32_t ncols = want <= 32 ? 32u : want <= 64 ? 64u : want <= 128 ? 128u : want <= 256 ? 256u : 512u;
+
+  if (tid < p.ntaps) {
+    s_dh[tid] = p.dh[tid];
+    s_dw[tid] = p.dw[tid];
+  }
+  if (tid < BN) s_bias[tid] = p.bias ? p.bias[tid] : 0.f;
+  if (warp == 3) {
+    if (lane == 0) {
+      for (int s = 0; s < NHS; ++s) {
+        mbar_init(bar_hfull + 8 * s, 1);
+        mbar_init(bar_hempty + 8 * s, 1);
+      }
+      for (int s = 0; s < BS; ++s) {
+        mbar_init(bar_bfull + 8 * s, 1);
+        mbar_init(bar_bempty + 8 * s, 1);
+      }
+      for (int s = 0; s < AS; ++s) {
+        mbar_init(bar_tfull + 8 * s, 1);
+        mbar_init(bar_tempty + 8 * s, 4);   // one arrival per epilogue warp
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_dyn(smem_u32(&tmem_slot), ncols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ halo producer
+    if (lane == 0) {
+      int hc = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        const int tx = w % tiles_x, r1 = w / tiles_x, ty = r1 % tiles_y, n = r1 / tiles_y;
+        for (int cc = 0; cc < nchunks; ++cc, ++hc) {
+          const int hs = hc % NHS;
+          mbar_wait(bar_hempty + 8 * hs, (uint32_t)(((hc / NHS) & 1) ^ 1));
+          int c = cc * 8, si = 0;
+          while (si < p.nsrc - 1 && c >= p.src[si].chunks) {
+            c -= p.src[si].chunks;
+            ++si;
+          }
+          int nmod = p.src[0].n_mod;
+          if (si == 1) nmod = p.src[1].n_mod;
+          if (si == 2) nmod = p.src[2].n_mod;
+          if (si == 3) nmod = p.src[3].n_mod;
+          mbar_expect_tx(bar_hfull + 8 * hs, (uint32_t)(HP * 128));
+          tma_load_4d(h_base + hs * halo_stage_bytes, &maps.m[si], bar_hfull + 8 * hs, c * 8, tx * 8 + p.hox, ty * 16 * MT + p.hoy,
+                      nmod ? (n % nmod) : n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ weight producer
+    if (lane == 0) {
+      const uint8_t* wt = reinterpret_cast<const uint8_t*>(p.wpack);
+      const int per_tile = nchunks * p.ntaps;
+      int bc = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        for (int it = 0; it < per_tile; ++it, ++bc) {
+          const int bs = bc % BS;
+          mbar_wait(bar_bempty + 8 * bs, (uint32_t)(((bc / BS) & 1) ^ 1));
+          mbar_expect_tx(bar_bfull + 8 * bs, kBStage);
+          bulk_g2s(b_base + bs * kBStage, wt + (size_t)it * kBStage, kBStage, bar_bfull + 8 * bs);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
+    const uint32_t ahi = desc_hi((uint32_t)(Wh * 128)), bhi = desc_hi(1024);
+    const uint32_t a_mstep = (uint32_t)(16 * Wh * 128) >> 4;
+    int hc = 0, bc = 0, wi = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++wi) {
+      const int as = wi % AS;
+      mbar_wait(bar_tempty + 8 * as, (uint32_t)(((wi / AS) & 1) ^ 1));
+      tc_fence_after();
+      const uint32_t tacc = tmem + as * acc_cols;
+      for (int cc = 0; cc < nchunks; ++cc, ++hc) {
+        const int hs = hc % NHS;
+        const int rem = m_chunks - cc * 8;
+        const int nk16 = rem >= 8 ? 4 : (rem + 1) / 2;
+        mbar_wait(bar_hfull + 8 * hs, (uint32_t)((hc / NHS) & 1));
+        const uint32_t hsrc = h_base + hs * halo_stage_bytes;
+        for (int t = 0; t < p.ntaps; ++t, ++bc) {
+          const int bs = bc % BS;
+          mbar_wait(bar_bfull + 8 * bs, (uint32_t)((bc / BS) & 1));
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t blo = desc_lo(b_base + bs * kBStage, 16);
+            uint32_t alo = desc_lo(hsrc + (uint32_t)((s_dh[t] * Wh + s_dw[t]) * 128), 16);
+            const uint32_t acc0 = (uint32_t)((cc | t) != 0);
+            for (int m = 0; m < MT; ++m, alo += a_mstep) {
+              const uint32_t td = tacc + m * BN;
+              for (int k = 0; k < nk16; ++k) umma_bf16_lh(td, alo + 2 * k, ahi, blo + 2 * k, bhi, idesc, k ? 1u : acc0);
+            }
+            umma_commit(bar_bempty + 8 * bs);
+            if (t == p.ntaps - 1) umma_commit(bar_hempty + 8 * hs);
+            if (cc == nchunks - 1 && t == p.ntaps - 1) umma_commit(bar_tfull + 8 * as);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue (warps 4..7 -> TMEM lanes 32*(warp-4)..)
+    const int q = warp - 4;
+    const int r = q * 32 + lane;
+    int wi = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++wi) {
+      const int tx = w % tiles_x, r1 = w / tiles_x, ty = r1 % tiles_y, n = r1 / tiles_y;
+      const int as = wi % AS;
+      mbar_wait(bar_tfull + 8 * as, (uint32_t)((wi / AS) & 1));
+      tc_fence_after();
+      for (int m = 0; m < MT; ++m) {
+        const int oy = ty * 16 * MT + 16 * m + (r >> 3), ox = tx * 8 + (r & 7);
+        const bool valid = oy < p.OH && ox < p.OW;
+        const size_t dpix = valid ? ((size_t)(n * p.DH + oy * p.osh + p.oa) * p.DW + ox * p.osw + p.ob) : 0;
+        epi_row<BN>(p, tmem + ((uint32_t)(q * 32) << 16) + as * acc_cols + m * BN, 0, dpix, valid, s_bias);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) tmem_dealloc_dyn(tmem, ncols);
+}
+
 // ======================================================================================================= wgrad
 // D[co][kcol] = sum_pix g[pix][co] * A[pix][kcol]; both operands are "MN-major" (the reduction dim = pixels is the slow
 // dimension of NHWC), staged as two [64 pixels][64 channels] SWIZZLE_128B sub-tiles each.
@@ -1034,6 +1205,39 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   for (int i = 0; use_tma && i < d->nsrc; ++i)
     if (((uintptr_t)d->src[i].ptr + (size_t)d->src[i].c_off * 2) % 16 || !encode_src_map(&maps.m[i], d->src[i], d->N, d->H, d->W, Wh, Hh)) use_tma = 0;
   if (!use_tma) memset(&maps, 0, sizeof(maps));
+  // persistent variant: measured (r01) to win on single-chunk thin layers (weights re-streamed per tile are tiny) and to lose on
+  // the wide ones at MT=1 (one weight stream per SM instead of 2-3 co-resident CTAs); CIS_PERSIST_MODE: 0 off, 1 thin (default), 2 all
+  static const int persist_mode = getenv("CIS_PERSIST_MODE") ? atoi(getenv("CIS_PERSIST_MODE")) : 1;
+  const bool persist_ok = persist_mode == 2 || (persist_mode == 1 && BN <= 32 && nchunks == 1 && d->ntaps <= 9);
+  if (persist_ok && use_tma && d->n_tiles == 1 && splits == 1) {
+    // persistent, warp-specialised variant: two halo stages, two accumulator stages when TMEM allows
+    const int AS = (2 * d->MT * BN <= 512) ? 2 : 1;
+    const int p_nhs = 2;
+    const int p_fixed = p_nhs * halo_stage + 1024;
+    int p_bs = (200 * 1024 - p_fixed) / (BN * 128);
+    if (p_bs > kHaloMaxBStages) p_bs = kHaloMaxBStages;
+    const int steps_all = nchunks * d->ntaps;
+    if (p_bs > steps_all && steps_all >= 2) p_bs = steps_all;
+    if (p_bs >= 2) {
+      const int p_smem = p_fixed + p_bs * BN * 128;
+      static int attr_p = 0;
+      if (p_smem > attr_p) {
+        cudaError_t e = cudaFuncSetAttribute(conv_halo_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, p_smem);
+        if (e != cudaSuccess) return cis_set_cuda_error(e, "cudaFuncSetAttribute(conv_halo_persist)");
+        attr_p = p_smem;
+      }
+      const int want = AS * d->MT * BN;
+      const int tcols = want <= 32 ? 32 : want <= 64 ? 64 : want <= 128 ? 128 : want <= 256 ? 256 : 512;
+      int cps = (227 * 1024) / (p_smem + 1024);
+      if (cps > 512 / tcols) cps = 512 / tcols;
+      if (cps > 4) cps = 4;
+      if (cps < 1) cps = 1;
+      int g = tiles * d->N;
+      if (g > 148 * cps) g = 148 * cps;
+      conv_halo_persist_kernel<BN><<<g, kPThreads, p_smem, st>>>(*d, halo_stage, p_bs, p_nhs, AS, maps);
+      return cis_check_launch("conv_halo_persist");
+    }
+  }
   conv_halo_kernel<BN><<<grid, kThreads, smem, st>>>(*d, halo_stage, BS, nhs, maps, use_tma);
   return cis_check_launch("conv_halo");
 }

@@ -252,8 +252,10 @@ def setup_halo(d, taps, dil, n_tiles):
     m_chunks = sum(d.src[i].chunks for i in range(d.nsrc))
     nchunks = -(-m_chunks // 8)
     nhs = 2 if nchunks > 1 else 1
+    import os
+    force = int(os.environ.get('CIS_FORCE_MT128', '0')) if d.BN == 128 else 0
     for MT in (1, 2, 3, 4):
-        if MT * d.BN > 512:
+        if MT * d.BN > 512 or (force and MT != force):
             continue
         HP = (8 + ex) * (16 * MT + ey)
         fixed = nhs * ru(HP * 128, 1024) + HP * 4 + 1024

@@ -49,7 +49,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in o.split(',')])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.02)
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())

@@ -105,6 +105,9 @@ const char* cis_last_error(void);
 int cis_version(void);
 
 int cis_conv_igemm(const CisConv* d, cis_stream_t stream);
+/* which launches use the persistent warp-specialised halo kernel: 0 none, 1 thin single-chunk layers (default), 2 all eligible,
+ * -1 back to the default / CIS_PERSIST_MODE environment variable.  Host-side switch, not a stream operation. */
+int cis_set_persist_mode(int mode);
 int cis_conv_wgrad(const CisWgrad* d, cis_stream_t stream);
 
 /* ---- parameter-space helpers (fp32 master weights <-> packed bf16 operands) ---- */

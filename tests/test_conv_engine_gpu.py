@@ -46,3 +46,39 @@ def test_conv_engine(case):
         assert r['db_err'] <= 2 ** -7 * r['db_ref'] + 1e-3, r
     if 'dgamma_err' in r:
         assert r['dgamma_err'] <= 2 ** -6 * r['dgamma_ref'] + 1e-2, r
+
+
+MODE_CASES = [CASES[0], CASES[1], CASES[4], CASES[6], CASES[11], CASES[12], CASES[14], CASES[17]]
+
+
+@pytest.mark.parametrize('case', MODE_CASES, ids=lambda c: 'k%d_d%d_c%s_o%d' % (c['k'], c.get('dil', 1), '+'.join(map(str, c['cins'])), c['cout']))
+def test_conv_engine_persistent_kernel_everywhere(case):
+    """Force the persistent warp-specialised halo kernel for every eligible launch (default: thin layers only)."""
+    from unsupervised_detection_b200 import _lib
+    _lib.load().cis_set_persist_mode(2)
+    try:
+        r = run_conv_case(**case)
+    finally:
+        _lib.load().cis_set_persist_mode(-1)
+    tol = lambda ref: 2 ** -7 * ref + 1e-3
+    assert r['fwd_err'] <= tol(r['fwd_ref']), r
+    if 'dx_err' in r:
+        assert r['dx_err'] <= tol(r['dx_ref']), r
+        assert r['dw_err'] <= 2 ** -7 * r['dw_ref'] + 1e-3, r
+
+
+@pytest.mark.parametrize('case', MODE_CASES, ids=lambda c: 'k%d_d%d_c%s_o%d' % (c['k'], c.get('dil', 1), '+'.join(map(str, c['cins'])), c['cout']))
+def test_conv_engine_split_k(case):
+    """The deterministic single-launch split-K path (disabled by default) stays correct; two runs are bit-identical."""
+    from unsupervised_detection_b200 import engine
+    engine.SPLITK = True
+    try:
+        r = run_conv_case(**case)
+        r2 = run_conv_case(**case)
+    finally:
+        engine.SPLITK = False
+    tol = lambda ref: 2 ** -7 * ref + 1e-3
+    assert r['fwd_err'] <= tol(r['fwd_ref']), r
+    assert r['fwd_err'] == r2['fwd_err']
+    if 'dx_err' in r:
+        assert r['dx_err'] <= tol(r['dx_ref']), r

@@ -1161,6 +1161,12 @@ static bool encode_src_map(CUtensorMap* m, const CisSrc& s, int N, int H, int W,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+static int g_persist_mode = -1;   // -1: environment / default (1 = thin layers)
+extern "C" int cis_set_persist_mode(int mode) {
+  g_persist_mode = mode;
+  return CIS_OK;
+}
+
 template <int BN>
 static int launch_halo(const CisConv* d, cudaStream_t st) {
   const int Wh = 8 + d->ex, Hh = 16 * d->MT + d->ey, HP = Wh * Hh;
@@ -1207,7 +1213,7 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   if (!use_tma) memset(&maps, 0, sizeof(maps));
   // persistent variant: measured (r01) to win on single-chunk thin layers (weights re-streamed per tile are tiny) and to lose on
   // the wide ones at MT=1 (one weight stream per SM instead of 2-3 co-resident CTAs); CIS_PERSIST_MODE: 0 off, 1 thin (default), 2 all
-  static const int persist_mode = getenv("CIS_PERSIST_MODE") ? atoi(getenv("CIS_PERSIST_MODE")) : 1;
+  const int persist_mode = g_persist_mode >= 0 ? g_persist_mode : (getenv("CIS_PERSIST_MODE") ? atoi(getenv("CIS_PERSIST_MODE")) : 1);
   const bool persist_ok = persist_mode == 2 || (persist_mode == 1 && BN <= 32 && nchunks == 1 && d->ntaps <= 9);
   if (persist_ok && use_tma && d->n_tiles == 1 && splits == 1) {
     // persistent, warp-specialised variant: two halo stages, two accumulator stages when TMEM allows

@@ -4,8 +4,6 @@ import os, sys, json, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from unsupervised_detection_b200 import engine
-if os.environ.get('CIS_SPLITK') == '0':
-    engine.SPLITK = False
 from unsupervised_detection_b200.common_flags import Config
 from unsupervised_detection_b200.models.adversarial_learner import AdversarialLearner
 
@@ -25,14 +23,22 @@ for pname, plan, w in (('fwd', g.fwd, 4), ('bwdG', g.bwd['G'], 3), ('bwdR', g.bw
     for i, (fn, a, name, fl, lane) in enumerate(plan.ops):
         if fn is None:
             continue
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # replay through a CUDA graph so host-side launch cost (descriptor checks, tensor-map encodes) is excluded
         fn(*a, st.cuda_stream)
-        e0.record(st)
-        for _ in range(REPS):
-            fn(*a, st.cuda_stream)
-        e1.record(st)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            cs = torch.cuda.current_stream().cuda_stream
+            for _ in range(REPS):
+                fn(*a, cs)
+        gr.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        gr.replay()
+        e1.record()
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / REPS
+        del gr
         info = ''
         if name == 'cis_conv_igemm':
             d = a[0]._obj
@@ -50,8 +56,8 @@ for p, w, n, us, fl, info in rows:
     agg[k][0] += w / 4.0; agg[k][1] += w * us / 4; agg[k][2] += w * fl / 4
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     print('%-34s n/step %6.1f  %8.1f us/step  %6.1f%%  %s' % (k, v[0], v[1], 100 * v[1] / tot, ('%.0f TF/s' % (v[2] / v[1] / 1e6)) if v[2] else ''))
-print('--- top 40 ops by weighted time')
-for p, w, n, us, fl, info in sorted(rows, key=lambda r: -r[1] * r[3])[:40]:
+print('--- all conv ops by weighted time')
+for p, w, n, us, fl, info in sorted([r for r in rows if 'conv' in r[2]], key=lambda r: -r[1] * r[3]):
     print('%-5s x%d %-18s %8.1f us %7.1f GF %6.0f TF/s  %s' % (p, w, n[4:], us, fl / 1e9, fl / us / 1e6 if us else 0, info))
 small = [r for r in rows if r[2] == 'cis_conv_igemm' and r[3] < 15]
 print('conv launches < 15 us: n/step %.0f, us/step %.0f' % (sum(r[1] for r in small) / 4, sum(r[1] * r[3] for r in small) / 4))

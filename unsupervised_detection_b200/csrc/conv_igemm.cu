@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
   const int ny = blockIdx.y;
   __shared__ int s_flag;
   __shared__ float s_bias[BN];
-  if (tid < BN) s_bias[tid] = p.bias ? p.bias[ny * BN + tid] : 0.f;
+  pdl_launch_dependents();
 
   if (tid < p.ntaps) {
     s_dh[tid] = p.dh[tid];
@@ -343,6 +343,8 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
     __syncwarp();
     tmem_alloc<Cfg::kTmemCols>(smem_u32(&tmem_slot));
   }
+  pdl_wait();   // everything above touched only kernel parameters / shared memory / TMEM
+  if (tid < BN) s_bias[tid] = p.bias ? p.bias[ny * BN + tid] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -522,7 +524,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   const int cin8 = m_chunks * 8;
   __shared__ int s_flag;
   __shared__ float s_bias[BN];
-  if (tid < BN) s_bias[tid] = p.bias ? p.bias[ny * BN + tid] : 0.f;
+  pdl_launch_dependents();
   const uint32_t ncols = (MT * BN <= 32) ? 32u : (MT * BN <= 64) ? 64u : (MT * BN <= 128) ? 128u : (MT * BN <= 256) ? 256u : 512u;
 
   if (tid < p.ntaps) {
@@ -558,6 +560,8 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     __syncwarp();
     tmem_alloc_dyn(smem_u32(&tmem_slot), ncols);
   }
+  pdl_wait();
+  if (tid < BN) s_bias[tid] = p.bias ? p.bias[ny * BN + tid] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -758,11 +762,11 @@ __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __gr
   const uint32_t want = acc_cols * AS;
   const uint32_t ncols = want <= 32 ? 32u : want <= 64 ? 64u : want <= 128 ? 128u : want <= 256 ? 256u : 512u;
 
+  pdl_launch_dependents();
   if (tid < p.ntaps) {
     s_dh[tid] = p.dh[tid];
     s_dw[tid] = p.dw[tid];
   }
-  if (tid < BN) s_bias[tid] = p.bias ? p.bias[tid] : 0.f;
   if (warp == 3) {
     if (lane == 0) {
       for (int s = 0; s < NHS; ++s) {
@@ -782,6 +786,8 @@ __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __gr
     __syncwarp();
     tmem_alloc_dyn(smem_u32(&tmem_slot), ncols);
   }
+  pdl_wait();
+  if (tid < BN) s_bias[tid] = p.bias ? p.bias[tid] : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -913,6 +919,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
   const uint32_t bar_empty = smem_u32(&bars[S]);
   const uint32_t bar_accum = smem_u32(&bars[2 * S]);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
   if (tid < p.ntaps) {
     s_dh[tid] = p.dh[tid];
     s_dw[tid] = p.dw[tid];
@@ -941,6 +948,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
     __syncwarp();
     tmem_alloc<128>(smem_u32(&tmem_slot));
   }
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1112,6 +1120,28 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
 
 using namespace cis;
 
+// Launch with programmatic stream serialization so the kernel's prologue can overlap the previous kernel's tail (the kernels call
+// griddepcontrol.wait before touching dependent memory).  CIS_PDL=0 disables it.
+static bool pdl_enabled() {
+  static const bool on = !(getenv("CIS_PDL") && atoi(getenv("CIS_PDL")) == 0);
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int BN>
 static int launch_fwd(const CisConv* d, cudaStream_t st) {
   using Cfg = FwdCfg<BN>;
@@ -1128,7 +1158,8 @@ static int launch_fwd(const CisConv* d, cudaStream_t st) {
     if (!d->sk_scratch || !d->sk_counters || (splits - 1) * per >= nkb) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm: bad split-K setup");
   }
   dim3 grid((M + kBM - 1) / kBM, d->n_tiles, splits);
-  conv_igemm_kernel<BN><<<grid, kThreads, Cfg::kSmem, st>>>(*d);
+  cudaError_t le = launch_pdl(conv_igemm_kernel<BN>, grid, dim3(kThreads), Cfg::kSmem, st, *d);
+  if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_igemm)");
   return cis_check_launch("conv_igemm");
 }
 
@@ -1240,11 +1271,13 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
       if (cps < 1) cps = 1;
       int g = tiles * d->N;
       if (g > 148 * cps) g = 148 * cps;
-      conv_halo_persist_kernel<BN><<<g, kPThreads, p_smem, st>>>(*d, halo_stage, p_bs, p_nhs, AS, maps);
+      cudaError_t le = launch_pdl(conv_halo_persist_kernel<BN>, dim3(g), dim3(kPThreads), p_smem, st, *d, halo_stage, p_bs, p_nhs, AS, maps);
+      if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_halo_persist)");
       return cis_check_launch("conv_halo_persist");
     }
   }
-  conv_halo_kernel<BN><<<grid, kThreads, smem, st>>>(*d, halo_stage, BS, nhs, maps, use_tma);
+  cudaError_t le = launch_pdl(conv_halo_kernel<BN>, grid, dim3(kThreads), smem, st, *d, halo_stage, BS, nhs, maps, use_tma);
+  if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_halo)");
   return cis_check_launch("conv_halo");
 }
 
@@ -1306,6 +1339,7 @@ extern "C" int cis_conv_wgrad(const CisWgrad* d, cis_stream_t stream) {
     if (!ok) return cis_set_error(CIS_ERR_CUDA, "cis_conv_wgrad: cuTensorMapEncodeTiled failed / unavailable");
   }
   dim3 grid((d->K_pad + 127) / 128, d->splits);
-  conv_wgrad_kernel<<<grid, kThreads, kWSmem, (cudaStream_t)stream>>>(*d, maps);
+  cudaError_t le = launch_pdl(conv_wgrad_kernel, grid, dim3(kThreads), kWSmem, (cudaStream_t)stream, *d, maps);
+  if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_wgrad)");
   return cis_check_launch("conv_wgrad");
 }

@@ -202,7 +202,9 @@ def _pow2_cols(c):
     return 1024
 
 
-SPLITK = False   # measured r01: per-CTA fixed latencies dominate the low-resolution layers; splitting K made them slower
+import os as _os
+SPLITK = _os.environ.get('CIS_SPLITK', '0') == '1'   # measured r01: not a win at batch 4; kept selectable
+SPLITK_MAX = int(_os.environ.get('CIS_SPLITK_MAX', '4'))
 
 
 def setup_splitk(d, device, keep):
@@ -217,9 +219,9 @@ def setup_splitk(d, device, keep):
         ncta, units, min_units, mt = tiles * d.n_tiles, -(-m_chunks // 8), 1, d.MT
     else:
         ncta, units, min_units, mt = (-(-(d.N * d.OH * d.OW) // 128)) * d.n_tiles, d.K_pad // 64, 4, 1
-    if ncta >= 100:
+    if ncta > 64:
         return
-    splits = min(units // min_units, -(-2 * NUM_SMS // ncta))
+    splits = min(units // min_units, -(-2 * NUM_SMS // ncta), SPLITK_MAX)
     if splits < 2:
         return
     per = -(-units // splits)

@@ -31,6 +31,8 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 // ------------------------------------------------------------------------------------------------ weights
 __global__ void pack_weights_kernel(const float* __restrict__ w, const int* __restrict__ kmap, int K_pad, int rows, int cout, int sn,
                                     const int* __restrict__ nmap, bf16* __restrict__ wp) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)rows * K_pad) return;
   const int n = (int)(i / K_pad), k = (int)(i % K_pad);
@@ -43,6 +45,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const int* __re
 // tap t with the SWIZZLE_128B pattern already applied (16-byte chunk index ^= n & 7), so a plain bulk copy lands the UMMA layout.
 __global__ void pack_weights_tiled_kernel(const float* __restrict__ w, const int* __restrict__ kmap, int cin8, int ntaps, int n_tiles, int BN,
                                           int cout, int sn, const int* __restrict__ nmap, bf16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nchunks = (cin8 + 63) / 64;
   const size_t total = (size_t)n_tiles * nchunks * ntaps * BN * 64;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -66,6 +70,8 @@ __global__ void pack_weights_tiled_kernel(const float* __restrict__ w, const int
 }
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const int* __restrict__ kmap, int K_pad, int cout,
                                     float* __restrict__ dw) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)cout * K_pad) return;
   const int n = (int)(i / K_pad), k = (int)(i % K_pad);
@@ -75,6 +81,8 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const int* __
 #define BN_RSQRT 0.99950037468777323f /* 1/sqrt(1 + 1e-3): tf.layers.batch_normalization defaults, convolution_utils.py:50 */
 __global__ void bn_fold_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
                                const float* __restrict__ beta, size_t nw, int cout, float* __restrict__ w_eff, float* __restrict__ b_eff) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nw) w_eff[i] = w[i] * gamma[i % cout] * BN_RSQRT;
   if (i < (size_t)cout) b_eff[i] = bias[i] * gamma[i] * BN_RSQRT + beta[i];
@@ -82,6 +90,8 @@ __global__ void bn_fold_kernel(const float* __restrict__ w, const float* __restr
 __global__ void bn_chain_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
                                 float* __restrict__ dwe, const float* __restrict__ dbe, size_t nw, int cout, float* __restrict__ dbias,
                                 float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int co = blockIdx.x;
   const size_t rows = nw / cout;
   float acc = 0.f;
@@ -108,6 +118,8 @@ __global__ void bn_chain_kernel(const float* __restrict__ w, const float* __rest
 // ------------------------------------------------------------------------------------------------ gradient helpers
 __global__ void dact_mul_kernel(bf16* g, int gp, int gc, const bf16* __restrict__ y, int yp, int yc, const bf16* __restrict__ res, int rp,
                                 int rc, size_t npix, int chunks, int act, float alpha) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix * chunks) return;
   const size_t pix = i / chunks;
@@ -131,6 +143,8 @@ __global__ void dact_mul_kernel(bf16* g, int gp, int gc, const bf16* __restrict_
 }
 __global__ void add_slice_kernel(bf16* dst, int dp, int dc, const bf16* __restrict__ src, int sp, int sc, size_t npix, int chunks, int reps,
                                  int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix * chunks) return;
   const size_t pix = i / chunks;
@@ -147,6 +161,8 @@ __global__ void add_slice_kernel(bf16* dst, int dp, int dc, const bf16* __restri
 }
 // db[c] += sum_pix g[pix][c].  blockDim = 256 = P pixel lanes x chunks (chunks <= 32).
 __global__ void colsum_kernel(const bf16* __restrict__ g, int gp, int gc, size_t npix, int nch, int chunks, float* __restrict__ db) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];  // [P][chunks*8]
   const int P = blockDim.x / chunks;
   const int ck = threadIdx.x % chunks, pl = threadIdx.x / chunks;
@@ -184,6 +200,8 @@ __device__ __forceinline__ Lerp legacy_lerp(int d, int n_in, float scale) {
 }
 __global__ void resize_bilinear_bf16_kernel(const bf16* __restrict__ src, int sp, int sc, int N, int H, int W, bf16* __restrict__ dst, int dp,
                                             int dc, int OH, int OW, int chunks) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)N * OH * OW * chunks;
   if (i >= total) return;
@@ -218,6 +236,8 @@ __device__ __forceinline__ void legacy_range(int i, int n_out, float scale, int&
 }
 __global__ void resize_bilinear_bf16_bwd_kernel(const bf16* __restrict__ dd, int dp, int dc, int N, int OH, int OW, bf16* ds, int sp, int sc,
                                                 int H, int W, int chunks, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t total = (size_t)N * H * W * chunks;
   if (i >= total) return;
@@ -248,6 +268,8 @@ __global__ void resize_bilinear_bf16_bwd_kernel(const bf16* __restrict__ dd, int
 }
 __global__ void resize_bilinear_f32_kernel(const float* __restrict__ src, int N, int H, int W, int C, float* __restrict__ dst, int OH, int OW,
                                            float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= (size_t)N * OH * OW) return;
   const int ox = (int)(pix % OW);
@@ -265,6 +287,8 @@ __global__ void resize_bilinear_f32_kernel(const float* __restrict__ src, int N,
 // transpose of the fp32 legacy resize, result stored as a bf16 8-channel chunk (C <= 8 real channels)
 __global__ void resize_f32_bwd_to_bf16_kernel(const float* __restrict__ dd, int N, int OH, int OW, int C, int H, int W, bf16* __restrict__ ds,
                                               int sp) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= (size_t)N * H * W) return;
   const int x = (int)(pix % W);
@@ -293,6 +317,8 @@ __device__ __forceinline__ int nn_src(int d, int n_in) {
   return min((int)roundf(d * scale), n_in - 1);
 }
 __global__ void upsample_nn2x_kernel(const bf16* __restrict__ src, int N, int H, int W, int pitch, bf16* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int chunks = pitch / 8;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)N * 4 * H * W * chunks) return;
@@ -305,6 +331,8 @@ __global__ void upsample_nn2x_kernel(const bf16* __restrict__ src, int N, int H,
   *reinterpret_cast<uint4*>(dst + pix * pitch + c) = *reinterpret_cast<const uint4*>(src + ((size_t)(n * H + sy) * W + sx) * pitch + c);
 }
 __global__ void upsample_nn2x_bwd_kernel(const bf16* __restrict__ dd, int N, int H, int W, int pitch, bf16* ds, int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int chunks = pitch / 8;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)N * H * W * chunks) return;
@@ -328,6 +356,8 @@ __global__ void upsample_nn2x_bwd_kernel(const bf16* __restrict__ dd, int N, int
   *o = pack8(a);
 }
 __global__ void resize_nn_f32_kernel(const float* __restrict__ src, int N, int H, int W, int C, float* __restrict__ dst, int OH, int OW) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= (size_t)N * OH * OW) return;
   const int ox = (int)(pix % OW);
@@ -364,6 +394,8 @@ __device__ __forceinline__ void warp_chunk(const bf16* __restrict__ img, int pit
 }
 __global__ void dense_image_warp_kernel(const bf16* __restrict__ img, int pitch, int coff, const float* __restrict__ flow, float fs, int B,
                                         int h, int w, int chunks, bf16* __restrict__ out, int op) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)B * h * w * chunks) return;
   const int c = (int)(i % chunks) * 8;
@@ -382,6 +414,8 @@ static constexpr int kCvSmem = (kCvTH * kCvTW + kCvHH * kCvHW) * kCvPitch * 4;
 __global__ void __launch_bounds__(256) warp_costvol_kernel(const bf16* __restrict__ c1, int c1p, int c1o, const bf16* __restrict__ c2, int c2p,
                                                            int c2o, const float* __restrict__ flow, float fs, int B, int h, int w, int C,
                                                            bf16* __restrict__ out, int op, int oo) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float cvs[];
   float* s1 = cvs;                                 // [128][36]
   float* s2 = cvs + kCvTH * kCvTW * kCvPitch;      // [384][36]
@@ -468,6 +502,8 @@ __global__ void __launch_bounds__(256) warp_costvol_kernel(const bf16* __restric
 
 // ------------------------------------------------------------------------------------------------ input packing
 __global__ void pack_f32_to_bf16_kernel(const float* __restrict__ src, size_t npix, int C, float offset, bf16* __restrict__ dst, int dp, int dc) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (pix >= npix) return;
   float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -475,6 +511,8 @@ __global__ void pack_f32_to_bf16_kernel(const float* __restrict__ src, size_t np
   *reinterpret_cast<uint4*>(dst + pix * dp + dc) = pack8(v);
 }
 __global__ void flow_stats_kernel(const float* __restrict__ flow, size_t hw, double* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   double s0 = 0, s1 = 0, q0 = 0, q1 = 0;
   for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += (size_t)gridDim.x * blockDim.x) {
@@ -489,6 +527,8 @@ __global__ void flow_stats_kernel(const float* __restrict__ flow, size_t hw, dou
 }
 __global__ void pack_generator_input_kernel(const float* __restrict__ image, const float* __restrict__ flow, const double* __restrict__ stats,
                                             size_t hw, bf16* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= hw) return;
@@ -503,6 +543,8 @@ __global__ void pack_generator_input_kernel(const float* __restrict__ image, con
 
 // ------------------------------------------------------------------------------------------------ mask (x) flow + loss
 __global__ void mask_apply_kernel(const float* __restrict__ flow, const float* __restrict__ mask, size_t npix, bf16* __restrict__ dst) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npix) return;
   const float m = mask[p], f0 = flow[p * 2], f1 = flow[p * 2 + 1];
@@ -539,6 +581,8 @@ __device__ __forceinline__ float dcharb_dpred(float d, float cbn) {  // d = gt -
 }
 __global__ void cis_loss_fwd_kernel(const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ flow1, int B, int H,
                                     int W, int h1, int w1, float cbn, double* __restrict__ sums, float* __restrict__ pred_out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const size_t hw = (size_t)H * W;
   float a[5] = {0, 0, 0, 0, 0};
@@ -569,6 +613,8 @@ __global__ void cis_loss_fwd_kernel(const float* __restrict__ flow, const float*
 }
 __global__ void cis_loss_reduce_kernel(const double* __restrict__ sums, int B, int GB, double hw, float eps, float* __restrict__ scalars,
                                        float* __restrict__ coef) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double rec_total = 0, rr = 0, rrc = 0;
   for (int b = 0; b < B; ++b) {
@@ -591,6 +637,8 @@ __global__ void cis_loss_reduce_kernel(const double* __restrict__ sums, int B, i
 __global__ void cis_loss_bwd_kernel(const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ flow1,
                                     const float* __restrict__ coef, const float* __restrict__ scalars, int B, int H, int W, int h1, int w1,
                                     float cbn, int which, float* __restrict__ dpred, float* __restrict__ dmask) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.y;
   const size_t hw = (size_t)H * W;
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -626,6 +674,8 @@ __global__ void cis_loss_bwd_kernel(const float* __restrict__ flow, const float*
 }
 __global__ void mask_bwd_kernel(const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ dmd,
                                 const bf16* __restrict__ din, size_t npix, bf16* __restrict__ dlogits) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= npix) return;
   const float m = mask[p], f0 = flow[p * 2], f1 = flow[p * 2 + 1];
@@ -642,6 +692,8 @@ __global__ void mask_bwd_kernel(const float* __restrict__ flow, const float* __r
 
 // ------------------------------------------------------------------------------------------------ optimiser
 __global__ void grad_avg_abs_kernel(const float* __restrict__ g, const long long* __restrict__ seg, int nseg, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int s = blockIdx.x;
   const long long a = seg[2 * s], e = seg[2 * s + 1];
   float acc = 0.f;
@@ -663,6 +715,8 @@ __device__ __forceinline__ uint32_t hash32(uint64_t x) {
 __global__ void clip_adam_kernel(float* __restrict__ param, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ grad, size_t n,
                                  float gscale, float clip, float lr, float b1, float b2, float eps, const long long* __restrict__ step,
                                  const float* __restrict__ avg_abs, int can_change, unsigned long long seed) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const long long t = step[0] + 1;
@@ -680,18 +734,26 @@ __global__ void clip_adam_kernel(float* __restrict__ param, float* __restrict__ 
   v[i] = vi;
   param[i] -= lr_t * mi / (sqrtf(vi) + eps);
 }
-__global__ void step_inc_kernel(long long* step) { step[0] += 1; }
+__global__ void step_inc_kernel(long long* step) {
+  pdl_launch_dependents();
+  pdl_wait(); step[0] += 1; }
 __global__ void abs_sum_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   float acc = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) acc += fabsf(g[i]);
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
 }
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ s, size_t n, bf16* __restrict__ d) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[i] = __float2bfloat16(s[i]);
 }
 __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ s, size_t npix, int pitch, int coff, int C, float* __restrict__ d) {
+  pdl_launch_dependents();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix * C) return;
   const size_t p = i / C;
@@ -702,6 +764,31 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ s, size_t npix, in
 }  // namespace cis
 
 using namespace cis;
+#include <stdlib.h>
+#include <string.h>
+
+// every kernel here starts with griddepcontrol.launch_dependents + griddepcontrol.wait, so it may be launched with programmatic
+// stream serialization: its CTAs are scheduled while the previous kernel drains (CIS_PDL=0 turns the attribute off).
+static bool misc_pdl_enabled() {
+  static const bool on = !(getenv("CIS_PDL") && atoi(getenv("CIS_PDL")) == 0);
+  return on;
+}
+template <typename... KArgs, typename... Args>
+static void cis_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = misc_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#define CIS_LAUNCH(kern, grid, block, smem, st, ...) cis_launch(kern, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__)
 #define ST ((cudaStream_t)stream)
 static inline unsigned nblk(size_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 typedef const __nv_bfloat16* cbf;
@@ -711,38 +798,38 @@ extern "C" {
 
 int cis_pack_weights(const float* w, const int32_t* kmap, int32_t K_pad, int32_t rows, int32_t cout, int32_t sn, const int32_t* nmap, void* wp,
                      cis_stream_t stream) {
-  pack_weights_kernel<<<nblk((size_t)rows * K_pad), 256, 0, ST>>>(w, kmap, K_pad, rows, cout, sn, nmap, (mbf)wp);
+  CIS_LAUNCH(pack_weights_kernel, nblk((size_t)rows * K_pad), 256, 0, ST, w, kmap, K_pad, rows, cout, sn, nmap, (mbf)wp);
   return cis_check_launch("pack_weights");
 }
 int cis_pack_weights_tiled(const float* w, const int32_t* kmap, int32_t cin8, int32_t ntaps, int32_t n_tiles, int32_t BN, int32_t cout, int32_t sn,
                            const int32_t* nmap, void* out, cis_stream_t stream) {
   const size_t total = (size_t)n_tiles * ((cin8 + 63) / 64) * ntaps * BN * 64;
-  pack_weights_tiled_kernel<<<nblk(total), 256, 0, ST>>>(w, kmap, cin8, ntaps, n_tiles, BN, cout, sn, nmap, (mbf)out);
+  CIS_LAUNCH(pack_weights_tiled_kernel, nblk(total), 256, 0, ST, w, kmap, cin8, ntaps, n_tiles, BN, cout, sn, nmap, (mbf)out);
   return cis_check_launch("pack_weights_tiled");
 }
 int cis_unpack_wgrad(const float* dwp, const int32_t* kmap, int32_t K_pad, int32_t cout, float* dw, cis_stream_t stream) {
-  unpack_wgrad_kernel<<<nblk((size_t)cout * K_pad), 256, 0, ST>>>(dwp, kmap, K_pad, cout, dw);
+  CIS_LAUNCH(unpack_wgrad_kernel, nblk((size_t)cout * K_pad), 256, 0, ST, dwp, kmap, K_pad, cout, dw);
   return cis_check_launch("unpack_wgrad");
 }
 int cis_bn_fold(const float* w, const float* bias, const float* gamma, const float* beta, int64_t nw, int32_t cout, float* w_eff, float* b_eff,
                 cis_stream_t stream) {
-  bn_fold_kernel<<<nblk((size_t)nw), 256, 0, ST>>>(w, bias, gamma, beta, (size_t)nw, cout, w_eff, b_eff);
+  CIS_LAUNCH(bn_fold_kernel, nblk((size_t)nw), 256, 0, ST, w, bias, gamma, beta, (size_t)nw, cout, w_eff, b_eff);
   return cis_check_launch("bn_fold");
 }
 int cis_bn_chain(const float* w, const float* bias, const float* gamma, float* dwe, const float* dbe, int64_t nw, int32_t cout, float* dbias,
                  float* dgamma, float* dbeta, cis_stream_t stream) {
-  bn_chain_kernel<<<cout, 256, 0, ST>>>(w, bias, gamma, dwe, dbe, (size_t)nw, cout, dbias, dgamma, dbeta);
+  CIS_LAUNCH(bn_chain_kernel, cout, 256, 0, ST, w, bias, gamma, dwe, dbe, (size_t)nw, cout, dbias, dgamma, dbeta);
   return cis_check_launch("bn_chain");
 }
 int cis_dact_mul(void* g, int32_t gp, int32_t gc, const void* y, int32_t yp, int32_t yc, const void* res, int32_t rp, int32_t rc, int64_t npix,
                  int32_t chunks, int32_t act, float alpha, cis_stream_t stream) {
   if (act == CIS_ACT_NONE) return CIS_OK;
-  dact_mul_kernel<<<nblk((size_t)npix * chunks), 256, 0, ST>>>((mbf)g, gp, gc, (cbf)y, yp, yc, (cbf)res, rp, rc, (size_t)npix, chunks, act, alpha);
+  CIS_LAUNCH(dact_mul_kernel, nblk((size_t)npix * chunks), 256, 0, ST, (mbf)g, gp, gc, (cbf)y, yp, yc, (cbf)res, rp, rc, (size_t)npix, chunks, act, alpha);
   return cis_check_launch("dact_mul");
 }
 int cis_add_slice(void* dst, int32_t dp, int32_t dc, const void* src, int32_t sp, int32_t sc, int64_t npix, int32_t chunks, int32_t reps,
                   int32_t accumulate, cis_stream_t stream) {
-  add_slice_kernel<<<nblk((size_t)npix * chunks), 256, 0, ST>>>((mbf)dst, dp, dc, (cbf)src, sp, sc, (size_t)npix, chunks, reps, accumulate);
+  CIS_LAUNCH(add_slice_kernel, nblk((size_t)npix * chunks), 256, 0, ST, (mbf)dst, dp, dc, (cbf)src, sp, sc, (size_t)npix, chunks, reps, accumulate);
   return cis_check_launch("add_slice");
 }
 int cis_colsum(const void* g, int32_t gp, int32_t gc, int64_t npix, int32_t nch, float* db, cis_stream_t stream) {
@@ -752,35 +839,35 @@ int cis_colsum(const void* g, int32_t gp, int32_t gc, int64_t npix, int32_t nch,
   unsigned blocks = (unsigned)((npix + P * 16 - 1) / (P * 16));
   if (blocks > 592) blocks = 592;
   if (blocks < 1) blocks = 1;
-  colsum_kernel<<<blocks, 256, P * chunks * 8 * sizeof(float), ST>>>((cbf)g, gp, gc, (size_t)npix, nch, chunks, db);
+  CIS_LAUNCH(colsum_kernel, blocks, 256, P * chunks * 8 * sizeof(float), ST, (cbf)g, gp, gc, (size_t)npix, nch, chunks, db);
   return cis_check_launch("colsum");
 }
 int cis_resize_bilinear_bf16(const void* src, int32_t sp, int32_t sc, int32_t N, int32_t H, int32_t W, void* dst, int32_t dp, int32_t dc, int32_t OH,
                              int32_t OW, int32_t chunks, cis_stream_t stream) {
-  resize_bilinear_bf16_kernel<<<nblk((size_t)N * OH * OW * chunks), 256, 0, ST>>>((cbf)src, sp, sc, N, H, W, (mbf)dst, dp, dc, OH, OW, chunks);
+  CIS_LAUNCH(resize_bilinear_bf16_kernel, nblk((size_t)N * OH * OW * chunks), 256, 0, ST, (cbf)src, sp, sc, N, H, W, (mbf)dst, dp, dc, OH, OW, chunks);
   return cis_check_launch("resize_bilinear_bf16");
 }
 int cis_resize_bilinear_bf16_bwd(const void* dd, int32_t dp, int32_t dc, int32_t N, int32_t OH, int32_t OW, void* ds, int32_t sp, int32_t sc, int32_t H,
                                  int32_t W, int32_t chunks, int32_t accumulate, cis_stream_t stream) {
-  resize_bilinear_bf16_bwd_kernel<<<nblk((size_t)N * H * W * chunks), 256, 0, ST>>>((cbf)dd, dp, dc, N, OH, OW, (mbf)ds, sp, sc, H, W, chunks,
+  CIS_LAUNCH(resize_bilinear_bf16_bwd_kernel, nblk((size_t)N * H * W * chunks), 256, 0, ST, (cbf)dd, dp, dc, N, OH, OW, (mbf)ds, sp, sc, H, W, chunks,
                                                                                      accumulate);
   return cis_check_launch("resize_bilinear_bf16_bwd");
 }
 int cis_resize_bilinear_f32(const float* src, int32_t N, int32_t H, int32_t W, int32_t C, float* dst, int32_t OH, int32_t OW, float scale,
                             cis_stream_t stream) {
-  resize_bilinear_f32_kernel<<<nblk((size_t)N * OH * OW), 256, 0, ST>>>(src, N, H, W, C, dst, OH, OW, scale);
+  CIS_LAUNCH(resize_bilinear_f32_kernel, nblk((size_t)N * OH * OW), 256, 0, ST, src, N, H, W, C, dst, OH, OW, scale);
   return cis_check_launch("resize_bilinear_f32");
 }
 int cis_upsample_nn2x(const void* src, int32_t N, int32_t H, int32_t W, int32_t pitch, void* dst, cis_stream_t stream) {
-  upsample_nn2x_kernel<<<nblk((size_t)N * 4 * H * W * (pitch / 8)), 256, 0, ST>>>((cbf)src, N, H, W, pitch, (mbf)dst);
+  CIS_LAUNCH(upsample_nn2x_kernel, nblk((size_t)N * 4 * H * W * (pitch / 8)), 256, 0, ST, (cbf)src, N, H, W, pitch, (mbf)dst);
   return cis_check_launch("upsample_nn2x");
 }
 int cis_upsample_nn2x_bwd(const void* dd, int32_t N, int32_t H, int32_t W, int32_t pitch, void* ds, int32_t accumulate, cis_stream_t stream) {
-  upsample_nn2x_bwd_kernel<<<nblk((size_t)N * H * W * (pitch / 8)), 256, 0, ST>>>((cbf)dd, N, H, W, pitch, (mbf)ds, accumulate);
+  CIS_LAUNCH(upsample_nn2x_bwd_kernel, nblk((size_t)N * H * W * (pitch / 8)), 256, 0, ST, (cbf)dd, N, H, W, pitch, (mbf)ds, accumulate);
   return cis_check_launch("upsample_nn2x_bwd");
 }
 int cis_resize_nn_f32(const float* src, int32_t N, int32_t H, int32_t W, int32_t C, float* dst, int32_t OH, int32_t OW, cis_stream_t stream) {
-  resize_nn_f32_kernel<<<nblk((size_t)N * OH * OW), 256, 0, ST>>>(src, N, H, W, C, dst, OH, OW);
+  CIS_LAUNCH(resize_nn_f32_kernel, nblk((size_t)N * OH * OW), 256, 0, ST, src, N, H, W, C, dst, OH, OW);
   return cis_check_launch("resize_nn_f32");
 }
 int cis_warp_costvol(const void* c1, int32_t c1p, int32_t c1o, const void* c2, int32_t c2p, int32_t c2o, const float* flow, float fs, int32_t B,
@@ -793,83 +880,83 @@ int cis_warp_costvol(const void* c1, int32_t c1p, int32_t c1o, const void* c2, i
     attr = true;
   }
   dim3 grid((w + kCvTW - 1) / kCvTW, (h + kCvTH - 1) / kCvTH, B);
-  warp_costvol_kernel<<<grid, 256, kCvSmem, ST>>>((cbf)c1, c1p, c1o, (cbf)c2, c2p, c2o, flow, fs, B, h, w, C, (mbf)out, op, oo);
+  CIS_LAUNCH(warp_costvol_kernel, grid, 256, kCvSmem, ST, (cbf)c1, c1p, c1o, (cbf)c2, c2p, c2o, flow, fs, B, h, w, C, (mbf)out, op, oo);
   return cis_check_launch("warp_costvol");
 }
 int cis_dense_image_warp(const void* img, int32_t pitch, int32_t coff, const float* flow, float fs, int32_t B, int32_t h, int32_t w, int32_t C,
                          void* out, int32_t op, cis_stream_t stream) {
   const int chunks = (C + 7) / 8;
-  dense_image_warp_kernel<<<nblk((size_t)B * h * w * chunks), 256, 0, ST>>>((cbf)img, pitch, coff, flow, fs, B, h, w, chunks, (mbf)out, op);
+  CIS_LAUNCH(dense_image_warp_kernel, nblk((size_t)B * h * w * chunks), 256, 0, ST, (cbf)img, pitch, coff, flow, fs, B, h, w, chunks, (mbf)out, op);
   return cis_check_launch("dense_image_warp");
 }
 int cis_pack_f32_to_bf16(const float* src, int64_t npix, int32_t C, float offset, void* dst, int32_t dp, int32_t dc, cis_stream_t stream) {
   if (C > 8) return cis_set_error(CIS_ERR_BAD_ARG, "cis_pack_f32_to_bf16: C > 8");
-  pack_f32_to_bf16_kernel<<<nblk((size_t)npix), 256, 0, ST>>>(src, (size_t)npix, C, offset, (mbf)dst, dp, dc);
+  CIS_LAUNCH(pack_f32_to_bf16_kernel, nblk((size_t)npix), 256, 0, ST, src, (size_t)npix, C, offset, (mbf)dst, dp, dc);
   return cis_check_launch("pack_f32_to_bf16");
 }
 int cis_flow_stats(const float* flow, int32_t B, int64_t hw, double* stats, cis_stream_t stream) {
   dim3 grid(64, B);
-  flow_stats_kernel<<<grid, 256, 0, ST>>>(flow, (size_t)hw, stats);
+  CIS_LAUNCH(flow_stats_kernel, grid, 256, 0, ST, flow, (size_t)hw, stats);
   return cis_check_launch("flow_stats");
 }
 int cis_pack_generator_input(const float* image, const float* flow, const double* stats, int32_t B, int64_t hw, void* dst, cis_stream_t stream) {
   dim3 grid(nblk((size_t)hw), B);
-  pack_generator_input_kernel<<<grid, 256, 0, ST>>>(image, flow, stats, (size_t)hw, (mbf)dst);
+  CIS_LAUNCH(pack_generator_input_kernel, grid, 256, 0, ST, image, flow, stats, (size_t)hw, (mbf)dst);
   return cis_check_launch("pack_generator_input");
 }
 int cis_mask_apply(const float* flow, const float* mask, int32_t B, int64_t hw, void* dst, cis_stream_t stream) {
-  mask_apply_kernel<<<nblk((size_t)B * hw), 256, 0, ST>>>(flow, mask, (size_t)B * hw, (mbf)dst);
+  CIS_LAUNCH(mask_apply_kernel, nblk((size_t)B * hw), 256, 0, ST, flow, mask, (size_t)B * hw, (mbf)dst);
   return cis_check_launch("mask_apply");
 }
 int cis_cis_loss_fwd(const float* flow, const float* mask, const float* flow1, int32_t B, int32_t H, int32_t W, int32_t h1, int32_t w1, float cbn,
                      double* sums, float* pred_out, cis_stream_t stream) {
   dim3 grid(148, B);
-  cis_loss_fwd_kernel<<<grid, 256, 0, ST>>>(flow, mask, flow1, B, H, W, h1, w1, cbn, sums, pred_out);
+  CIS_LAUNCH(cis_loss_fwd_kernel, grid, 256, 0, ST, flow, mask, flow1, B, H, W, h1, w1, cbn, sums, pred_out);
   return cis_check_launch("cis_loss_fwd");
 }
 int cis_cis_loss_reduce(const double* sums, int32_t B, int32_t global_batch, int64_t hw, float epsilon, float* scalars, float* coef,
                         cis_stream_t stream) {
-  cis_loss_reduce_kernel<<<1, 32, 0, ST>>>(sums, B, global_batch, (double)hw, epsilon, scalars, coef);
+  CIS_LAUNCH(cis_loss_reduce_kernel, 1, 32, 0, ST, sums, B, global_batch, (double)hw, epsilon, scalars, coef);
   return cis_check_launch("cis_loss_reduce");
 }
 int cis_cis_loss_bwd(const float* flow, const float* mask, const float* flow1, const float* coef, const float* scalars, int32_t B, int32_t H,
                      int32_t W, int32_t h1, int32_t w1, float cbn, int32_t which, float* dpred, float* dmask, cis_stream_t stream) {
   dim3 grid(nblk((size_t)H * W), B);
-  cis_loss_bwd_kernel<<<grid, 256, 0, ST>>>(flow, mask, flow1, coef, scalars, B, H, W, h1, w1, cbn, which, dpred, dmask);
+  CIS_LAUNCH(cis_loss_bwd_kernel, grid, 256, 0, ST, flow, mask, flow1, coef, scalars, B, H, W, h1, w1, cbn, which, dpred, dmask);
   return cis_check_launch("cis_loss_bwd");
 }
 int cis_resize_f32_bwd_to_bf16(const float* dd, int32_t N, int32_t OH, int32_t OW, int32_t C, int32_t H, int32_t W, void* ds, int32_t sp,
                                cis_stream_t stream) {
   if (C > 8) return cis_set_error(CIS_ERR_BAD_ARG, "cis_resize_f32_bwd_to_bf16: C > 8");
-  resize_f32_bwd_to_bf16_kernel<<<nblk((size_t)N * H * W), 256, 0, ST>>>(dd, N, OH, OW, C, H, W, (mbf)ds, sp);
+  CIS_LAUNCH(resize_f32_bwd_to_bf16_kernel, nblk((size_t)N * H * W), 256, 0, ST, dd, N, OH, OW, C, H, W, (mbf)ds, sp);
   return cis_check_launch("resize_f32_bwd_to_bf16");
 }
 int cis_mask_bwd(const float* flow, const float* mask, const float* dmd, const void* din, int32_t B, int64_t hw, void* dlogits, cis_stream_t stream) {
-  mask_bwd_kernel<<<nblk((size_t)B * hw), 256, 0, ST>>>(flow, mask, dmd, (cbf)din, (size_t)B * hw, (mbf)dlogits);
+  CIS_LAUNCH(mask_bwd_kernel, nblk((size_t)B * hw), 256, 0, ST, flow, mask, dmd, (cbf)din, (size_t)B * hw, (mbf)dlogits);
   return cis_check_launch("mask_bwd");
 }
 int cis_abs_sum(const float* g, int64_t n, float* stat, cis_stream_t stream) {
-  abs_sum_kernel<<<296, 256, 0, ST>>>(g, (size_t)n, stat);
+  CIS_LAUNCH(abs_sum_kernel, 296, 256, 0, ST, g, (size_t)n, stat);
   return cis_check_launch("abs_sum");
 }
 int cis_grad_avg_abs(const float* g, const int64_t* seg_off, int32_t nseg, float* out_avg, cis_stream_t stream) {
-  grad_avg_abs_kernel<<<nseg, 256, 0, ST>>>(g, (const long long*)seg_off, nseg, out_avg);
+  CIS_LAUNCH(grad_avg_abs_kernel, nseg, 256, 0, ST, g, (const long long*)seg_off, nseg, out_avg);
   return cis_check_launch("grad_avg_abs");
 }
 int cis_clip_adam(float* param, float* m, float* v, const float* grad, int64_t n, float grad_scale, float clip, float lr, float beta1, float beta2,
                   float eps, int64_t* step_state, const float* avg_abs, int32_t can_change, uint64_t seed, cis_stream_t stream) {
   if (can_change && !avg_abs) return cis_set_error(CIS_ERR_BAD_ARG, "cis_clip_adam: can_change needs avg_abs");
-  clip_adam_kernel<<<nblk((size_t)n), 256, 0, ST>>>(param, m, v, grad, (size_t)n, grad_scale, clip, lr, beta1, beta2, eps,
+  CIS_LAUNCH(clip_adam_kernel, nblk((size_t)n), 256, 0, ST, param, m, v, grad, (size_t)n, grad_scale, clip, lr, beta1, beta2, eps,
                                                     (const long long*)step_state, avg_abs, can_change, (unsigned long long)seed);
-  step_inc_kernel<<<1, 1, 0, ST>>>((long long*)step_state);
+  CIS_LAUNCH(step_inc_kernel, 1, 1, 0, ST, (long long*)step_state);
   return cis_check_launch("clip_adam");
 }
 int cis_cast_f32_to_bf16(const float* src, int64_t n, void* dst, cis_stream_t stream) {
-  cast_f32_bf16_kernel<<<nblk((size_t)n), 256, 0, ST>>>(src, (size_t)n, (mbf)dst);
+  CIS_LAUNCH(cast_f32_bf16_kernel, nblk((size_t)n), 256, 0, ST, src, (size_t)n, (mbf)dst);
   return cis_check_launch("cast_f32_to_bf16");
 }
 int cis_cast_bf16_to_f32(const void* src, int64_t npix, int32_t pitch, int32_t coff, int32_t C, float* dst, cis_stream_t stream) {
-  cast_bf16_f32_kernel<<<nblk((size_t)npix * C), 256, 0, ST>>>((cbf)src, (size_t)npix, pitch, coff, C, dst);
+  CIS_LAUNCH(cast_bf16_f32_kernel, nblk((size_t)npix * C), 256, 0, ST, (cbf)src, (size_t)npix, pitch, coff, C, dst);
   return cis_check_launch("cast_bf16_to_f32");
 }
 

@@ -1,0 +1,86 @@
+"""Host-side DAVIS2016 reader on a tiny synthetic dataset tree written to tmp."""
+import os
+import cv2
+import numpy as np
+import pytest
+import torch
+
+from oracle import tf_ops as T
+from unsupervised_detection_b200.data import davis2016_data_utils as D
+
+
+@pytest.fixture(scope='module')
+def root(tmp_path_factory):
+    r = str(tmp_path_factory.mktemp('davis'))
+    rng = np.random.RandomState(0)
+    lines = {'train': [], 'val': []}
+    for part, seqs in (('train', ['bear', 'bus']), ('val', ['cows'])):
+        for s in seqs:
+            os.makedirs(os.path.join(r, 'JPEGImages/480p', s))
+            os.makedirs(os.path.join(r, 'Annotations/480p', s))
+            for i in range(6):
+                img = (rng.rand(48, 80, 3) * 255).astype(np.uint8)
+                img[:, :, 0] = i * 20                       # blue channel encodes the frame index (BGR order for cv2)
+                cv2.imwrite(os.path.join(r, 'JPEGImages/480p', s, '%05d.jpg' % i), img, [cv2.IMWRITE_JPEG_QUALITY, 100])
+                ann = np.zeros((48, 80), np.uint8)
+                ann[10:30, 20 + i:50 + i] = 255
+                cv2.imwrite(os.path.join(r, 'Annotations/480p', s, '%05d.png' % i), ann)
+                lines[part].append('/JPEGImages/480p/%s/%05d.jpg /Annotations/480p/%s/%05d.png' % (s, i, s, i))
+    os.makedirs(os.path.join(r, 'ImageSets/480p'))
+    for part in ('train', 'val'):
+        open(os.path.join(r, 'ImageSets/480p', part + '.txt'), 'w').write('\n'.join(lines[part]) + '\n')
+    open(os.path.join(r, 'ImageSets/480p', 'trainval.txt'), 'w').write('\n'.join(lines['train'] + lines['val']) + '\n')
+    return r
+
+
+def test_directory_iterator(root):
+    it = D.DirectoryIterator(root, 'train')
+    assert it.samples == 12 and it.num_experiments == 2 and len(it.image_filenames[0]) == 6
+    assert it.image_filenames[1][0].endswith('JPEGImages/480p/bus/00000.jpg')
+    with pytest.raises(IOError):
+        D.DirectoryIterator(root, 'nope')
+    with pytest.raises(IOError):
+        D.DirectoryIterator('/nonexistent', 'train')
+
+
+def test_resizes_match_the_oracle():
+    x = np.random.RandomState(1).rand(7, 9, 3).astype(np.float32)
+    a = D.legacy_resize(x, 12, 16)
+    b = T.resize_bilinear_legacy(torch.from_numpy(x)[None], 12, 16)[0].numpy()
+    assert np.abs(a - b).max() < 1e-6
+    m = np.random.RandomState(2).rand(7, 9, 1).astype(np.float32)
+    assert np.array_equal(D.nn_resize(m, 5, 4), T.resize_nn_legacy(torch.from_numpy(m)[None], 5, 4)[0].numpy())
+    assert D.central_crop_box(384, 640, 0.9) == (19, 32, 346, 576)
+
+
+def test_training_pairs(root):
+    rd = D.Davis2016Reader(root, max_temporal_len=2, min_temporal_len=1, num_threads=2, seed=3)
+    it = rd.image_inputs(batch_size=4, partition='train', train_crop=0.9)
+    # per sequence of 6 frames: forward heads 0..3, backward tails 2..5 -> 8 pairs x 2 sequences
+    assert len(it.pairs) == 16
+    assert sorted(p[0] for p in it.pairs if p[1] > 0) == [0, 1, 2, 3, 6, 7, 8, 9]
+    assert sorted(p[0] for p in it.pairs if p[1] < 0) == [2, 3, 4, 5, 8, 9, 10, 11]
+    i1, i2, seg, names = it.batch(4, pinned=False)
+    assert i1.shape == (4, 384, 640, 3) and i2.shape == (4, 384, 640, 3) and i1.dtype == torch.float32
+    assert float(i1.min()) >= -0.5 - 1e-6 and float(i1.max()) <= 0.5 + 1e-6
+    assert len(names) == 4 and all(n.endswith('.jpg') for n in names)
+    # the pair never crosses a sequence boundary: frame index encoded in the red..blue channel differs by 1 or 2 steps of 20/255
+    d = (i1[..., 2].mean(dim=(1, 2)) - i2[..., 2].mean(dim=(1, 2))).abs() * 255 / 20
+    assert all(0.8 < float(v) < 2.2 for v in d)
+    for _ in range(6):                       # endless (repeat + reshuffle)
+        it.batch(4, pinned=False)
+
+
+def test_test_iterator_order_and_boundaries(root):
+    rd = D.Davis2016Reader(root, num_threads=1)
+    it = rd.test_inputs(batch_size=2, partition='val', t_len=1, with_fname=True, test_crop=0.9)
+    assert rd.val_samples == 6
+    assert it.pairs == [(0, 1.0), (1, 1.0), (2, 1.0), (3, 1.0), (4, 1.0), (5, -1.0)]   # last frame looks backward
+    i1, i2, seg, names = it.batch(6, pinned=False)
+    assert [os.path.basename(n) for n in names] == ['%05d.jpg' % i for i in range(6)]
+    assert seg.shape == (6, 384, 640, 1) and float(seg.max()) == 1.0 and float(seg.min()) == 0.0
+    blue = lambda t: t[..., 2].mean(dim=(1, 2)) * 255 + 127.5
+    # JPEG chroma coding blurs the exact value; direction and rough size are what matter: +1 frame forward, last frame backward
+    assert 5 < float(blue(i2)[0] - blue(i1)[0]) < 35 and -35 < float(blue(i2)[5] - blue(i1)[5]) < -5
+    it2 = rd.test_inputs(partition='val', t_len=-2)
+    assert it2.pairs[:2] == [(0, 1.0), (1, 1.0)] and it2.pairs[2] == (2, -1.0)

@@ -1,0 +1,230 @@
+"""Host-side DAVIS2016 reader: the reference's tf.data pipeline (data/davis2016_data_utils.py:6-354,
+data/aug_flips.py:35-45) restated with numpy + OpenCV + a thread pool, feeding pinned torch tensors to AdversarialLearner.
+
+Same folder contract (`ImageSets/480p/{train,val,trainval}.txt` listing `/JPEGImages/480p/<seq>/<frame>.jpg
+/Annotations/480p/<seq>/<frame>.png`), same sampling (frame pairs with a temporal shift in [min,max]_temporal_len forward from
+the head of a sequence / backward from its tail), same preprocessing (x/255-0.5, legacy-bilinear resize to 384x640, random
+flips applied to both frames, random / central crop resized back).  JPEG decoding and augmentation stay on the CPU.
+"""
+import os
+import random
+from concurrent.futures import ThreadPoolExecutor
+
+import cv2
+import numpy as np
+import torch
+
+ORIG_H, ORIG_W = 384, 640   # preprocess_image :87-90
+
+
+class DirectoryIterator(object):
+    """davis2016_data_utils.py:6-65."""
+
+    def __init__(self, directory, part='train'):
+        self.directory = directory
+        name_division = {'train': 'ImageSets/480p/train.txt', 'val': 'ImageSets/480p/val.txt', 'trainval': 'ImageSets/480p/trainval.txt'}
+        if part not in name_division:
+            raise IOError("Partition file not found")
+        part_file = os.path.join(directory, name_division[part])
+        if not os.path.isfile(part_file):
+            raise IOError("Partition file not found")
+        self.components = np.loadtxt(part_file, dtype=str, ndmin=2)
+        self.samples = 0
+        self.image_filenames = []
+        self.annotation_filenames = []
+        self._parse_components(self.components)
+        if self.samples == 0:
+            raise IOError("Did not find any file in the dataset folder")
+        self.num_experiments = len(self.image_filenames)
+        print('Found {} images belonging to {} experiments.'.format(self.samples, self.num_experiments))
+
+    def _parse_components(self, components):
+        current_experiment, cur_f, cur_a = '', None, None
+        for string in components:
+            folder_name = string[0].split('/')[3]
+            if folder_name != current_experiment:
+                current_experiment = folder_name
+                if cur_f is not None:
+                    self.image_filenames.append(cur_f)
+                    self.annotation_filenames.append(cur_a)
+                cur_f, cur_a = [], []
+            cur_f.append(os.path.join(self.directory, string[0][1:]))
+            cur_a.append(os.path.join(self.directory, string[1][1:]))
+            self.samples += 1
+        if cur_f is not None:
+            self.image_filenames.append(cur_f)
+            self.annotation_filenames.append(cur_a)
+
+
+def legacy_resize(x, oh, ow):
+    """tf.image.resize_images (legacy bilinear, App. A.6) on an HWC float32 array."""
+    h, w = x.shape[:2]
+    if (h, w) == (oh, ow):
+        return x
+
+    def ax(n_in, n_out):
+        s = np.arange(n_out, dtype=np.float32) * np.float32(n_in / n_out)
+        lo = np.floor(s).astype(np.int64)
+        return lo, np.minimum(lo + 1, n_in - 1), (s - lo).astype(np.float32)
+    hl, hh, hf = ax(h, oh)
+    wl, wh, wf = ax(w, ow)
+    top, bot = x[hl], x[hh]
+    wf = wf[None, :, None]
+    t = top[:, wl] + (top[:, wh] - top[:, wl]) * wf
+    b = bot[:, wl] + (bot[:, wh] - bot[:, wl]) * wf
+    return t + (b - t) * hf[:, None, None]
+
+
+def nn_resize(x, oh, ow):
+    """tf.image.resize_images(method=NEAREST_NEIGHBOR), align_corners=False."""
+    h, w = x.shape[:2]
+    yi = np.minimum(np.floor(np.arange(oh, dtype=np.float32) * np.float32(h / oh)).astype(np.int64), h - 1)
+    xi = np.minimum(np.floor(np.arange(ow, dtype=np.float32) * np.float32(w / ow)).astype(np.int64), w - 1)
+    return x[yi][:, xi]
+
+
+def central_crop_box(h, w, frac):
+    """tf.image.central_crop geometry: offset = int((dim - dim*frac)/2), size = dim - 2*offset."""
+    y0 = int((h - h * frac) / 2)
+    x0 = int((w - w * frac) / 2)
+    return y0, x0, h - 2 * y0, w - 2 * x0
+
+
+class _Iter(object):
+    """Endless batch iterator with the interface AdversarialLearner uses: .batch(n) -> (img1, img2, seg1, fnames)."""
+
+    def __init__(self, reader, pairs, train, shuffle, num_threads):
+        self.reader, self.pairs, self.train, self.shuffle = reader, list(pairs), train, shuffle
+        self.pool = ThreadPoolExecutor(max_workers=max(1, num_threads))
+        self.pos = 0
+        self.order = list(range(len(self.pairs)))
+        if shuffle:
+            reader.rng.shuffle(self.order)
+
+    def _next_index(self):
+        if self.pos >= len(self.order):          # dataset.repeat(None) (+ reshuffle_each_iteration)
+            self.pos = 0
+            if self.shuffle:
+                self.reader.rng.shuffle(self.order)
+        i = self.order[self.pos]
+        self.pos += 1
+        return i
+
+    def batch(self, n, pinned=True):
+        idx = [self._next_index() for _ in range(n)]
+        fn = self.reader._train_sample if self.train else self.reader._test_sample
+        seeds = [self.reader.rng.getrandbits(32) for _ in idx]
+        res = list(self.pool.map(lambda a: fn(self.pairs[a[0]], a[1]), zip(idx, seeds)))
+        out = [torch.from_numpy(np.stack([r[k] for r in res])) for k in range(3)]
+        if pinned and torch.cuda.is_available():
+            out = [t.pin_memory() for t in out]
+        return out[0], out[1], out[2], [r[3] for r in res]
+
+
+class Davis2016Reader(object):
+    """davis2016_data_utils.py:68-354."""
+
+    def __init__(self, root_dir, max_temporal_len=3, min_temporal_len=1, num_threads=6, seed=8964):
+        self.root_dir = root_dir
+        self.max_temporal_len, self.min_temporal_len = max_temporal_len, min_temporal_len
+        assert min_temporal_len < max_temporal_len, "Temporal lenghts are not consistenst"
+        assert min_temporal_len > 0, "Min temporal len should be positive"
+        self.num_threads = num_threads
+        self.rng = random.Random(seed)
+
+    def get_filenames_list(self, partition):
+        it = DirectoryIterator(self.root_dir, partition)
+        self.val_samples = it.samples
+        return it.image_filenames, it.annotation_filenames
+
+    # ---- preprocessing (:84-99)
+    @staticmethod
+    def preprocess_image(path):
+        bgr = cv2.imread(path, cv2.IMREAD_COLOR)
+        if bgr is None:
+            raise IOError("Could not read image %s" % path)
+        rgb = cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB).astype(np.float32) / np.float32(255.0) - np.float32(0.5)
+        return legacy_resize(rgb, ORIG_H, ORIG_W)
+
+    @staticmethod
+    def preprocess_mask(path):
+        m = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+        if m is None:
+            raise IOError("Could not read annotation %s" % path)
+        return nn_resize(m.astype(np.float32)[..., None] / np.float32(255.0), ORIG_H, ORIG_W)
+
+    @staticmethod
+    def central_cropping(img, frac, nearest=False):
+        h, w = img.shape[:2]
+        y0, x0, ch, cw = central_crop_box(h, w, frac)
+        c = img[y0:y0 + ch, x0:x0 + cw]
+        return nn_resize(c, h, w) if nearest else legacy_resize(c, h, w)   # the reference resizes masks bilinearly here too (:133)
+
+    # ---- samples
+    def _train_sample(self, pair, seed):
+        """dataset_map :150-178 + augment_pair :136-148 + aug_flips.random_flip_images."""
+        r = random.Random(seed)
+        i1, direction = pair
+        t_shift = r.randint(self.min_temporal_len, self.max_temporal_len)
+        i2 = int(t_shift * direction + i1)
+        a, b = self.preprocess_image(self.filenames[i1]), self.preprocess_image(self.filenames[i2])
+        case = r.randrange(4)                      # keep | rotate 180 | left-right | top-down, each 25 %
+        if case == 1:
+            a, b = a[::-1, ::-1], b[::-1, ::-1]
+        elif case == 2:
+            a, b = a[:, ::-1], b[:, ::-1]
+        elif case == 3:
+            a, b = a[::-1], b[::-1]
+        pct = self.train_crop + r.random() * (1 - self.train_crop)       # random_crop_image_pair :101-128
+        h, w = a.shape[:2]
+        ch, cw = int(h * pct), int(w * pct)
+        y0, x0 = r.randint(0, h - ch), r.randint(0, w - cw)
+        a = legacy_resize(np.ascontiguousarray(a[y0:y0 + ch, x0:x0 + cw]), h, w)
+        b = legacy_resize(np.ascontiguousarray(b[y0:y0 + ch, x0:x0 + cw]), h, w)
+        return a.astype(np.float32), b.astype(np.float32), np.ones((h, w, 1), np.float32), self.filenames[i1]
+
+    def _test_sample(self, pair, seed):
+        """test_dataset_map :293-326."""
+        i1, direction = pair
+        i2 = int(self.test_t_len * direction + i1)
+        a, b = self.preprocess_image(self.filenames[i1]), self.preprocess_image(self.filenames[i2])
+        s = self.preprocess_mask(self.annotation_filenames[i1])
+        c = self.test_crop
+        return (self.central_cropping(a, c).astype(np.float32), self.central_cropping(b, c).astype(np.float32),
+                self.central_cropping(s, c).astype(np.float32), self.filenames[i1])
+
+    # ---- iterators
+    def image_inputs(self, batch_size=32, partition='train', train_crop=1.0, num_threads=6):
+        """:180-230 -> endless shuffled iterator of augmented training pairs."""
+        t_len = self.max_temporal_len
+        file_list, _ = self.get_filenames_list(partition)
+        self.train_crop = train_crop
+        pairs, N = [], 0
+        for fnames in file_list:
+            pairs += [(i, 1.0) for i in range(N, N + len(fnames) - t_len)]       # forward from the head
+            N += len(fnames)
+        N = 0
+        for fnames in file_list:
+            pairs += [(i, -1.0) for i in range(N + t_len, N + len(fnames))]      # backward from the tail
+            N += len(fnames)
+        self.filenames = [f for fl in file_list for f in fl]
+        return _Iter(self, pairs, train=True, shuffle=True, num_threads=self.num_threads)
+
+    def test_inputs(self, batch_size=32, partition='val', t_len=2, with_fname=False, test_crop=1.0):
+        """:233-290 -> ordered iterator (img_1, img_2, seg_1, fname); time(img2)-time(img1) = t_len except at sequence ends."""
+        file_list, ann_list = self.get_filenames_list(partition)
+        self.test_crop = test_crop
+        first, last, N = [], [], 0
+        for fnames in file_list:
+            if t_len < 0:
+                last += list(range(N + abs(t_len), N + len(fnames)))
+                first += list(range(N, N + abs(t_len)))
+            elif t_len > 0:
+                first += list(range(N, N + len(fnames) - t_len))
+                last += list(range(N + len(fnames) - t_len, N + len(fnames)))
+            N += len(fnames)
+        self.test_t_len = abs(t_len)
+        self.filenames = [f for fl in file_list for f in fl]
+        self.annotation_filenames = [f for fl in ann_list for f in fl]
+        pairs = [(i, 1.0) for i in first] + [(i, -1.0) for i in last]
+        return _Iter(self, pairs, train=False, shuffle=False, num_threads=1)

@@ -41,11 +41,26 @@ class AdversarialLearner(object):
             self.reader = SyntheticReader(PWC_H, PWC_W, seed=8964 + self.rank)
             self.num_samples_val = self.reader.val_samples
             return
-        if ds in ('DAVIS2016', 'FBMS', 'SEGTRACK'):
+        if ds == 'DAVIS2016':
+            from ..data.davis2016_data_utils import Davis2016Reader
+            cfg = self.config
+            rd = Davis2016Reader(cfg.root_dir, max_temporal_len=cfg.max_temporal_len, min_temporal_len=cfg.min_temporal_len,
+                                 num_threads=cfg.num_threads, seed=8964 + self.rank)
+            if getattr(self, '_inference', False):
+                self.reader = rd.test_inputs(batch_size=cfg.batch_size, t_len=cfg.test_temporal_shift, with_fname=True,
+                                             test_crop=(1.0 if self.aug_test else cfg.test_crop), partition=cfg.test_partition)
+                self.reader.val_samples = rd.val_samples
+            else:
+                self.val_reader = rd.test_inputs(batch_size=cfg.batch_size, t_len=cfg.test_temporal_shift, test_crop=cfg.test_crop,
+                                                 partition='val')
+                self.num_samples_val = rd.val_samples
+                self.reader = rd.image_inputs(batch_size=cfg.batch_size, train_crop=cfg.train_crop, partition=cfg.train_partition)
+                self.reader.val_samples = self.num_samples_val
+            return
+        if ds in ('FBMS', 'SEGTRACK'):
             if not os.path.isdir(self.config.root_dir):
                 raise IOError("Dataset folder %s not found" % self.config.root_dir)
-            raise NotImplementedError("dataset readers for %s are a later row of the scope table (SURVEY.md 8f-2); "
-                                      "use --dataset=SYNTHETIC" % ds)
+            raise NotImplementedError("the %s reader is a later row of the scope table (SURVEY.md 8f-2); use DAVIS2016 or SYNTHETIC" % ds)
         raise IOError("Dataset should be DAVIS2016 / FBMS / SEGTRACK")
 
     # ------------------------------------------------------------------------------------------------ graphs
@@ -214,8 +229,9 @@ class AdversarialLearner(object):
     def epoch_end_callback(self, sess, sv, epoch_num):
         """adversarial_learner.py:422-448: validation IoU, save best / every save_freq epochs."""
         validation_iou = 0.0
+        vr = getattr(self, 'val_reader', None) or self.reader
         for _ in range(self.val_steps_per_epoch):
-            img1, img2, gt, _ = self.reader.batch(self.local_batch)
+            img1, img2, gt, _ = vr.batch(self.local_batch)
             self.feed(img1, img2)
             self.graph.forward()
             masks = self.graph.mask.cpu().numpy()
@@ -241,6 +257,7 @@ class AdversarialLearner(object):
         cfg = self.config
         self._init_dist()
         self.local_batch = cfg.batch_size
+        self._inference = True
         self.load_training_data()
         self.graph = CISGraph(cfg.img_height, cfg.img_width, self.local_batch, device=self.device, flow_normalizer=cfg.flow_normalizer,
                               cbn=cfg.cbn, epsilon=cfg.epsilon, with_pwc=True, train=False)
@@ -254,6 +271,7 @@ class AdversarialLearner(object):
         cfg = self.config
         self._init_dist()
         self.local_batch = len(self.test_crops)
+        self._inference = True
         self.load_training_data()
         self.graph = CISGraph(cfg.img_height, cfg.img_width, self.local_batch, device=self.device, flow_normalizer=cfg.flow_normalizer,
                               with_pwc=True, train=False)

@@ -1,5 +1,6 @@
 """CLI eval, same flag surface as the reference's test_generator.py (:42-144): per-category IoU / MAE of the generated
-masks (threshold 0.1, border-score disambiguation).  PNG / .mat dumps are a later row."""
+masks (threshold 0.1, border-score disambiguation); with --generate_visualization the PNG overlays and the .mat files of :93-118."""
+import os
 import sys
 
 import numpy as np
@@ -7,7 +8,9 @@ from absl import flags as gflags
 
 from unsupervised_detection_b200.common_flags import FLAGS
 from unsupervised_detection_b200.models.adversarial_learner import AdversarialLearner
-from unsupervised_detection_b200.models.utils.general_utils import compute_IoU, compute_mae
+from unsupervised_detection_b200.models.utils.general_utils import compute_IoU, compute_mae, postprocess_image, postprocess_mask
+
+des_width, des_height = 640, 384      # test_generator.py:14-15
 
 
 def _test_masks():
@@ -30,6 +33,19 @@ def _test_masks():
             mae = compute_mae(gt_mask=gt_mask, pred_mask_f=out_mask)
             CategoryIou.setdefault(category, []).append(iou)
             CategoryMae.setdefault(category, []).append(mae)
+            if FLAGS.generate_visualization:                       # test_generator.py:93-118
+                import cv2
+                import scipy.io as sio
+                save_dir = os.path.join(FLAGS.test_save_dir, category)
+                os.makedirs(save_dir, exist_ok=True)
+                k = len(CategoryIou[category])
+                bgr = postprocess_image(inference['input_image'][b])
+                red = postprocess_mask(out_mask.astype(np.float32))
+                res = cv2.resize(cv2.addWeighted(bgr, 0.5, red, 0.4, 0), (des_width, des_height))
+                cv2.imwrite(os.path.join(save_dir, "frame_{:08d}.png".format(k)), res)
+                sio.savemat(os.path.join(save_dir, 'result_{}.mat'.format(k)),
+                            {'flow': inference['gt_flow'][b], 'img1': cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB), 'pred_mask': out_mask,
+                             'gt_mask': inference['gt_masks'][b]})
             i += 1
     tot_ious = tot_maes = 0
     per_cat_iou = []

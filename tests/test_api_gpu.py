@@ -1,5 +1,6 @@
 """The reference-facing surface on the GPU: AdversarialLearner.step()/inference() through host buffers, and
 size-independent properties at BASELINE's full size (256x448, batch 4)."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -90,3 +91,30 @@ def test_inference_keys(learner):
     from unsupervised_detection_b200.models.utils.general_utils import compute_IoU
     iou, ann = compute_IoU(r['gt_masks'][0], r['gen_masks'][0])
     assert 0.0 <= iou <= 1.0
+
+
+def test_cli_eval_scripts_write_the_reference_dumps(tmp_path):
+    """test_generator.py / test_generator_ensemble.py end to end on synthetic frames: per-category report, PNG overlays and .mat
+    files with the keys the offline post-processing reads (generate_soft_score_from_buffer.py:45-92)."""
+    import scipy.io as sio
+    import test_generator as TG
+    import test_generator_ensemble as TE
+    from unsupervised_detection_b200.common_flags import FLAGS
+    out1, out2 = str(tmp_path / 'single'), str(tmp_path / 'ens')
+    FLAGS(['prog', '--dataset=SYNTHETIC', '--ckpt_file=synthetic', '--img_height=128', '--img_width=224', '--batch_size=2',
+           '--generate_visualization', '--test_save_dir=' + out1])
+    TG._test_masks()
+    cats = os.listdir(out1)
+    assert cats and any(f.endswith('.png') for f in os.listdir(os.path.join(out1, cats[0])))
+    mat = [f for f in os.listdir(os.path.join(out1, cats[0])) if f.endswith('.mat')][0]
+    m = sio.loadmat(os.path.join(out1, cats[0], mat))
+    assert {'flow', 'img1', 'pred_mask', 'gt_mask'} <= set(m) and m['flow'].shape == (128, 224, 2)
+    FLAGS(['prog', '--dataset=SYNTHETIC', '--ckpt_file=synthetic', '--img_height=128', '--img_width=224', '--batch_size=1',
+           '--generate_visualization', '--test_save_dir=' + out2])
+    TE._test_masks()
+    cats = os.listdir(out2)
+    mat = [f for f in os.listdir(os.path.join(out2, cats[0])) if f.endswith('.mat')][0]
+    m = sio.loadmat(os.path.join(out2, cats[0], mat))
+    for c in (85, 90, 95, 100):
+        assert 'img_1_%03d' % c in m and 'pred_mask_%03d' % c in m and 'gt_mask_%03d' % c in m
+    assert m['pred_mask_100'].shape[:2] == (128, 224)

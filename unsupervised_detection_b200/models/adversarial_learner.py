@@ -305,7 +305,7 @@ class AdversarialLearner(object):
         """adversarial_learner.py:606-623 -> dict with the reference's keys (numpy arrays)."""
         g = self.graph
         if batch is None:
-            batch = self.reader.batch(self.local_batch)
+            batch = self.reader.batch(1 if self.aug_test else self.local_batch)
         img1, img2, gt, names = batch
         if self.aug_test:
             # crops [0.85,0.9,0.95,1.0] of ONE frame pair, each resized back to 384x640 (davis2016_data_utils.py:328-354)

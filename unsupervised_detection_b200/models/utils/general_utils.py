@@ -44,3 +44,18 @@ def compute_IoU(gt_mask, pred_mask_f, threshold=0.1, mask_threshold=0.6):
 def compute_mae(gt_mask, pred_mask_f):
     """test_generator.py:38-40."""
     return np.mean(np.abs(gt_mask.astype(np.float32) - pred_mask_f.astype(np.float32)))
+
+
+# ---- dump helpers of test_generator*.py (models/utils/general_utils.py:22-51 of the reference), host side
+def postprocess_image(image):
+    """[H,W,3] in [-0.5,0.5] RGB -> uint8 BGR (general_utils.py:22-35)."""
+    import cv2
+    un = np.asarray((image + 0.5) * 255, np.uint8)
+    return cv2.cvtColor(un, cv2.COLOR_RGB2BGR)
+
+
+def postprocess_mask(mask):
+    """[H,W,1] in [0,1] -> uint8 [H,W,3] with the mask in the green slot (general_utils.py:37-51)."""
+    un = np.asarray(mask * 255.0, np.uint8)
+    tile = np.zeros_like(un, dtype=np.uint8)
+    return np.concatenate((tile, un, tile), axis=-1)

@@ -103,6 +103,11 @@ typedef struct {
 
 const char* cis_last_error(void);
 int cis_version(void);
+/* Host-side CRC-32C (Castagnoli, reflected 0x82F63B78), extend form: returns crc32c(concat(A, data)) given crc = crc32c(A)
+ * (pass 0 to start).  Used by the TF tensor-bundle checkpoint reader/writer; it replaces
+ * tensorflow/core/lib/hash/crc32c.h (TensorFlow 1.13, third-party, not vendored in the reference) behind
+ * tf.train.Saver (models/adversarial_learner.py:326-331).  Not a stream operation; no GPU needed. */
+uint32_t cis_crc32c(uint32_t crc, const void* data, size_t n);
 
 int cis_conv_igemm(const CisConv* d, cis_stream_t stream);
 /* which launches use the persistent warp-specialised halo kernel: 0 none, 1 thin single-chunk layers (default), 2 all eligible,

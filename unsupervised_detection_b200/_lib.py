@@ -81,7 +81,7 @@ _PROTOS = {
     'cis_cast_f32_to_bf16': [_p, _i64, _p],
     'cis_cast_bf16_to_f32': [_p, _i64, _i32, _i32, _i32, _p],
 }
-EXPORTS = sorted(list(_PROTOS) + ['cis_last_error', 'cis_version', 'cis_set_persist_mode'])
+EXPORTS = sorted(list(_PROTOS) + ['cis_last_error', 'cis_version', 'cis_set_persist_mode', 'cis_crc32c'])
 
 _lib = None
 
@@ -98,6 +98,8 @@ def load():
         lib.cis_version.restype = C.c_int
         lib.cis_set_persist_mode.argtypes = [C.c_int]
         lib.cis_set_persist_mode.restype = C.c_int
+        lib.cis_crc32c.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t]
+        lib.cis_crc32c.restype = C.c_uint32
         for name, args in _PROTOS.items():
             fn = getattr(lib, name)
             fn.argtypes = list(args) + [C.c_void_p]

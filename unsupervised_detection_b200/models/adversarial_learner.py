@@ -17,6 +17,7 @@ import torch
 from ..step_graph import CISGraph, PWC_H, PWC_W
 from ..data.synthetic import SyntheticReader
 from .. import params_init
+from .. import checkpoint as ckpt_io
 from .utils.general_utils import compute_all_IoU
 
 
@@ -91,6 +92,34 @@ class AdversarialLearner(object):
         self._init_params()
         self._pinned = None
 
+    # ------------------------------------------------------------------------------------------------ checkpoints
+    @staticmethod
+    def _is_ckpt(path):
+        """True for a native `.pt` file or a TF V2 bundle prefix (`<prefix>.index` exists; `.index` / `.data-*` spellings ok)."""
+        return bool(path) and (os.path.isfile(path) and path.endswith('.pt') or ckpt_io.is_bundle(ckpt_io.normalize_prefix(path)))
+
+    @staticmethod
+    def _read_ckpt(path, wanted, strict=True):
+        """-> ({internal name: tensor}, global_step|None) from a native `.pt` file or a tf.train.Saver V2 bundle."""
+        if os.path.isfile(path) and path.endswith('.pt'):
+            st = torch.load(path, map_location='cpu')
+            pr = st.get('params', st)
+            if strict:
+                miss = [k for k in wanted if k not in pr]
+                if miss:
+                    raise KeyError('checkpoint %s lacks %d variables, first %s' % (path, len(miss), miss[0]))
+            return {k: pr[k] for k in wanted if k in pr}, st.get('global_step')
+        prefix = ckpt_io.normalize_prefix(path)
+        want = set(wanted)
+        tfn = set(ckpt_io.to_tf_name(k, sep) for k in want for sep in ('//', '/')) | {'train_op/global_step', 'global_step'}
+        got, gs = ckpt_io.import_params(ckpt_io.read_bundle(prefix, names=lambda n: n in tfn), wanted, strict=strict)
+        return {k: torch.from_numpy(np.array(v, dtype=np.float32)) for k, v in got.items()}, gs
+
+    def _names(self, *scopes):
+        g = self.graph
+        stores = {'MaskNet': g.gen_store, 'FlownetS': g.rec_store, 'pwcnet': getattr(g, 'pwc_store', None)}
+        return [e[0] for sc in scopes for e in stores[sc].entries]
+
     def _init_params(self):
         cfg = self.config
         p = {}
@@ -100,21 +129,23 @@ class AdversarialLearner(object):
         fc = getattr(cfg, 'flow_ckpt', '')
         if fc.startswith('synthetic'):
             p.update(params_init.init_pwcnet(g.pwc_store.entries))
-        elif fc and os.path.isfile(fc):
-            p.update(torch.load(fc, map_location='cpu'))
+        elif self._is_ckpt(fc):
+            p.update(self._read_ckpt(fc, self._names('pwcnet'))[0])               # flow_saver.restore, adversarial_learner.py:339-341
             print("Flow net loaded from {}".format(fc))
         else:
             raise IOError("Could not find flow ckpt file. Aborting.")          # adversarial_learner.py:343
         if getattr(cfg, 'resume_train', False):
-            ck = cfg.full_model_ckpt if os.path.isfile(cfg.full_model_ckpt) else self._latest_checkpoint(cfg.checkpoint_dir)
+            ck = cfg.full_model_ckpt if self._is_ckpt(cfg.full_model_ckpt) else self._latest_checkpoint(cfg.checkpoint_dir)
             assert ck, "Found no checkpoint to resume training!"               # :351
-            st = torch.load(ck, map_location='cpu')
-            p.update(st['params'])
-            self.global_step = int(st.get('global_step', 0))
+            # self.saver covers every trainable variable + global_step (:326-327); PWC-Net is frozen but trainable-typed
+            # in the reference graph only through flow_saver, so it is optional here
+            pr, gs = self._read_ckpt(ck, self._names('MaskNet', 'FlownetS'))
+            p.update(pr)
+            p.update(self._read_ckpt(ck, self._names('pwcnet'), strict=False)[0])
+            self.global_step = int(gs or 0)
             print("Resumed training from model {}".format(ck))
-        elif getattr(cfg, 'recover_ckpt', '') and os.path.isfile(cfg.recover_ckpt):
-            st = torch.load(cfg.recover_ckpt, map_location='cpu')
-            p.update({k: v for k, v in st.get('params', st).items() if k.startswith('FlownetS/')})
+        elif self._is_ckpt(getattr(cfg, 'recover_ckpt', '')):
+            p.update(self._read_ckpt(cfg.recover_ckpt, self._names('FlownetS'))[0])  # recover_saver.restore, :354-358
             print("Recover net loaded from previous ckpt")
         else:
             print("No recover checkpoint found! Train Recover from Scratch")   # :360
@@ -122,21 +153,33 @@ class AdversarialLearner(object):
 
     @staticmethod
     def _latest_checkpoint(d):
+        """tf.train.latest_checkpoint(checkpoint_dir) (:349); falls back to the newest native `.pt` file."""
         if not d or not os.path.isdir(d):
             return None
+        tfp = ckpt_io.latest_checkpoint(d)
+        if tfp:
+            return tfp
         c = [f for f in os.listdir(d) if f.startswith('model') and f.endswith('.pt')]
         return os.path.join(d, max(c, key=lambda f: os.path.getmtime(os.path.join(d, f)))) if c else None
 
     def save(self, sess, checkpoint_dir, step):
-        """adversarial_learner.py:300-310.  Native format: torch file holding the trainables keyed by TF variable names
-        + global_step (Adam slots are not saved, like the reference's Saver)."""
+        """adversarial_learner.py:300-310: `saver.save(sess, checkpoint_dir/model[.best], global_step=step)` -- written as a
+        tf.train.Saver V2 bundle (`model-<step>.index` + `.data-00000-of-00001` + the `checkpoint` state file, trainables +
+        global_step, no Adam slots, max_to_keep=40 :327) that the reference itself can restore, plus the same tensors as a
+        native torch file."""
         if self.rank != 0:
             return
-        name = 'model.best.pt' if step == 'best' else 'model-%s.pt' % step
+        base = 'model.best' if step == 'best' else 'model-%s' % step
         print(" [*] Saving checkpoint to {}/model-{}".format(checkpoint_dir, step))
         os.makedirs(checkpoint_dir, exist_ok=True)
-        torch.save({'params': {k: v.cpu() for k, v in self.graph.export_params().items()}, 'global_step': self.global_step},
-                   os.path.join(checkpoint_dir, name))
+        params = {k: v.cpu() for k, v in self.graph.export_params().items()}
+        torch.save({'params': params, 'global_step': self.global_step}, os.path.join(checkpoint_dir, base + '.pt'))
+        ckpt_io.write_bundle(os.path.join(checkpoint_dir, base), ckpt_io.export_params(params, self.global_step))
+        for old in ckpt_io.update_checkpoint_state(checkpoint_dir, base, keep=40):
+            for suf in ('.index', '.data-00000-of-00001', '.pt'):
+                fp = os.path.join(checkpoint_dir, old + suf)
+                if os.path.isfile(fp) and old != 'model.best':
+                    os.remove(fp)
 
     # ------------------------------------------------------------------------------------------------ stepping
     def _allreduce(self):
@@ -288,15 +331,16 @@ class AdversarialLearner(object):
             self.build_test_graph()
 
     def restore(self, ckpt_file):
-        """test_generator.py:45-58: restores ALL trainables (incl. PWC-Net) from one checkpoint."""
+        """test_generator.py:45-58: restores ALL trainables (incl. PWC-Net) from one checkpoint (TF V2 bundle or native `.pt`)."""
         if ckpt_file.startswith('synthetic'):
             p = {}
             p.update(params_init.init_generator())
             p.update(params_init.init_recover())
             p.update(params_init.init_pwcnet(self.graph.pwc_store.entries))
-        elif ckpt_file and os.path.isfile(ckpt_file):
-            st = torch.load(ckpt_file, map_location='cpu')
-            p = st.get('params', st)
+        elif self._is_ckpt(ckpt_file):
+            p = params_init.init_recover()          # the mask path does not read the recover net; restored when present
+            p.update(self._read_ckpt(ckpt_file, self._names('MaskNet', 'pwcnet'))[0])
+            p.update(self._read_ckpt(ckpt_file, self._names('FlownetS'), strict=False)[0])
         else:
             raise IOError("Checkpoint file not found")                         # test_generator.py:58
         self.graph.load_params(p)

@@ -156,3 +156,46 @@ def test_checkpoint_save_resume_and_restore_roundtrip(learner, tmp_path):
     torch.cuda.synchronize()
     # same parameters, same kernels: the masks agree (bf16 round-off headroom only; wrong weights would differ by O(0.1))
     assert np.abs(r['gen_masks'] - L.graph.mask.cpu().numpy()).max() < 2e-3
+
+
+def test_step_summaries_written_like_collect_summaries(learner, tmp_path):
+    """adversarial_learner.py:260-298,391-403: on a summary step the event file gets the 8 loss scalars, 6 images and one clipped-
+    gradient histogram per recover and generator variable (both nets, although only one train op runs)."""
+    from unsupervised_detection_b200.summary import read_events
+    L = learner
+    L.config.checkpoint_dir = str(tmp_path / 'logs')
+    w = L.collect_summaries()
+    before = {k: v.clone() for k, v in L.graph.export_params().items()}
+    batch = L.reader.batch(4)
+    res = None
+    for _ in range(2):                              # summary_freq = 2: exactly one of the two steps is a summary step
+        res = L.step(batch, summarize=True)
+    w.close()
+    L.summary_writer = None
+    L.config.checkpoint_dir = ''
+    ev = read_events(w.path)
+    assert len(ev) == 2 and ev[1]['step'] == res['global_step']
+    vals = ev[1]['values']
+    scal = {v['tag']: v['simple_value'] for v in vals if 'simple_value' in v}
+    assert set(scal) == {'generator', 'recover', 'red_rate', 'red_rate_compl', 'reconstruction_loss', 'reconstruction_compl_loss',
+                         'denominator_red_rate', 'denominator_red_rate_compl'}
+    assert all(np.isfinite(x) for x in scal.values()) and scal['denominator_red_rate'] > L.config.epsilon
+    assert abs(scal['generator'] - (scal['red_rate'] + scal['red_rate_compl'])) < 1e-4
+    imgs = [v for v in vals if 'image' in v]
+    assert [v['tag'] for v in imgs] == ['input_image/image', 'next_image/image', 'masked_flow/image', 'PWC_Flow/image', 'Rec_flow/image',
+                                        'Rec_flow_compl/image']
+    assert (imgs[0]['image']['height'], imgs[0]['image']['width']) == (256, 448)
+    assert (imgs[1]['image']['height'], imgs[1]['image']['width']) == (384, 640)
+    hist = [v for v in vals if 'histo' in v]
+    nR, nG = len(L.graph.rec_store.entries), len(L.graph.gen_store.entries)
+    assert len(hist) == nR + nG
+    assert all(h['tag'].startswith('FlownetS//') and h['tag'].endswith('/gradients') for h in hist[:nR])
+    assert all(h['tag'].startswith('MaskNet//') for h in hist[nR:]) and hist[nR]['tag'] == 'MaskNet//conv1/kernel/gradients'
+    for h in (hist[0], hist[nR], hist[-1]):
+        hh = h['histo']
+        assert hh['num'] > 0 and -0.2001 <= hh['min'] <= hh['max'] <= 0.2001 and sum(hh['bucket']) == hh['num']
+    assert any(h['histo']['max'] > 0 for h in hist[:nR]) and any(h['histo']['max'] > 0 for h in hist[nR:])
+    # the summary pre-pass must not have changed what the two steps train: both nets' parameters still finite, one net updated per step
+    after = L.graph.export_params()
+    assert all(torch.isfinite(v).all() for v in after.values())
+    assert any(not torch.equal(after[k], before[k]) for k in before if not k.startswith('pwcnet/'))

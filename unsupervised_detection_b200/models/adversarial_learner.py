@@ -218,7 +218,7 @@ class AdversarialLearner(object):
             ev.record(self._copy_stream)
         self._staged = (batch[0], d1, d2, ev)
 
-    def step(self, batch=None, fetch_losses=None, use_graph=True, next_batch=None):
+    def step(self, batch=None, fetch_losses=None, use_graph=True, next_batch=None, summarize=False):
         """One iteration of the training loop body (adversarial_learner.py:380-409): picks train_recover_op or
         train_generator_op from the running step counter, consumes one batch, returns {global_step, loss_*?}."""
         cfg = self.config
@@ -231,6 +231,8 @@ class AdversarialLearner(object):
         if batch is None:
             batch = self.reader.batch(self.local_batch)
         self.feed(batch[0], batch[1])
+        summarize = summarize and step % cfg.summary_freq == 0                 # :391-394 (same decision on every rank)
+        other_grads = self._summary_prepass(mode) if summarize else None
         self.graph.train_step(mode, allreduce=self._allreduce(), use_graph=use_graph)
         if next_batch is not None:
             self.prefetch(next_batch)          # overlaps this step's kernels; consumed by the next step() call
@@ -238,7 +240,66 @@ class AdversarialLearner(object):
         if fetch_losses if fetch_losses is not None else (step % cfg.summary_freq == 0):
             L = self.graph.losses()                                            # device -> host read
             res["loss_recover"], res["loss_generator"] = L['recover'], L['generator']
+        if summarize:
+            self._write_step_summary(self.global_step, mode, other_grads)      # add_summary(results["summary"], gs), :403
         return res
+
+    # ------------------------------------------------------------------------------------------------ summaries
+    def collect_summaries(self):
+        """adversarial_learner.py:260-298: opens the event file under checkpoint_dir (the Supervisor's logdir, :362-364) on
+        rank 0.  Step summaries = 8 loss scalars, 6 images (first batch element), clipped-gradient histograms of every
+        recover and generator variable; validation summary = "IoU on Validation"."""
+        from ..summary import SummaryWriter
+        cfg = self.config
+        self.summary_writer = SummaryWriter(cfg.checkpoint_dir) if (self.rank == 0 and getattr(cfg, 'checkpoint_dir', '')) else None
+        return self.summary_writer
+
+    def _net_gradients(self, mode):
+        """Host copy of one net's per-variable gradients as train_op returns them (loss_utils.py:28-32: clipped to +-0.2)."""
+        store = self.graph.rec_store if mode == 'R' else self.graph.gen_store
+        flat = store.grad.detach().clamp(-0.2, 0.2).cpu().numpy()
+        return [(name, flat[off:off + n]) for name, _, n, off, _ in store.entries]
+
+    def _summary_prepass(self, mode):
+        """The merged `step_sum` needs BOTH nets' gradients on a summary step (:283-289) although only one train op runs:
+        evaluate the other net's gradient on the same batch and parameters before the optimiser step."""
+        other = 'G' if mode == 'R' else 'R'
+        g = self.graph
+        g.forward()
+        g.bwd[other].run()
+        ar = self._allreduce()
+        if ar is not None:
+            ar((g.rec_store if other == 'R' else g.gen_store).grad)
+        torch.cuda.synchronize()
+        return self._net_gradients(other)
+
+    def _write_step_summary(self, gs, mode, other_grads):
+        w = getattr(self, 'summary_writer', None)
+        if w is None:
+            return
+        from .utils.flow_utils import flow_to_image_pm
+        from .utils.general_utils import disambiguate_forw_back
+        g = self.graph
+        B = g.B
+        for k, v in g.losses(full=True).items():                               # :262-263
+            w.add_scalar(k, v)
+        flow = g.flow.cpu().numpy()
+        mask = g.mask.cpu().numpy()
+        pred = g.pred.cpu().numpy()
+        rec = pred[:B] * mask + flow * (1.0 - mask)                            # self.pred_flow, :251
+        rec_c = pred[B:2 * B] * (1.0 - mask) + flow * mask                     # self.pred_flow_compl, :252
+        w.add_image("input_image", g.image[:1].cpu().numpy())                  # :265-268
+        w.add_image("next_image", g.img2[:1].cpu().numpy())
+        flow_img = flow_to_image_pm(flow)
+        w.add_image("masked_flow", flow_img * (1.0 - disambiguate_forw_back(mask)))   # :269-272
+        w.add_image("PWC_Flow", flow_img)
+        w.add_image("Rec_flow", flow_to_image_pm(rec))
+        w.add_image("Rec_flow_compl", flow_to_image_pm(rec_c))
+        grads = {mode: self._net_gradients(mode), ('G' if mode == 'R' else 'R'): other_grads}
+        for m in ('R', 'G'):                                                   # :283-289, recover first
+            for name, gv in grads[m]:
+                w.add_histogram(ckpt_io.to_tf_name(name) + "/gradients", gv)
+        w.flush_step(gs)
 
     def train(self, config):
         """adversarial_learner.py:312-420."""
@@ -250,9 +311,10 @@ class AdversarialLearner(object):
             print("-------------------------------------")
             print("Training {} Recover and {} Generator".format(config.iters_rec, config.iters_gen))
             print("-------------------------------------")
+        self.collect_summaries()
         for step in count(start=1):
             start_time = time.time()
-            results = self.step()
+            results = self.step(summarize=True)
             if step % config.summary_freq == 0 and self.rank == 0:
                 train_epoch = math.ceil(step / self.train_steps_per_epoch)
                 train_step = step - (train_epoch - 1) * self.train_steps_per_epoch
@@ -287,6 +349,10 @@ class AdversarialLearner(object):
             validation_iou = float(t)
         validation_iou /= self.val_steps_per_epoch * self.config.batch_size
         if self.rank == 0:
+            w = getattr(self, 'summary_writer', None)
+            if w is not None:
+                w.add_scalar("IoU on Validation", validation_iou)             # :296-298, :436-439
+                w.flush_step(epoch_num)
             print("Epoch [{}] Validation IoU: {}".format(epoch_num, validation_iou))
         if validation_iou > self.min_val_iou:
             self.save(sess, self.config.checkpoint_dir, 'best')

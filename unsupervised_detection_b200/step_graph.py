@@ -233,6 +233,13 @@ class CISGraph(object):
         self.graphs[mode] = (g1, g2)
         return self.graphs[mode]
 
-    def losses(self):
+    def losses(self, full=False):
+        """The `losses` dict of adversarial_learner.py:196-204 (device -> host read).  full=True adds the four first-sample
+        diagnostics (:201-204) taken from the per-sample Charbonnier sums {rec, rec_c, prior, den, den_c}."""
         s = self.scalars.tolist()
-        return dict(generator=s[0], recover=s[1], red_rate=s[2], red_rate_compl=s[3])
+        out = dict(generator=s[0], recover=s[1], red_rate=s[2], red_rate_compl=s[3])
+        if full:
+            r = self.sums[0].tolist()
+            out.update(reconstruction_loss=r[0], reconstruction_compl_loss=r[1], denominator_red_rate=r[3] + self.eps_rr,
+                       denominator_red_rate_compl=r[4] + self.eps_rr)
+        return out

@@ -42,11 +42,19 @@ class AdversarialLearner(object):
             self.reader = SyntheticReader(PWC_H, PWC_W, seed=8964 + self.rank)
             self.num_samples_val = self.reader.val_samples
             return
-        if ds == 'DAVIS2016':
-            from ..data.davis2016_data_utils import Davis2016Reader
+        if ds in ('DAVIS2016', 'FBMS', 'SEGTRACK'):
             cfg = self.config
-            rd = Davis2016Reader(cfg.root_dir, max_temporal_len=cfg.max_temporal_len, min_temporal_len=cfg.min_temporal_len,
-                                 num_threads=cfg.num_threads, seed=8964 + self.rank)
+            if ds == 'DAVIS2016':
+                from ..data.davis2016_data_utils import Davis2016Reader as Reader
+            elif ds == 'FBMS':
+                from ..data.fbms_data_utils import FBMS59Reader as Reader
+                if getattr(self, '_inference', False) and self.aug_test:
+                    assert 'FBMS' in cfg.root_dir                              # adversarial_learner.py:542
+            else:
+                from ..data.segtrackv2_data_utils import SegTrackV2Reader as Reader
+            rd = Reader(cfg.root_dir, max_temporal_len=cfg.max_temporal_len, min_temporal_len=cfg.min_temporal_len,
+                        num_threads=cfg.num_threads, seed=8964 + self.rank)
+            self.dataset_reader = rd
             if getattr(self, '_inference', False):
                 self.reader = rd.test_inputs(batch_size=cfg.batch_size, t_len=cfg.test_temporal_shift, with_fname=True,
                                              test_crop=(1.0 if self.aug_test else cfg.test_crop), partition=cfg.test_partition)
@@ -57,11 +65,9 @@ class AdversarialLearner(object):
                 self.num_samples_val = rd.val_samples
                 self.reader = rd.image_inputs(batch_size=cfg.batch_size, train_crop=cfg.train_crop, partition=cfg.train_partition)
                 self.reader.val_samples = self.num_samples_val
+            if ds == 'FBMS':
+                self.num_categories = rd.num_categories                       # :52
             return
-        if ds in ('FBMS', 'SEGTRACK'):
-            if not os.path.isdir(self.config.root_dir):
-                raise IOError("Dataset folder %s not found" % self.config.root_dir)
-            raise NotImplementedError("the %s reader is a later row of the scope table (SURVEY.md 8f-2); use DAVIS2016 or SYNTHETIC" % ds)
         raise IOError("Dataset should be DAVIS2016 / FBMS / SEGTRACK")
 
     # ------------------------------------------------------------------------------------------------ graphs

@@ -205,6 +205,10 @@ def _pow2_cols(c):
 import os as _os
 SPLITK = _os.environ.get('CIS_SPLITK', '0') == '1'   # measured r01: not a win at batch 4; kept selectable
 SPLITK_MAX = int(_os.environ.get('CIS_SPLITK_MAX', '4'))
+# experiment switch (default off = current behaviour): stride-1 layers whose padded input width is <= this many channels and that
+# have >= 16 taps (generator conv1 5x5x8, recover flow1 5x5) use the K-dense gather kernel (ceil(taps*cin8/64) pipeline steps)
+# instead of the halo kernel (one step and one mostly-zero BN x 128 B weight tile per tap); see DESIGN.md section 6, E1
+HALO_SKIP_THIN = int(_os.environ.get('CIS_HALO_SKIP_THIN', '0'))
 
 
 def setup_splitk(d, device, keep):
@@ -252,6 +256,8 @@ def setup_halo(d, taps, dil, n_tiles):
     best = None
     ntaps = len(taps)
     m_chunks = sum(d.src[i].chunks for i in range(d.nsrc))
+    if HALO_SKIP_THIN and m_chunks * 8 <= HALO_SKIP_THIN and ntaps >= 16:
+        return False
     nchunks = -(-m_chunks // 8)
     nhs = 2 if nchunks > 1 else 1
     import os

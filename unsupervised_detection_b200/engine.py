@@ -5,6 +5,8 @@ step and backward for the generator step -- that are then replayed (optionally i
 PyTorch only owns device memory and streams here; there is no autograd and no torch compute on the hot path.
 """
 import ctypes as C
+import os
+
 import numpy as np
 import torch
 
@@ -202,15 +204,14 @@ def _pow2_cols(c):
     return 1024
 
 
-import os as _os
-SPLITK = _os.environ.get('CIS_SPLITK', '0') == '1'   # measured r01: not a win at batch 4; kept selectable
-SPLITK_MAX = int(_os.environ.get('CIS_SPLITK_MAX', '4'))
-SPLITK_NCTA = int(_os.environ.get('CIS_SPLITK_NCTA', '64'))          # only launches with at most this many CTAs are split
-SPLITK_MIN_UNITS = int(_os.environ.get('CIS_SPLITK_MIN_UNITS', '0'))  # ... and at least this many K units (64-wide blocks / chunks)
+SPLITK = os.environ.get('CIS_SPLITK', '0') == '1'   # measured r01: not a win at batch 4; kept selectable
+SPLITK_MAX = int(os.environ.get('CIS_SPLITK_MAX', '4'))
+SPLITK_NCTA = int(os.environ.get('CIS_SPLITK_NCTA', '64'))          # only launches with at most this many CTAs are split
+SPLITK_MIN_UNITS = int(os.environ.get('CIS_SPLITK_MIN_UNITS', '0'))  # ... and at least this many K units (64-wide blocks / chunks)
 # experiment switch (default off = current behaviour): stride-1 layers whose padded input width is <= this many channels and that
 # have >= 16 taps (generator conv1 5x5x8, recover flow1 5x5) use the K-dense gather kernel (ceil(taps*cin8/64) pipeline steps)
 # instead of the halo kernel (one step and one mostly-zero BN x 128 B weight tile per tap); see DESIGN.md section 6, E1
-HALO_SKIP_THIN = int(_os.environ.get('CIS_HALO_SKIP_THIN', '0'))
+HALO_SKIP_THIN = int(os.environ.get('CIS_HALO_SKIP_THIN', '0'))
 
 
 def setup_splitk(d, device, keep):
@@ -262,7 +263,6 @@ def setup_halo(d, taps, dil, n_tiles):
         return False
     nchunks = -(-m_chunks // 8)
     nhs = 2 if nchunks > 1 else 1
-    import os
     force = int(os.environ.get('CIS_FORCE_MT128', '0')) if d.BN == 128 else 0
     for MT in (1, 2, 3, 4):
         if MT * d.BN > 512 or (force and MT != force):

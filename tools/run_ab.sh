@@ -1,0 +1,18 @@
+# One GPU call that measures the round-2 experiment switches of DESIGN.md section 6 against the default build:
+# per-launch CUDA-graph-replay times (tools/time_ops.py) + the whole-step bench for each configuration.
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/run_ab.sh'
+mkdir -p gpurun_out/ab
+run() {   # name, env assignments...
+  name=$1; shift
+  env "$@" TIME_OPS_JSON=gpurun_out/ab/$name.json timeout 200 python tools/time_ops.py > gpurun_out/ab/$name.txt 2>&1
+  env "$@" timeout 120 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/ab/$name.bench.json 2> gpurun_out/ab/$name.bench.err
+  echo "== $name: $(head -c 300 gpurun_out/ab/$name.bench.json | python -c 'import sys,json; d=json.loads(sys.stdin.readline() or "{}"); print(d.get("value"), d.get("ms_per_step"))' 2>/dev/null)  $(grep -m1 "sum of warm" gpurun_out/ab/$name.txt)"
+}
+run base
+run e1_thin8 CIS_HALO_SKIP_THIN=8
+run e1_thin64 CIS_HALO_SKIP_THIN=64
+run e2_sk16 CIS_SPLITK=1 CIS_SPLITK_MAX=16 CIS_SPLITK_NCTA=8 CIS_SPLITK_MIN_UNITS=32
+run e2_sk8 CIS_SPLITK=1 CIS_SPLITK_MAX=8 CIS_SPLITK_NCTA=16 CIS_SPLITK_MIN_UNITS=16
+for v in e1_thin8 e1_thin64 e2_sk16 e2_sk8; do
+  echo "---- $v vs base"; python tools/ab_diff.py gpurun_out/ab/base.json gpurun_out/ab/$v.json 3 | head -25
+done

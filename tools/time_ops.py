@@ -48,6 +48,9 @@ for pname, plan, w in (('fwd', g.fwd, 4), ('bwdG', g.bwd['G'], 3), ('bwdR', g.bw
             d = a[0]._obj
             info = 'tma%d N%d %dx%d taps%d cout%d K%d sp%d' % (d.tma, d.N, d.OH, d.OW, d.ntaps, d.Cout, d.K_pad, d.splits)
         rows.append((pname, w, name, us, fl, info))
+if os.environ.get('TIME_OPS_JSON'):
+    # one row per launch, keyed by (plan, index-in-plan): lets tools/ab_diff.py line up the same layer across two configurations
+    json.dump([dict(plan=p, w=w, op=n, us=us, flops=fl, info=info) for p, w, n, us, fl, info in rows], open(os.environ['TIME_OPS_JSON'], 'w'))
 tot = sum(r[1] * r[3] for r in rows) / 4
 print('sum of warm per-op times per step: %.1f us' % tot)
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0])

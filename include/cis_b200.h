@@ -80,7 +80,8 @@ typedef struct {
    * fixed order (deterministic), applies the epilogue and resets the ticket. */
   int32_t splits;        /* 0/1 = off */
   float* sk_scratch;     /* >= tiles * splits * 128 * BN floats (tiles = grid.x * grid.y * MT); need not be initialised */
-  int32_t* sk_counters;  /* zero-initialised, >= grid.x * grid.y ints */
+  int32_t* sk_counters;  /* zero-initialised, >= grid.x * grid.y ints; NULL = two-launch mode: the conv kernel only writes the slices and
+                          * a second (parallel) kernel launched by the same call sums them in the same fixed order + runs the epilogue */
 } CisConv;
 
 /* Weight gradient of the same convolution: dWp[co][(t,c)] += sum_rows g[row][co] * A[row][(t,c)]  (fp32, split-K atomics).

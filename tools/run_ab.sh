@@ -11,8 +11,16 @@ run() {   # name, env assignments...
 run base
 run e1_thin8 CIS_HALO_SKIP_THIN=8
 run e1_thin64 CIS_HALO_SKIP_THIN=64
-run e2_sk16 CIS_SPLITK=1 CIS_SPLITK_MAX=16 CIS_SPLITK_NCTA=8 CIS_SPLITK_MIN_UNITS=32
-run e2_sk8 CIS_SPLITK=1 CIS_SPLITK_MAX=8 CIS_SPLITK_NCTA=16 CIS_SPLITK_MIN_UNITS=16
-for v in e1_thin8 e1_thin64 e2_sk16 e2_sk8; do
+# two-launch split-K is experimental: validate it first, skip its timing runs if the parity test fails
+if CIS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_conv_engine_gpu.py -x -q -k two_launch > gpurun_out/ab/two_launch_test.txt 2>&1; then
+  run e2_sk2_16 CIS_SPLITK=2 CIS_SPLITK_MAX=16 CIS_SPLITK_NCTA=8 CIS_SPLITK_MIN_UNITS=32
+  run e2_sk2_8 CIS_SPLITK=2 CIS_SPLITK_MAX=8 CIS_SPLITK_NCTA=16 CIS_SPLITK_MIN_UNITS=16
+  run e2_sk2_wide CIS_SPLITK=2 CIS_SPLITK_MAX=16 CIS_SPLITK_NCTA=32 CIS_SPLITK_MIN_UNITS=8
+else
+  echo "two-launch split-K parity FAILED:"; tail -5 gpurun_out/ab/two_launch_test.txt
+fi
+run e2_sk1_16 CIS_SPLITK=1 CIS_SPLITK_MAX=16 CIS_SPLITK_NCTA=8 CIS_SPLITK_MIN_UNITS=32
+for v in e1_thin8 e1_thin64 e2_sk2_16 e2_sk2_8 e2_sk2_wide e2_sk1_16; do
+  [ -f gpurun_out/ab/$v.json ] || continue
   echo "---- $v vs base"; python tools/ab_diff.py gpurun_out/ab/base.json gpurun_out/ab/$v.json 3 | head -25
 done

@@ -432,7 +432,8 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
       const int tile_id = blockIdx.x * gridDim.y + ny;
       float* tile0 = p.sk_scratch + (size_t)tile_id * nsplit * kBM * BN;
       splitk_store_partial<BN>(tile0 + (size_t)blockIdx.z * kBM * BN, t_row, row);
-      if (splitk_ticket(p.sk_counters + tile_id, nsplit, tid, &s_flag)) {
+      // sk_counters == NULL: two-launch mode, splitk_finish_kernel reduces the slices and runs the epilogue
+      if (p.sk_counters != nullptr && splitk_ticket(p.sk_counters + tile_id, nsplit, tid, &s_flag)) {
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
           float v[16];
@@ -650,7 +651,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
       for (int m = 0; m < MT; ++m)
         splitk_store_partial<BN>(p.sk_scratch + (((size_t)tile_id * MT + m) * nsplit + blockIdx.z) * kBM * BN,
                                  tmem + ((uint32_t)(warp * 32) << 16) + m * BN, r);
-      last = splitk_ticket(p.sk_counters + tile_id, nsplit, tid, &s_flag);
+      last = p.sk_counters != nullptr ? splitk_ticket(p.sk_counters + tile_id, nsplit, tid, &s_flag) : false;   // NULL: two-launch mode
     }
     if (last) {
       for (int m = 0; m < MT; ++m) {
@@ -725,6 +726,62 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
 }
 
 
+// ======================================================================================================= split-K finish
+// Second launch of the two-launch split-K mode (CisConv.sk_counters == NULL).  The single-launch mode lets the last-arriving CTA of
+// a tile read all nsplit x 64 KB slices by itself -- one SM pulling up to 1 MB through L2 -- which costs more than the split saves
+// on the low-resolution layers it is meant for.  Here the reduction + fused epilogue of a tile is spread over 128 * BN/16 threads
+// of several CTAs: thread = (accumulator row, 16-column group), column group fastest so slice reads and NHWC stores coalesce.
+template <int BN>
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const __grid_constant__ CisConv p) {
+  constexpr int G = BN / 16;                               // 16-column groups per row
+  constexpr int kBlock = (128 * G < 256) ? 128 * G : 256;
+  constexpr int kSub = 128 * G / kBlock;                   // CTAs per (tile, m)
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tid = threadIdx.x;
+  if (tid >= kBlock) return;
+  const int m = blockIdx.z / kSub;
+  const int item = (blockIdx.z % kSub) * kBlock + tid;
+  const int r = item / G, c0 = (item % G) * 16;
+  const int ny = blockIdx.y;
+  const int nsplit = p.splits;
+  const int tile_id = blockIdx.x * gridDim.y + ny;
+  bool valid;
+  size_t dpix = 0;
+  const float* tile0;
+  if (p.halo) {
+    const int MT = p.MT, d = p.dil;
+    const int Hp0 = (p.OH + d - 1) / d, Wp0 = (p.OW + d - 1) / d;
+    const int tiles_x = (Wp0 + 7) / 8, tiles_y = (Hp0 + 16 * MT - 1) / (16 * MT);
+    int bid = blockIdx.x;
+    const int tx = bid % tiles_x; bid /= tiles_x;
+    const int ty = bid % tiles_y; bid /= tiles_y;
+    const int ph = bid % (d * d);
+    const int n = bid / (d * d);
+    const int pa = ph / d, pb = ph % d;
+    const int gy = ty * 16 * MT + 16 * m + (r >> 3), gx = tx * 8 + (r & 7);
+    const int oy = pa + d * gy, ox = pb + d * gx;
+    valid = oy < p.OH && ox < p.OW;
+    if (valid) dpix = (size_t)(n * p.DH + oy * p.osh + p.oa) * p.DW + ox * p.osw + p.ob;
+    tile0 = p.sk_scratch + ((size_t)tile_id * MT + m) * nsplit * kBM * BN;
+  } else {
+    const int M = p.N * p.OH * p.OW;
+    const int g = blockIdx.x * kBM + r;
+    valid = g < M;
+    if (valid) {
+      const int ow = g % p.OW;
+      const int t = g / p.OW;
+      const int oh = t % p.OH;
+      const int n = t / p.OH;
+      dpix = (size_t)(n * p.DH + oh * p.osh + p.oa) * p.DW + ow * p.osw + p.ob;
+    }
+    tile0 = p.sk_scratch + (size_t)tile_id * nsplit * kBM * BN;
+  }
+  if (!valid) return;
+  float v[16];
+  splitk_reduce16<BN>(tile0, nsplit, r, c0, v);
+  epi_chunk(p, v, ny * BN + c0, dpix);
+}
 // ======================================================================================================= persistent halo conv
 // Same math as conv_halo_kernel (TMA halo path only), restructured as a persistent, fully warp-specialised pipeline so the
 // per-tile latency chain (halo fetch -> MMAs -> TMEM read-back -> stores) of one tile overlaps the next tiles:
@@ -1143,6 +1200,15 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 }
 
 template <int BN>
+static cudaError_t launch_splitk_finish(const CisConv* d, dim3 main_grid, cudaStream_t st) {
+  constexpr int G = BN / 16;
+  constexpr int kBlock = (128 * G < 256) ? 128 * G : 256;
+  constexpr int kSub = 128 * G / kBlock;
+  const int mt = d->halo ? d->MT : 1;
+  return launch_pdl(splitk_finish_kernel<BN>, dim3(main_grid.x, main_grid.y, mt * kSub), dim3(kBlock), 0, st, *d);
+}
+
+template <int BN>
 static int launch_fwd(const CisConv* d, cudaStream_t st) {
   using Cfg = FwdCfg<BN>;
   static bool attr_set = false;
@@ -1155,11 +1221,15 @@ static int launch_fwd(const CisConv* d, cudaStream_t st) {
   int splits = d->splits > 1 ? d->splits : 1;
   if (splits > 1) {
     const int nkb = d->K_pad / kBK, per = (nkb + splits - 1) / splits;
-    if (!d->sk_scratch || !d->sk_counters || (splits - 1) * per >= nkb) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm: bad split-K setup");
+    if (!d->sk_scratch || (splits - 1) * per >= nkb) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm: bad split-K setup");
   }
   dim3 grid((M + kBM - 1) / kBM, d->n_tiles, splits);
   cudaError_t le = launch_pdl(conv_igemm_kernel<BN>, grid, dim3(kThreads), Cfg::kSmem, st, *d);
   if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_igemm)");
+  if (splits > 1 && !d->sk_counters) {
+    le = launch_splitk_finish<BN>(d, grid, st);
+    if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(splitk_finish)");
+  }
   return cis_check_launch("conv_igemm");
 }
 
@@ -1231,7 +1301,7 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   int splits = d->splits > 1 ? d->splits : 1;
   if (splits > 1) {
     const int per = (nchunks + splits - 1) / splits;
-    if (!d->sk_scratch || !d->sk_counters || (splits - 1) * per >= nchunks) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm(halo): bad split-K setup");
+    if (!d->sk_scratch || (splits - 1) * per >= nchunks) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm(halo): bad split-K setup");
   }
   dim3 grid(tiles * dd * dd * d->N, d->n_tiles, splits);
   // TMA halo path: undilated, every concat source except the last a multiple of 64 channels (a chunk never straddles sources)
@@ -1278,6 +1348,10 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   }
   cudaError_t le = launch_pdl(conv_halo_kernel<BN>, grid, dim3(kThreads), smem, st, *d, halo_stage, BS, nhs, maps, use_tma);
   if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_halo)");
+  if (splits > 1 && !d->sk_counters) {
+    le = launch_splitk_finish<BN>(d, grid, st);
+    if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(splitk_finish)");
+  }
   return cis_check_launch("conv_halo");
 }
 

@@ -107,7 +107,17 @@ class Plan(object):
             main.wait_event(ev)
 
     def count(self):
-        return sum(1 for op in self.ops if op[0] is not None)
+        """Kernel launches of one replay (a two-launch split-K conv counts twice)."""
+        n = 0
+        for fn, args, name, _, _ in self.ops:
+            if fn is None:
+                continue
+            n += 1
+            if name == 'cis_conv_igemm':
+                d = args[0]._obj
+                if d.splits > 1 and not d.sk_counters:
+                    n += 1
+        return n
 
     def extend(self, other):
         self.ops += other.ops
@@ -204,7 +214,10 @@ def _pow2_cols(c):
     return 1024
 
 
-SPLITK = os.environ.get('CIS_SPLITK', '0') == '1'   # measured r01: not a win at batch 4; kept selectable
+# split-K of launches that cover only a few SMs.  0 = off (default; the single-launch mode measured slower in r01),
+# 1 = single launch, last-arriving CTA reduces (deterministic ticket), 2 = two launches: partial slices + a parallel finish kernel
+# (written after r01's GPU budget was spent: compiled, covered by tests/test_conv_engine_gpu.py, not yet timed -- DESIGN.md section 6 E2)
+SPLITK = int(os.environ.get('CIS_SPLITK', '0'))
 SPLITK_MAX = int(os.environ.get('CIS_SPLITK_MAX', '4'))
 SPLITK_NCTA = int(os.environ.get('CIS_SPLITK_NCTA', '64'))          # only launches with at most this many CTAs are split
 SPLITK_MIN_UNITS = int(os.environ.get('CIS_SPLITK_MIN_UNITS', '0'))  # ... and at least this many K units (64-wide blocks / chunks)
@@ -236,9 +249,14 @@ def setup_splitk(d, device, keep):
     if splits < 2:
         return
     sc = torch.empty(ncta * mt * splits * 128 * d.BN, dtype=torch.float32, device=device)
-    ct = torch.zeros(ncta, dtype=torch.int32, device=device)
-    keep += [sc, ct]
-    d.splits, d.sk_scratch, d.sk_counters = splits, sc.data_ptr(), ct.data_ptr()
+    keep.append(sc)
+    d.splits, d.sk_scratch = splits, sc.data_ptr()
+    if int(SPLITK) == 2:
+        d.sk_counters = None                      # NULL selects the two-launch mode in cis_conv_igemm
+    else:
+        ct = torch.zeros(ncta, dtype=torch.int32, device=device)
+        keep.append(ct)
+        d.sk_counters = ct.data_ptr()
 
 
 def setup_halo(d, taps, dil, n_tiles):

@@ -112,6 +112,7 @@ uint32_t cis_crc32c(uint32_t crc, const void* data, size_t n);
 
 int cis_conv_igemm(const CisConv* d, cis_stream_t stream);
 /* which launches use the persistent warp-specialised halo kernel: 0 none, 1 thin single-chunk layers (default), 2 all eligible,
+ * 3 = 1 + the weight-stationary variant for thin layers whose whole weight set fits in shared memory (experimental),
  * -1 back to the default / CIS_PERSIST_MODE environment variable.  Host-side switch, not a stream operation. */
 int cis_set_persist_mode(int mode);
 int cis_conv_wgrad(const CisWgrad* d, cis_stream_t stream);

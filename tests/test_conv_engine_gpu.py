@@ -107,3 +107,28 @@ def test_conv_engine_split_k_two_launch(case):
     if 'dx_err' in r2:
         assert r2['dx_err'] <= tol(r2['dx_ref']), r2
         assert r2['dx_err'] == r1['dx_err']
+
+
+WS_CASES = [CASES[2], CASES[11], CASES[16], CASES[17], CASES[18], CASES[0],
+            dict(N=2, H=64, W=96, cins=[5], cout=32, k=5, act=ACT_ELU, bn=True, backward=False),
+            dict(N=3, H=48, W=80, cins=[16, 16, 16, 2], cout=2, k=5, backward=False)]
+
+
+@pytest.mark.skipif(os.environ.get('CIS_TEST_EXPERIMENTAL') != '1',
+                    reason='weight-stationary persistent kernel was written after the GPU budget of round 1 was spent: compiled but '
+                           'never run; set CIS_TEST_EXPERIMENTAL=1 to validate it before enabling CIS_PERSIST_WS=1')
+@pytest.mark.parametrize('case', WS_CASES, ids=lambda c: 'k%d_c%s_o%d_%dx%d' % (c['k'], '+'.join(map(str, c['cins'])), c['cout'], c['H'], c['W']))
+def test_conv_engine_weight_stationary_persistent(case):
+    """Persist mode 3: thin layers whose whole weight set fits in shared memory keep it resident across the tiles of a CTA."""
+    from unsupervised_detection_b200 import _lib
+    r0 = run_conv_case(**case)
+    _lib.load().cis_set_persist_mode(3)
+    try:
+        r = run_conv_case(**case)
+    finally:
+        _lib.load().cis_set_persist_mode(-1)
+    tol = lambda ref: 2 ** -7 * ref + 1e-3
+    assert r['fwd_err'] <= tol(r['fwd_ref']), r
+    assert r['fwd_err'] == r0['fwd_err']          # same MMAs in the same order: bit-identical to the default kernels
+    if 'dx_err' in r:
+        assert r['dx_err'] <= tol(r['dx_ref']), r

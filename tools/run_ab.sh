@@ -19,8 +19,13 @@ if CIS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_conv_engine_g
 else
   echo "two-launch split-K parity FAILED:"; tail -5 gpurun_out/ab/two_launch_test.txt
 fi
+if CIS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_conv_engine_gpu.py -x -q -k weight_stationary > gpurun_out/ab/ws_test.txt 2>&1; then
+  run e1_ws CIS_PERSIST_WS=1
+else
+  echo "weight-stationary persistent kernel parity FAILED:"; tail -5 gpurun_out/ab/ws_test.txt
+fi
 run e2_sk1_16 CIS_SPLITK=1 CIS_SPLITK_MAX=16 CIS_SPLITK_NCTA=8 CIS_SPLITK_MIN_UNITS=32
-for v in e1_thin8 e1_thin64 e2_sk2_16 e2_sk2_8 e2_sk2_wide e2_sk1_16; do
+for v in e1_thin8 e1_thin64 e1_ws e2_sk2_16 e2_sk2_8 e2_sk2_wide e2_sk1_16; do
   [ -f gpurun_out/ab/$v.json ] || continue
   echo "---- $v vs base"; python tools/ab_diff.py gpurun_out/ab/base.json gpurun_out/ab/$v.json 3 | head -25
 done

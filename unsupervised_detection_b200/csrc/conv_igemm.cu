@@ -793,7 +793,10 @@ static constexpr int kPThreads = 256;
 template <int BN>
 __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __grid_constant__ CisConv p, const int halo_stage_bytes,
                                                                        const int BS, const int NHS, const int AS,
-                                                                       const __grid_constant__ HaloMaps maps) {
+                                                                       const __grid_constant__ HaloMaps maps, const int ws) {
+  // ws = 1 (weight-stationary, experimental): all nchunks*ntaps weight tiles of the layer are fetched ONCE per CTA into
+  // b_base[0 .. per_tile) (one mbarrier, BS = 1 for the barrier bookkeeping) and stay resident for every tile the CTA walks;
+  // thin many-tap layers (generator conv1 5x5x8, recover flow1) otherwise re-stream 25 mostly-zero 4 KB tiles per output tile.
   constexpr int kBStage = BN * 128;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * 3 + 2 * kHaloMaxBStages + 4];
@@ -880,6 +883,12 @@ __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __gr
       const uint8_t* wt = reinterpret_cast<const uint8_t*>(p.wpack);
       const int per_tile = nchunks * p.ntaps;
       int bc = 0;
+      if (ws) {
+        if ((int)blockIdx.x < total) {
+          mbar_expect_tx(bar_bfull, (uint32_t)(per_tile * kBStage));
+          for (int it = 0; it < per_tile; ++it) bulk_g2s(b_base + it * kBStage, wt + (size_t)it * kBStage, kBStage, bar_bfull);
+        }
+      } else
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         for (int it = 0; it < per_tile; ++it, ++bc) {
           const int bs = bc % BS;
@@ -895,6 +904,10 @@ __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __gr
     const uint32_t ahi = desc_hi((uint32_t)(Wh * 128)), bhi = desc_hi(1024);
     const uint32_t a_mstep = (uint32_t)(16 * Wh * 128) >> 4;
     int hc = 0, bc = 0, wi = 0;
+    if (ws && (int)blockIdx.x < total) {
+      mbar_wait(bar_bfull, 0u);      // the resident weight set; never released
+      tc_fence_after();
+    }
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++wi) {
       const int as = wi % AS;
       mbar_wait(bar_tempty + 8 * as, (uint32_t)(((wi / AS) & 1) ^ 1));
@@ -907,8 +920,8 @@ __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __gr
         mbar_wait(bar_hfull + 8 * hs, (uint32_t)((hc / NHS) & 1));
         const uint32_t hsrc = h_base + hs * halo_stage_bytes;
         for (int t = 0; t < p.ntaps; ++t, ++bc) {
-          const int bs = bc % BS;
-          mbar_wait(bar_bfull + 8 * bs, (uint32_t)((bc / BS) & 1));
+          const int bs = ws ? (cc * p.ntaps + t) : (bc % BS);
+          if (!ws) mbar_wait(bar_bfull + 8 * bs, (uint32_t)((bc / BS) & 1));
           tc_fence_after();
           if (elect_one()) {
             const uint32_t blo = desc_lo(b_base + bs * kBStage, 16);
@@ -918,7 +931,7 @@ __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __gr
               const uint32_t td = tacc + m * BN;
               for (int k = 0; k < nk16; ++k) umma_bf16_lh(td, alo + 2 * k, ahi, blo + 2 * k, bhi, idesc, k ? 1u : acc0);
             }
-            umma_commit(bar_bempty + 8 * bs);
+            if (!ws) umma_commit(bar_bempty + 8 * bs);
             if (t == p.ntaps - 1) umma_commit(bar_hempty + 8 * hs);
             if (cc == nchunks - 1 && t == p.ntaps - 1) umma_commit(bar_tfull + 8 * as);
           }
@@ -1315,7 +1328,33 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   // persistent variant: measured (r01) to win on single-chunk thin layers (weights re-streamed per tile are tiny) and to lose on
   // the wide ones at MT=1 (one weight stream per SM instead of 2-3 co-resident CTAs); CIS_PERSIST_MODE: 0 off, 1 thin (default), 2 all
   const int persist_mode = g_persist_mode >= 0 ? g_persist_mode : (getenv("CIS_PERSIST_MODE") ? atoi(getenv("CIS_PERSIST_MODE")) : 1);
-  const bool persist_ok = persist_mode == 2 || (persist_mode == 1 && BN <= 32 && nchunks == 1 && d->ntaps <= 9);
+  const bool persist_ok = persist_mode == 2 || ((persist_mode == 1 || persist_mode == 3) && BN <= 32 && nchunks == 1 && d->ntaps <= 9);
+  // weight-stationary persistent variant (mode 3 / CIS_PERSIST_WS=1; experimental, off by default): thin layers whose whole
+  // weight set (nchunks * ntaps tiles of BN x 128 B) fits next to two halo stages
+  static const int ws_env = getenv("CIS_PERSIST_WS") ? atoi(getenv("CIS_PERSIST_WS")) : 0;
+  static int attr_p = 0;   // largest dynamic-smem limit set so far on conv_halo_persist_kernel<BN> (shared by both variants)
+  const int per_tile = nchunks * d->ntaps;
+  const int ws_smem = 2 * halo_stage + 1024 + per_tile * BN * 128;
+  if ((persist_mode == 3 || (ws_env && g_persist_mode < 0)) && use_tma && d->n_tiles == 1 && splits == 1 && BN <= 32 && per_tile >= 2 &&
+      ws_smem <= 200 * 1024) {
+    const int AS = (2 * d->MT * BN <= 512) ? 2 : 1;
+    if (ws_smem > attr_p) {
+      cudaError_t e = cudaFuncSetAttribute(conv_halo_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem);
+      if (e != cudaSuccess) return cis_set_cuda_error(e, "cudaFuncSetAttribute(conv_halo_persist ws)");
+      attr_p = ws_smem;
+    }
+    const int want = AS * d->MT * BN;
+    const int tcols = want <= 32 ? 32 : want <= 64 ? 64 : want <= 128 ? 128 : want <= 256 ? 256 : 512;
+    int cps = (227 * 1024) / (ws_smem + 1024);
+    if (cps > 512 / tcols) cps = 512 / tcols;
+    if (cps > 4) cps = 4;
+    if (cps < 1) cps = 1;
+    int g = tiles * d->N;
+    if (g > 148 * cps) g = 148 * cps;
+    cudaError_t le = launch_pdl(conv_halo_persist_kernel<BN>, dim3(g), dim3(kPThreads), ws_smem, st, *d, halo_stage, 1, 2, AS, maps, 1);
+    if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_halo_persist ws)");
+    return cis_check_launch("conv_halo_persist ws");
+  }
   if (persist_ok && use_tma && d->n_tiles == 1 && splits == 1) {
     // persistent, warp-specialised variant: two halo stages, two accumulator stages when TMEM allows
     const int AS = (2 * d->MT * BN <= 512) ? 2 : 1;
@@ -1327,7 +1366,6 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
     if (p_bs > steps_all && steps_all >= 2) p_bs = steps_all;
     if (p_bs >= 2) {
       const int p_smem = p_fixed + p_bs * BN * 128;
-      static int attr_p = 0;
       if (p_smem > attr_p) {
         cudaError_t e = cudaFuncSetAttribute(conv_halo_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, p_smem);
         if (e != cudaSuccess) return cis_set_cuda_error(e, "cudaFuncSetAttribute(conv_halo_persist)");
@@ -1341,7 +1379,7 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
       if (cps < 1) cps = 1;
       int g = tiles * d->N;
       if (g > 148 * cps) g = 148 * cps;
-      cudaError_t le = launch_pdl(conv_halo_persist_kernel<BN>, dim3(g), dim3(kPThreads), p_smem, st, *d, halo_stage, p_bs, p_nhs, AS, maps);
+      cudaError_t le = launch_pdl(conv_halo_persist_kernel<BN>, dim3(g), dim3(kPThreads), p_smem, st, *d, halo_stage, p_bs, p_nhs, AS, maps, 0);
       if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_halo_persist)");
       return cis_check_launch("conv_halo_persist");
     }

@@ -98,7 +98,8 @@ typedef struct {
   int32_t Cout;      /* <= 128 */
   int32_t K_pad;
   int32_t splits;    /* split-K factor (grid.y) */
-  int32_t tma;       /* 1: stride-1 layer, operands fetched as 8x8-pixel TMA tiles; dwp columns are then laid out per tap in
+  int32_t tma;       /* 2: experimental halo-resident variant of 1 (same dwp layout; one activation halo per pixel tile, taps read in place);
+                        1: stride-1 layer, operands fetched as 8x8-pixel TMA tiles; dwp columns are then laid out per tap in
                         64-channel groups: col = (tap*ceil(Cin8/64) + chunk64)*64 + c, K_pad = that extent rounded to 128 */
 } CisWgrad;
 

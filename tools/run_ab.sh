@@ -1,6 +1,7 @@
 # One GPU call that measures the round-2 experiment switches of DESIGN.md section 6 against the default build:
 # per-launch CUDA-graph-replay times (tools/time_ops.py) + the whole-step bench for each configuration.
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/run_ab.sh'
+#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/run_ab.sh'      (about 10 configurations x ~90 s)
+# Experimental kernels (two-launch split-K, weight-stationary persistent conv, halo wgrad) are parity-tested first and skipped on failure.
 mkdir -p gpurun_out/ab
 run() {   # name, env assignments...
   name=$1; shift
@@ -24,8 +25,18 @@ if CIS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_conv_engine_g
 else
   echo "weight-stationary persistent kernel parity FAILED:"; tail -5 gpurun_out/ab/ws_test.txt
 fi
+# halo-resident wgrad: hardware probe first, then parity, then timing
+nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o /tmp/umma_probe_mn tools/umma_probe_mn.cu > gpurun_out/ab/probe_mn.txt 2>&1 && timeout 60 /tmp/umma_probe_mn >> gpurun_out/ab/probe_mn.txt 2>&1
+echo "umma_probe_mn: $(grep -c ' ok ' gpurun_out/ab/probe_mn.txt) ok, $(grep -c MISMATCH gpurun_out/ab/probe_mn.txt) mismatch"
+nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o /tmp/umma_probe_noswz tools/umma_probe_noswz.cu > gpurun_out/ab/probe_noswz.txt 2>&1 && timeout 60 /tmp/umma_probe_noswz >> gpurun_out/ab/probe_noswz.txt 2>&1
+echo "umma_probe_noswz: $(grep -c ': ok' gpurun_out/ab/probe_noswz.txt) ok, $(grep -c MISMATCH gpurun_out/ab/probe_noswz.txt) mismatch"
+if CIS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_conv_engine_gpu.py -x -q -k halo_wgrad > gpurun_out/ab/wgh_test.txt 2>&1; then
+  run e4_wgh CIS_WGRAD_HALO=1
+else
+  echo "halo wgrad parity FAILED:"; tail -5 gpurun_out/ab/wgh_test.txt
+fi
 run e2_sk1_16 CIS_SPLITK=1 CIS_SPLITK_MAX=16 CIS_SPLITK_NCTA=8 CIS_SPLITK_MIN_UNITS=32
-for v in e1_thin8 e1_thin64 e1_ws e2_sk2_16 e2_sk2_8 e2_sk2_wide e2_sk1_16; do
+for v in e1_thin8 e1_thin64 e1_ws e4_wgh e2_sk2_16 e2_sk2_8 e2_sk2_wide e2_sk1_16; do
   [ -f gpurun_out/ab/$v.json ] || continue
   echo "---- $v vs base"; python tools/ab_diff.py gpurun_out/ab/base.json gpurun_out/ab/$v.json 3 | head -25
 done

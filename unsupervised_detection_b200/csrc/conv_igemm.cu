@@ -1186,6 +1186,145 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
   if (warp == 4) tmem_dealloc<128>(tmem);
 }
 
+
+// ======================================================================================================= halo-resident wgrad
+// EXPERIMENTAL (CisWgrad.tma == 2; written after round 1's GPU budget was spent: compiled, never run -- DESIGN.md section 6, E4).
+// Swapped roles: D[kcol][co] = sum_pix x[pix + tap][c] * g[pix][co].  Per 8x8 pixel tile the CTA fetches ONE activation halo
+// ((8+ex) x (8+ey) pixels x 64 channels, TMA, SWIZZLE_128B) and ONE gradient tile (8x8 pixels x 64 channels) and reads every tap
+// in place: A = MN-major operand whose two 64-channel atoms are the taps 2q and 2q+1 (descriptor start = origin of tap 2q shifted
+// by two tile rows per K step, LBO = distance between the two tap origins, SBO = Wh*128 between the 8-pixel rows), B = the gradient
+// tile (N = Nh output channels), accumulator columns [q*Nh, (q+1)*Nh).  Relies on the tensor core applying the 128B swizzle on
+// absolute address bits for MN-major operands too (tools/umma_probe_mn.cu checks exactly these descriptor forms).
+// grid = (64-channel chunks of the input, pixel-tile splits, 64-channel halves of Cout); dwp layout = the tma == 1 layout.
+static constexpr int kWHMaxStages = 6;
+struct WgradHaloMaps {
+  CUtensorMap g;                 // (C8, OW, OH, N) gradient slice, box (64, 8, 8, 1)
+  CUtensorMap x[CIS_MAX_SRC];    // (C8, W, H, N) activation slices, box (64, Wh, Hh, 1)
+};
+
+__global__ void __launch_bounds__(kThreads) conv_wgrad_halo_kernel(const __grid_constant__ CisWgrad p, const __grid_constant__ WgradHaloMaps maps,
+                                                                    const int Wh, const int Hh, const int hoy, const int hox,
+                                                                    const int stage_bytes, const int S, const int Nh, const int ncols) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bars[2 * kWHMaxStages + 1];
+  __shared__ uint32_t tmem_slot;
+  __shared__ int s_off[CIS_MAX_TAPS + 1];   // tap origin inside the halo, in pixel rows of 128 B
+  const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_full = smem_u32(&bars[0]);
+  const uint32_t bar_empty = smem_u32(&bars[kWHMaxStages]);
+  const uint32_t bar_accum = smem_u32(&bars[2 * kWHMaxStages]);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
+  if (tid < p.ntaps) s_off[tid] = (p.dh[tid] - hoy) * Wh + (p.dw[tid] - hox);
+  if (tid == p.ntaps) s_off[tid] = 0;       // partner of an unpaired last tap (its accumulator rows are never stored)
+  const int halo_bytes = stage_bytes - 8192;                 // [halo (1024-rounded)] [gradient tile 8 KB]
+  const int tiles_x = (p.OW + 7) / 8, tiles_y = (p.OH + 7) / 8;
+  const int nkb_total = p.N * tiles_x * tiles_y;
+  const int per = (nkb_total + (int)gridDim.y - 1) / (int)gridDim.y;
+  const int kb0 = blockIdx.y * per;
+  const int nkb = min(per, nkb_total - kb0);
+  if (nkb <= 0) return;   // uniform per CTA: before any barrier / TMEM allocation
+  int m_chunks = 0;
+  for (int i = 0; i < p.nsrc; ++i) m_chunks += p.src[i].chunks;
+  const int nch64 = (m_chunks + 7) / 8;
+  const int c64 = blockIdx.x, half = blockIdx.z;
+  const int npair = (p.ntaps + 1) / 2;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(bar_full + 8 * s, 1);
+        mbar_init(bar_empty + 8 * s, 1);
+      }
+      mbar_init(bar_accum, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc_dyn(smem_u32(&tmem_slot), (uint32_t)ncols);
+  }
+  pdl_wait();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 4) {
+    if (tid == 0) {
+      // which concat source holds this 64-channel chunk (sources except the last are 64-channel aligned)
+      int c = c64 * 8, si = 0;
+      while (si < p.nsrc - 1 && c >= p.src[si].chunks) {
+        c -= p.src[si].chunks;
+        ++si;
+      }
+      int nm = p.src[0].n_mod;
+      if (si == 1) nm = p.src[1].n_mod;
+      if (si == 2) nm = p.src[2].n_mod;
+      if (si == 3) nm = p.src[3].n_mod;
+      const int tpi = tiles_x * tiles_y;
+      for (int it = 0; it < nkb; ++it) {
+        const int s = it % S;
+        mbar_wait(bar_empty + 8 * s, (uint32_t)(((it / S) & 1) ^ 1));
+        const int kb = kb0 + it;
+        const int n = kb / tpi, r = kb - n * tpi;
+        const int ty = r / tiles_x, tx = r - ty * tiles_x;
+        const uint32_t st = tile_base + s * stage_bytes, bar = bar_full + 8 * s;
+        mbar_expect_tx(bar, (uint32_t)(Wh * Hh * 128 + 8192));
+        tma_load_4d(st, &maps.x[si], bar, c * 8, tx * 8 + hox, ty * 8 + hoy, nm ? (n % nm) : n);     // out-of-image pixels / channels: zeros
+        tma_load_4d(st + halo_bytes, &maps.g, bar, half * 64, tx * 8, ty * 8, n);
+      }
+    }
+    __syncwarp();
+    // ---- epilogue: accumulator row r = (tap parity r / 64, input channel r % 64) of every tap pair; columns = output channels
+    mbar_wait(bar_accum, 0);
+    tc_fence_after();
+    const int r = warp * 32 + lane;
+    const int cch = r & 63;
+    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+    for (int q = 0; q < npair; ++q) {
+      const int t = 2 * q + (r >> 6);
+      const bool tv = t < p.ntaps;
+      const size_t kcol = ((size_t)t * nch64 + c64) * 64 + cch;
+#pragma unroll 1
+      for (int c0 = 0; c0 < Nh; c0 += 16) {
+        float v[16];
+        tmem_ld16(t_row + q * Nh + c0, v);     // whole-warp collective: no early exit before it
+        if (!tv) continue;
+        for (int e = 0; e < 16; ++e) {
+          const int co = half * 64 + c0 + e;
+          if (co < p.Cout) atomicAdd(p.dwp + (size_t)co * p.K_pad + kcol, v[e]);   // lanes = consecutive kcol: coalesced
+        }
+      }
+    }
+  } else {
+    const uint32_t idesc = make_idesc_bf16(128, Nh, 1, 1);
+    const uint32_t ahi = desc_hi((uint32_t)(Wh * 128)), bhi = desc_hi(1024);
+    for (int it = 0; it < nkb; ++it) {
+      const int s = it % S;
+      mbar_wait(bar_full + 8 * s, (uint32_t)((it / S) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t st = tile_base + s * stage_bytes;
+        const uint32_t blo0 = desc_lo(st + halo_bytes, 8192);
+        for (int q = 0; q < npair; ++q) {
+          const int o0 = s_off[2 * q], o1 = s_off[2 * q + 1];
+          const uint32_t lbo = (uint32_t)((o1 > o0 ? o1 - o0 : 1) * 128);      // distance between the two tap origins
+          const uint32_t alo0 = desc_lo(st + (uint32_t)(o0 * 128), lbo);
+          const uint32_t kstep = (uint32_t)(2 * Wh * 128) >> 4;                // 16 pixels = two tile rows of the halo
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16_lh(tmem + q * Nh, alo0 + k * kstep, ahi, blo0 + 128 * k, bhi, idesc, (uint32_t)((it | k) != 0));
+        }
+        umma_commit(bar_empty + 8 * s);
+        if (it == nkb - 1) umma_commit(bar_accum);
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc_dyn(tmem, (uint32_t)ncols);
+}
+
 }  // namespace cis
 
 using namespace cis;
@@ -1428,10 +1567,64 @@ extern "C" int cis_conv_igemm(const CisConv* d, cis_stream_t stream) {
   }
 }
 
+// Halo-resident swapped wgrad (CisWgrad.tma == 2, experimental).  Eligibility is re-checked here; the engine falls back to tma = 1.
+static int launch_wgrad_halo(const CisWgrad* d, cudaStream_t st) {
+  if (d->sh != 1 || d->sw != 1) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_wgrad(halo): needs a stride-1 layer");
+  int chunks = 0;
+  for (int i = 0; i < d->nsrc; ++i) chunks += d->src[i].chunks;
+  for (int i = 0; i < d->nsrc - 1; ++i)
+    if (d->src[i].chunks % 8) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_wgrad(halo): needs 64-channel aligned concat sources");
+  const int nch64 = (chunks + 7) / 8;
+  int hoy = d->dh[0], hox = d->dw[0], my = d->dh[0], mx = d->dw[0];
+  for (int t = 1; t < d->ntaps; ++t) {
+    if (d->dh[t] < hoy) hoy = d->dh[t];
+    if (d->dw[t] < hox) hox = d->dw[t];
+    if (d->dh[t] > my) my = d->dh[t];
+    if (d->dw[t] > mx) mx = d->dw[t];
+  }
+  for (int t = 1; t < d->ntaps; ++t)    // pairs (2q, 2q+1) need increasing origins: taps are listed row-major
+    if ((d->dh[t] - hoy) * 1024 + (d->dw[t] - hox) <= (d->dh[t - 1] - hoy) * 1024 + (d->dw[t - 1] - hox))
+      return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_wgrad(halo): taps must be listed in increasing row-major order");
+  const int Wh = 8 + (mx - hox), Hh = 8 + (my - hoy);
+  if (Wh > 256 || Hh > 256) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_conv_wgrad(halo): tap extent too large");
+  const int halo_bytes = (Wh * Hh * 128 + 1023) & ~1023;
+  const int stage = halo_bytes + 8192;
+  const int nhalf = d->Cout > 64 ? 2 : 1;
+  int Nh = d->Cout > 64 ? 64 : ((d->Cout + 15) & ~15);
+  const int npair = (d->ntaps + 1) / 2;
+  const int want = npair * Nh;
+  if (want > 512) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_conv_wgrad(halo): accumulators exceed TMEM");
+  const int ncols = want <= 32 ? 32 : want <= 64 ? 64 : want <= 128 ? 128 : want <= 256 ? 256 : 512;
+  int S = (200 * 1024) / stage;
+  if (S > kWHMaxStages) S = kWHMaxStages;
+  if (S > 4 && ncols <= 256) S = 4;       // leave room for a second co-resident CTA when TMEM allows one
+  if (S < 2) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_conv_wgrad(halo): halo does not fit shared memory");
+  const int smem = S * stage + 1024;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return cis_set_cuda_error(e, "cudaFuncSetAttribute(conv_wgrad_halo)");
+    attr_smem = smem;
+  }
+  if (d->K_pad < d->ntaps * nch64 * 64) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_wgrad(halo): K_pad smaller than taps * 64-channel groups");
+  WgradHaloMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  CisSrc gs;
+  gs.ptr = d->g; gs.pitch = d->g_pitch; gs.c_off = d->g_coff; gs.chunks = d->g_chunks; gs.n_mod = 0;
+  bool ok = encode_src_map(&maps.g, gs, d->N, d->OH, d->OW, 8, 8);
+  for (int i = 0; ok && i < d->nsrc; ++i) ok = encode_src_map(&maps.x[i], d->src[i], d->N, d->H, d->W, Wh, Hh);
+  if (!ok) return cis_set_error(CIS_ERR_CUDA, "cis_conv_wgrad(halo): cuTensorMapEncodeTiled failed / unavailable");
+  dim3 grid(nch64, d->splits, nhalf);
+  cudaError_t le = launch_pdl(conv_wgrad_halo_kernel, grid, dim3(kThreads), (size_t)smem, st, *d, maps, Wh, Hh, hoy, hox, stage, S, Nh, ncols);
+  if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_wgrad_halo)");
+  return cis_check_launch("conv_wgrad_halo");
+}
+
 extern "C" int cis_conv_wgrad(const CisWgrad* d, cis_stream_t stream) {
   if (!d || d->ntaps < 1 || d->ntaps > CIS_MAX_TAPS || d->nsrc < 1 || d->nsrc > CIS_MAX_SRC || d->K_pad % 64 != 0 || d->Cout < 1 ||
       d->Cout > 128 || d->splits < 1 || !d->g || !d->dwp)
     return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_wgrad: bad descriptor");
+  if (d->tma == 2) return launch_wgrad_halo(d, (cudaStream_t)stream);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem);

@@ -207,6 +207,26 @@ WGRAD_TMA = True
 MATERIALIZE_MISALIGNED_CONCAT = True
 
 
+WGRAD_HALO = os.environ.get('CIS_WGRAD_HALO', '0') == '1'   # experimental halo-resident swapped wgrad kernel (CisWgrad.tma = 2), off
+
+
+def wgrad_halo_fits(taps, cout, stride):
+    """Eligibility of the halo-resident wgrad kernel (mirrors launch_wgrad_halo in csrc/conv_igemm.cu): stride 1, taps listed in
+    increasing row-major order, (taps/2) x min(Cout16, 64) accumulator columns within TMEM, >= 2 pipeline stages in shared memory."""
+    if stride != 1 or not taps:
+        return False
+    hoy, hox = min(a for a, _ in taps), min(b for _, b in taps)
+    keys = [(a - hoy) * 1024 + (b - hox) for a, b in taps]
+    if any(k1 <= k0 for k0, k1 in zip(keys, keys[1:])):
+        return False
+    wh, hh = 8 + max(b for _, b in taps) - hox, 8 + max(a for a, _ in taps) - hoy
+    nh = 64 if cout > 64 else ru(cout, 16)
+    if ((len(taps) + 1) // 2) * nh > 512 or wh > 256 or hh > 256:
+        return False
+    stage = ru(wh * hh * 128, 1024) + 8192
+    return (200 * 1024) // stage >= 2
+
+
 def _pow2_cols(c):
     for v in (32, 64, 128, 256, 512):
         if c <= v:
@@ -656,7 +676,9 @@ class Builder(object):
                 # TMA operand path (8x8 pixel tiles) for stride-1 layers whose concat sources are 64-channel aligned
                 layer.wg_tma = bool(WGRAD_TMA and layer.stride == 1 and len(layer.in_chanmap) >= 32 and
                                     all(s_.C8 % 64 == 0 for s_ in srcs[:-1]))   # thin inputs: per-tap 64-channel padding would waste the loads
-                if layer.wg_tma:
+                layer.wg_halo = bool(WGRAD_HALO and wgrad_halo_fits(taps, layer.cout, layer.stride) and
+                                     all(s_.C8 % 64 == 0 for s_ in srcs[:-1]))
+                if layer.wg_tma or layer.wg_halo:
                     cin8 = len(layer.in_chanmap)
                     nch64 = -(-cin8 // 64)
                     ncol = layer.k * layer.k * nch64 * 64
@@ -676,9 +698,11 @@ class Builder(object):
             _fill_srcs(w, srcs)
             w.g, w.g_pitch, w.g_coff, w.g_chunks = G.ptr, G.pitch, G.c_off, G.C8 // 8
             w.dwp, w.Cout, w.K_pad = layer.dwp.data_ptr(), layer.cout, layer.wg_K_pad
-            w.tma = 1 if layer.wg_tma else 0
-            nkb = (nb * (-(-out.H // 8)) * (-(-out.W // 8))) if layer.wg_tma else -(-npix // 64)
+            w.tma = 2 if layer.wg_halo else (1 if layer.wg_tma else 0)
+            nkb = (nb * (-(-out.H // 8)) * (-(-out.W // 8))) if w.tma else -(-npix // 64)
             ntile = -(-layer.wg_K_pad // 128)
+            if w.tma == 2:      # grid.x = 64-channel chunks of the input, grid.z = 64-channel halves of Cout
+                ntile = (-(-len(layer.in_chanmap) // 64)) * (2 if layer.cout > 64 else 1)
             w.splits = max(1, min(nkb // 8 if nkb >= 8 else 1, max(1, (4 * NUM_SMS) // ntile)))
             bp.keep.append(w)
             bp.add('cis_conv_wgrad', C.byref(w), flops=2.0 * npix * layer.k * layer.k * layer.cin * layer.cout, lane=1)

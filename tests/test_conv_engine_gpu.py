@@ -153,3 +153,28 @@ def test_conv_engine_halo_wgrad(case):
     assert r['db_err'] <= 2 ** -7 * r['db_ref'] + 1e-3, r
     if 'dgamma_err' in r:
         assert r['dgamma_err'] <= 2 ** -6 * r['dgamma_ref'] + 1e-2, r
+
+
+CL_CASES = [CASES[0], CASES[1], CASES[6], CASES[12], CASES[13], CASES[14],
+            dict(N=4, H=48, W=80, cins=[128, 128, 64], cout=128, k=3, act=ACT_LEAKY, alpha=0.1, backward=False),
+            dict(N=2, H=32, W=64, cins=[256], cout=96, k=3, act=ACT_LEAKY, backward=False)]
+
+
+@pytest.mark.skipif(os.environ.get('CIS_TEST_EXPERIMENTAL') != '1',
+                    reason='2-CTA cluster weight multicast was written after the GPU budget of round 1 was spent: compiled but never run; '
+                           'set CIS_TEST_EXPERIMENTAL=1 (and run it under a short timeout) before enabling CIS_HALO_CLUSTER=2')
+@pytest.mark.parametrize('case', CL_CASES, ids=lambda c: 'k%d_c%s_o%d_%dx%d' % (c['k'], '+'.join(map(str, c['cins'])), c['cout'], c['H'], c['W']))
+def test_conv_engine_cluster_weight_multicast(case):
+    """CIS_HALO_CLUSTER=2: pairs of CTAs share every weight tile through multicast bulk copies; results are bit-identical to the
+    default launch (same MMAs, same order)."""
+    r0 = run_conv_case(**case)
+    os.environ['CIS_HALO_CLUSTER'] = '2'
+    try:
+        r = run_conv_case(**case)
+    finally:
+        del os.environ['CIS_HALO_CLUSTER']
+    tol = lambda ref: 2 ** -7 * ref + 1e-3
+    assert r['fwd_err'] <= tol(r['fwd_ref']), r
+    assert r['fwd_err'] == r0['fwd_err']
+    if 'dx_err' in r:
+        assert r['dx_err'] <= tol(r['dx_ref']), r

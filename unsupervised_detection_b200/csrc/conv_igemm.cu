@@ -486,7 +486,11 @@ struct HaloMaps {
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_constant__ CisConv p, const int halo_stage_bytes, const int BS, const int NHS,
-                                                        const __grid_constant__ HaloMaps maps, const int use_tma) {
+                                                        const __grid_constant__ HaloMaps maps, const int use_tma, const int cl) {
+  // cl = 2 (experimental, launched as 2-CTA clusters along blockIdx.x): the two CTAs work on neighbouring pixel tiles of the same
+  // n-tile, so they consume the same sequence of weight tiles; each fetches HALF of every tile and multicasts it to both, and a
+  // stage is refilled only after BOTH have committed their MMAs on it (bempty counts cl arrivals).  Halves the L2->SM weight
+  // stream that bounds the MT = 1 wide layers.  cl = 1: unchanged behaviour.
   constexpr int kBStage = BN * 128;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * 2 + 2 * kHaloMaxBStages + 1];
@@ -553,7 +557,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
       }
       for (int s = 0; s < BS; ++s) {
         mbar_init(bar_bfull + 8 * s, 1);   // one expect_tx arrival; the bulk copy completes the transaction bytes
-        mbar_init(bar_bempty + 8 * s, 1);
+        mbar_init(bar_bempty + 8 * s, cl); // one commit per CTA that reads the stage
       }
       mbar_init(bar_accum, 1);
       fence_mbar_init();
@@ -565,6 +569,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   if (tid < BN) s_bias[tid] = p.bias ? p.bias[ny * BN + tid] : 0.f;
   tc_fence_before();
   __syncthreads();
+  if (cl > 1) cluster_sync_all();   // the peer's barriers must be initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
@@ -634,7 +639,12 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
           const int bs = it % BS;
           mbar_wait(bar_bempty + 8 * bs, (uint32_t)(((it / BS) & 1) ^ 1));
           mbar_expect_tx(bar_bfull + 8 * bs, kBStage);
-          bulk_g2s(b_base + bs * kBStage, wt + (size_t)it * kBStage, kBStage, bar_bfull + 8 * bs);
+          if (cl > 1) {
+            const uint32_t hb = kBStage / 2, ho = cluster_ctarank() * hb;
+            bulk_g2s_mc(b_base + bs * kBStage + ho, wt + (size_t)it * kBStage + ho, hb, bar_bfull + 8 * bs, (uint16_t)3);
+          } else {
+            bulk_g2s(b_base + bs * kBStage, wt + (size_t)it * kBStage, kBStage, bar_bfull + 8 * bs);
+          }
         }
       }
     }
@@ -712,7 +722,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
               for (int k = 0; k < nk16; ++k) umma_bf16_lh(td, alo + 2 * k, ahi, blo + 2 * k, bhi, idesc, k ? 1u : acc0);
             }
           }
-          umma_commit(bar_bempty + 8 * bs);
+          if (cl > 1) umma_commit_mc(bar_bempty + 8 * bs, (uint16_t)3); else umma_commit(bar_bempty + 8 * bs);
           if (t == p.ntaps - 1) umma_commit(bar_hempty + 8 * hs);
           if (cc == nchunks - 1 && t == p.ntaps - 1) umma_commit(bar_accum);
         }
@@ -722,6 +732,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (cl > 1) cluster_sync_all();   // the peer may still be arriving on this CTA's bempty barriers
   if (warp == 4) tmem_dealloc_dyn(tmem, ncols);
 }
 
@@ -1351,6 +1362,27 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// Same as launch_pdl plus a thread-block-cluster dimension along x.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int BN>
 static cudaError_t launch_splitk_finish(const CisConv* d, dim3 main_grid, cudaStream_t st) {
   constexpr int G = BN / 16;
@@ -1523,7 +1555,15 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
       return cis_check_launch("conv_halo_persist");
     }
   }
-  cudaError_t le = launch_pdl(conv_halo_kernel<BN>, grid, dim3(kThreads), smem, st, *d, halo_stage, BS, nhs, maps, use_tma);
+  // experimental 2-CTA clusters sharing the weight stream (CIS_HALO_CLUSTER=2): wide n-tiles, an even number of pixel tiles
+  const char* cl_s = getenv("CIS_HALO_CLUSTER");   // read per launch (cheap) so tests can toggle it through os.environ
+  const int cl_env = cl_s ? atoi(cl_s) : 0;
+  cudaError_t le;
+  if (cl_env == 2 && BN >= 64 && grid.x % 2 == 0 && BS >= 2) {
+    le = launch_pdl_cluster(conv_halo_kernel<BN>, grid, dim3(kThreads), smem, st, 2, *d, halo_stage, BS, nhs, maps, use_tma, 2);
+  } else {
+    le = launch_pdl(conv_halo_kernel<BN>, grid, dim3(kThreads), smem, st, *d, halo_stage, BS, nhs, maps, use_tma, 1);
+  }
   if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_halo)");
   if (splits > 1 && !d->sk_counters) {
     le = launch_splitk_finish<BN>(d, grid, st);

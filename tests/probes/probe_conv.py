@@ -1,6 +1,6 @@
 """Scratch probe (GPU): prints the conv-engine errors per case to gpurun_out/probe_conv.txt."""
 import sys, os, json, traceback
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch
 from test_conv_engine_gpu import CASES
 from convref import run_conv_case

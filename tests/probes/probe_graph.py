@@ -2,7 +2,7 @@
 import os, sys, json, time, traceback
 import torch
 import torch.nn.functional as F
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))   # repo root
 from oracle import params as OP, losses as OL, nets as ON, pwcnet as OW
 from unsupervised_detection_b200.step_graph import CISGraph
 

@@ -118,7 +118,10 @@ class AdversarialLearner(object):
         prefix = ckpt_io.normalize_prefix(path)
         want = set(wanted)
         tfn = set(ckpt_io.to_tf_name(k, sep) for k in want for sep in ('//', '/')) | {'train_op/global_step', 'global_step'}
-        got, gs = ckpt_io.import_params(ckpt_io.read_bundle(prefix, names=lambda n: n in tfn), wanted, strict=strict)
+        # CIS_CKPT_NOVERIFY=1 skips the CRC-32C checks (block trailers, tensor payloads) -- an escape hatch for the first real
+        # TF-written file, against which the reader's checksum handling has not been pinned yet
+        verify = os.environ.get('CIS_CKPT_NOVERIFY') != '1'
+        got, gs = ckpt_io.import_params(ckpt_io.read_bundle(prefix, names=lambda n: n in tfn, verify=verify), wanted, strict=strict)
         return {k: torch.from_numpy(np.array(v, dtype=np.float32)) for k, v in got.items()}, gs
 
     def _names(self, *scopes):

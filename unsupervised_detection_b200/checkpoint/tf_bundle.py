@@ -15,8 +15,8 @@ the published on-disk format:
   * the data shard is the raw little-endian tensor bytes at [offset, offset+size).
 
 PARITY UNPINNED: no TF-written checkpoint exists in this environment (no TensorFlow, no network, the authors' files are a
-separate download), so the byte-level format is checked only against this module's own writer, the CRC-32C known-answer vectors
-and a hand-assembled table (tests/test_tf_bundle.py).  The first real `model.best` / `pwcnet.ckpt-595000` that is loaded should be
+separate download), so the byte-level format is checked only against this module's own writer, the CRC-32C known-answer vectors,
+TensorBoard's independent masked-CRC implementation (tests/test_summary_tensorboard.py) and a hand-assembled table (tests/test_tf_bundle.py).  The first real `model.best` / `pwcnet.ckpt-595000` that is loaded should be
 treated as the pinning test.
 """
 import ctypes as C

@@ -15,8 +15,10 @@ third-party dependency that is not available here; this restates its published f
   * histograms use tensorflow/core/lib/histogram/histogram.cc's default bucket limits (+-1e-12 * 1.1^k up to 1e20, DBL_MAX ends)
     with runs of empty buckets collapsed.
 
-PARITY UNPINNED against TensorBoard itself (not installed); tests read the files back with the reader below and check the
-CRC framing, the proto fields and the bucket rule.
+Pinned against TensorBoard's own implementation of the format: tests/test_summary_tensorboard.py reads these files back with
+`tensorboard.backend.event_processing` (TensorBoard 2.x is in the image; its TensorFlow stub re-implements the TFRecord framing and
+masked CRC-32C) and parses the payloads with TensorBoard's proto classes.  TensorFlow's own bucket table / image normalisation is not
+available offline; those two rules are restated from histogram.cc / summary_image_op.cc and checked structurally.
 """
 import os
 import socket

@@ -21,12 +21,12 @@ def ref_act(y, act, alpha):
 
 
 def run_conv_case(N, H, W, cins, cout, k, stride=1, dil=1, act=ACT_NONE, alpha=0.2, bn=False, seed=0, post_add=False, backward=True,
-                  n_mod_last=0, dev='cuda'):
+                  n_mod_last=0, dev='cuda', bn_cap=None):
     """Returns dict of max-abs errors (and reference scales) for forward / dgrad / wgrad / bias grad."""
     g = torch.Generator(device='cpu').manual_seed(seed)
     store = E.ParamStore(dev)
     cin = sum(cins)
-    layer = E.ConvLayer(store, 'L', k, cin, cout, stride, dil, act, alpha, tag='R', bn=bn)
+    layer = E.ConvLayer(store, 'L', k, cin, cout, stride, dil, act, alpha, tag='R', bn=bn, bn_cap=bn_cap)
     store.finalize(True)
     w = bf(torch.randn(k, k, cin, cout, generator=g) * (1.0 / (k * k * cin) ** 0.5))
     b = torch.randn(cout, generator=g) * 0.1

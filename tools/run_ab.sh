@@ -40,8 +40,15 @@ if CIS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_conv_engine_g
 else
   echo "cluster weight multicast parity FAILED:"; tail -5 gpurun_out/ab/cl_test.txt
 fi
+if CIS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_conv_engine_gpu.py -x -q -k narrow_n_tiles > gpurun_out/ab/narrow_test.txt 2>&1; then
+  run e2_bn32 CIS_SMALL_BN=32:5
+  run e2_bn32_l4 CIS_SMALL_BN=32:4
+  run e2_bn64_l4 CIS_SMALL_BN=64:4
+else
+  echo "narrow n-tile parity FAILED:"; tail -5 gpurun_out/ab/narrow_test.txt
+fi
 run e2_sk1_16 CIS_SPLITK=1 CIS_SPLITK_MAX=16 CIS_SPLITK_NCTA=8 CIS_SPLITK_MIN_UNITS=32
-for v in e1_thin8 e1_thin64 e1_ws e3_cluster e4_wgh e2_sk2_16 e2_sk2_8 e2_sk2_wide e2_sk1_16; do
+for v in e1_thin8 e1_thin64 e1_ws e3_cluster e4_wgh e2_bn32 e2_bn32_l4 e2_bn64_l4 e2_sk2_16 e2_sk2_8 e2_sk2_wide e2_sk1_16; do
   [ -f gpurun_out/ab/$v.json ] || continue
   echo "---- $v vs base"; python tools/ab_diff.py gpurun_out/ab/base.json gpurun_out/ab/$v.json 3 | head -25
 done

@@ -190,14 +190,28 @@ def _fill_srcs(d, srcs):
         d.src[i] = s.src()
 
 
-def pick_bn(cout):
+def pick_bn(cout, cap=None):
+    """(BN, n_tiles) of the GEMM N dimension.  `cap` (32 / 64) forces narrower n-tiles: more, smaller CTAs for layers whose pixel
+    count yields only a handful of 128-row tiles (experiment CIS_SMALL_BN)."""
     if cout <= 16:
         return 16, 1
     if cout <= 32:
         return 32, 1
+    if cap in (32, 64) and cout > cap:
+        return cap, -(-cout // cap)
     if cout <= 64:
         return 64, 1
     return 128, -(-cout // 128)
+
+
+def small_bn_cap(level):
+    """CIS_SMALL_BN="cap:level" (default unset = off): PWC-Net layers of pyramid level >= `level` (12x20 and coarser for level 5)
+    use n-tiles of `cap` columns.  Returns the cap for this level or None."""
+    spec = os.environ.get('CIS_SMALL_BN', '')
+    if not spec:
+        return None
+    cap, _, lvl = spec.partition(':')
+    return int(cap) if level >= int(lvl or 5) else None
 
 
 
@@ -392,11 +406,12 @@ class ConvLayer(object):
     the fp32 packed weight-gradient buffer and the channel maps that tie packed K positions to HWIO indices."""
 
     def __init__(self, store, name, k, cin, cout, stride=1, dil=1, act=ACT_NONE, alpha=0.2, tag='', bn=False,
-                 wname='kernel', bname='bias', transposed=False):
+                 wname='kernel', bname='bias', transposed=False, bn_cap=None):
         self.store, self.name, self.k, self.cin, self.cout = store, name, k, cin, cout
         self.stride, self.dil, self.act, self.alpha, self.tag, self.bn = stride, dil, act, alpha, tag, bn
         self.transposed = transposed
-        self.BN, self.n_tiles = pick_bn(cout)
+        self.bn_cap = bn_cap
+        self.BN, self.n_tiles = pick_bn(cout, bn_cap)
         self.npad = self.BN * self.n_tiles
         self.wkey, self.bkey = '%s/%s' % (name, wname), '%s/%s' % (name, bname)
         if transposed:
@@ -519,7 +534,7 @@ class ConvLayer(object):
         k, s, d = self.k, self.stride, self.dil
         g_chan = list(range(self.cout)) + [-1] * (ru(self.cout, 8) - self.cout)
         cin8 = len(self.in_chanmap)
-        bn_, nt = pick_bn(cin8)
+        bn_, nt = pick_bn(cin8, self.bn_cap)
         rows = bn_ * nt
         nmap = torch.tensor(list(self.in_chanmap) + [-1] * (rows - cin8), dtype=torch.int32, device=self.device)
         packs = []

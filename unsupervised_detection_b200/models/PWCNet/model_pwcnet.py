@@ -12,7 +12,7 @@ channels, and the 4x4 stride-2 transposed convs of the level above write up_flow
 import torch
 
 from ... import _lib
-from ...engine import ConvLayer, Act, ACT_NONE, ACT_LEAKY
+from ...engine import ConvLayer, Act, ACT_NONE, ACT_LEAKY, small_bn_cap
 
 NUM_CHANN = [None, 16, 32, 64, 96, 128, 196]       # model_pwcnet.py:151
 PYR_LVLS, FLOW_PRED_LVL, SEARCH_RANGE = 6, 2, 4    # _DEFAULT_PWCNET_TEST_OPTIONS :8-19
@@ -28,24 +28,25 @@ class ModelPWCNet(object):
     def __init__(self, store, name='pwcnet'):
         self.name = name
         self.L = {}
-        mk = lambda n, k, ci, co, s=1, d=1, act=ACT_LEAKY, tr=False: self.L.__setitem__(
-            n, ConvLayer(store, '%s/%s' % (name, n), k, ci, co, s, d, act, 0.1, tag='', transposed=tr))
+        # lvl: pyramid level of the layer's OUTPUT map (selects the experimental narrow n-tiles on the coarse levels, engine.small_bn_cap)
+        mk = lambda n, k, ci, co, s=1, d=1, act=ACT_LEAKY, tr=False, lvl=0: self.L.__setitem__(
+            n, ConvLayer(store, '%s/%s' % (name, n), k, ci, co, s, d, act, 0.1, tag='', transposed=tr, bn_cap=small_bn_cap(lvl)))
         cin = 3
         for l in range(1, PYR_LVLS + 1):
             f = NUM_CHANN[l]
-            mk('featpyr/conv%da' % l, 3, cin, f, 2)
-            mk('featpyr/conv%daa' % l, 3, f, f)
-            mk('featpyr/conv%db' % l, 3, f, f)
+            mk('featpyr/conv%da' % l, 3, cin, f, 2, lvl=l)
+            mk('featpyr/conv%daa' % l, 3, f, f, lvl=l)
+            mk('featpyr/conv%db' % l, 3, f, f, lvl=l)
             cin = f
         for l in range(PYR_LVLS, FLOW_PRED_LVL - 1, -1):
             c = 81 if l == PYR_LVLS else 81 + NUM_CHANN[l] + 4
             for i, co in enumerate(DENSE):
-                mk('predict_flow/conv%d_%d' % (l, i), 3, c, co)
+                mk('predict_flow/conv%d_%d' % (l, i), 3, c, co, lvl=l)
                 c += co
             mk('predict_flow/flow%d' % l, 3, c, 2, act=ACT_NONE)
             cc = c
             for i, (co, d) in enumerate(CTX, start=1):
-                mk('ctxt/dc_conv%d%d' % (l, i), 3, cc, co, 1, d, ACT_NONE if i == 7 else ACT_LEAKY)
+                mk('ctxt/dc_conv%d%d' % (l, i), 3, cc, co, 1, d, ACT_NONE if i == 7 else ACT_LEAKY, lvl=l)
                 cc = co
             if l != FLOW_PRED_LVL:
                 mk('upsample/up_flow%d' % l, 4, 2, 2, act=ACT_NONE, tr=True)

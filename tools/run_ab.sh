@@ -1,6 +1,6 @@
 # One GPU call that measures the round-2 experiment switches of DESIGN.md section 6 against the default build:
 # per-launch CUDA-graph-replay times (tools/time_ops.py) + the whole-step bench for each configuration.
-#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/run_ab.sh'      (about 10 configurations x ~90 s)
+#   /usr/local/graft/bin/gpurun --timeout 2700 -- 'bash tools/run_ab.sh'      (about 14 configurations x ~100 s + the gated parity tests)
 # Experimental kernels (two-launch split-K, weight-stationary persistent conv, halo wgrad) are parity-tested first and skipped on failure.
 mkdir -p gpurun_out/ab
 run() {   # name, env assignments...

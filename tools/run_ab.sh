@@ -14,9 +14,9 @@ run e1_thin8 CIS_HALO_SKIP_THIN=8
 run e1_thin64 CIS_HALO_SKIP_THIN=64
 # two-launch split-K is experimental: validate it first, skip its timing runs if the parity test fails
 if CIS_TEST_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_conv_engine_gpu.py -x -q -k two_launch > gpurun_out/ab/two_launch_test.txt 2>&1; then
-  run e2_sk2_16 CIS_SPLITK=2 CIS_SPLITK_MAX=16 CIS_SPLITK_NCTA=8 CIS_SPLITK_MIN_UNITS=32
-  run e2_sk2_8 CIS_SPLITK=2 CIS_SPLITK_MAX=8 CIS_SPLITK_NCTA=16 CIS_SPLITK_MIN_UNITS=16
-  run e2_sk2_wide CIS_SPLITK=2 CIS_SPLITK_MAX=16 CIS_SPLITK_NCTA=32 CIS_SPLITK_MIN_UNITS=8
+  run e2_sk2_16 CIS_SPLITK=2 CIS_SPLITK_MAX=16 CIS_SPLITK_NCTA=8 CIS_SPLITK_MIN_UNITS=32      # only the 6x10 / 4x7 maps (python tools/plan_report.py previews the selection)
+  run e2_sk2_8 CIS_SPLITK=2 CIS_SPLITK_MAX=16 CIS_SPLITK_NCTA=32 CIS_SPLITK_MIN_UNITS=32       # + 12x20 and 24x40 halo layers
+  run e2_sk2_wide CIS_SPLITK=2 CIS_SPLITK_MAX=8 CIS_SPLITK_NCTA=96 CIS_SPLITK_MIN_UNITS=45     # + the long 48x80 / 32x56 layers
 else
   echo "two-launch split-K parity FAILED:"; tail -5 gpurun_out/ab/two_launch_test.txt
 fi

@@ -254,7 +254,7 @@ def _pow2_cols(c):
 SPLITK = int(os.environ.get('CIS_SPLITK', '0'))
 SPLITK_MAX = int(os.environ.get('CIS_SPLITK_MAX', '4'))
 SPLITK_NCTA = int(os.environ.get('CIS_SPLITK_NCTA', '64'))          # only launches with at most this many CTAs are split
-SPLITK_MIN_UNITS = int(os.environ.get('CIS_SPLITK_MIN_UNITS', '0'))  # ... and at least this many K units (64-wide blocks / chunks)
+SPLITK_MIN_UNITS = int(os.environ.get('CIS_SPLITK_MIN_UNITS', '0'))  # ... and at least this many serial pipeline steps per CTA
 # experiment switch (default off = current behaviour): stride-1 layers whose padded input width is <= this many channels and that
 # have >= 16 taps (generator conv1 5x5x8, recover flow1 5x5) use the K-dense gather kernel (ceil(taps*cin8/64) pipeline steps)
 # instead of the halo kernel (one step and one mostly-zero BN x 128 B weight tile per tap); see DESIGN.md section 6, E1
@@ -273,7 +273,8 @@ def setup_splitk(d, device, keep):
         ncta, units, min_units, mt = tiles * d.n_tiles, -(-m_chunks // 8), 1, d.MT
     else:
         ncta, units, min_units, mt = (-(-(d.N * d.OH * d.OW) // 128)) * d.n_tiles, d.K_pad // 64, 4, 1
-    if ncta > SPLITK_NCTA or units < SPLITK_MIN_UNITS:
+    steps = units * (d.ntaps if d.halo else 1)     # serial pipeline steps of one CTA (halo: one per (chunk, tap); generic: one per 64-wide K block)
+    if ncta > SPLITK_NCTA or steps < SPLITK_MIN_UNITS:
         return
     splits = min(units // min_units, -(-2 * NUM_SMS // ncta), SPLITK_MAX)
     if splits < 2:

@@ -1,0 +1,98 @@
+"""The launch planner on CPU: the whole step graph (PWC-Net + generator + 3x recover + both backward plans) is BUILT on CPU tensors --
+nothing is launched -- and every conv / wgrad descriptor is checked against the rules the C-side launchers enforce
+(csrc/conv_igemm.cu: cis_conv_igemm, launch_halo, launch_fwd, cis_conv_wgrad), plus the bookkeeping the bench line relies on."""
+import collections
+
+import pytest
+
+from unsupervised_detection_b200 import engine
+from unsupervised_detection_b200.step_graph import CISGraph
+
+
+@pytest.fixture(scope='module')
+def graph():
+    return CISGraph(64, 96, 1, device='cpu', global_batch=2)
+
+
+def _convs(plan):
+    return [a[0]._obj for fn, a, name, fl, lane in plan.ops if name == 'cis_conv_igemm']
+
+
+def _check_conv(d):
+    assert 1 <= d.ntaps <= 49 and 1 <= d.nsrc <= 4 and d.K_pad > 0 and d.K_pad % 64 == 0 and d.n_tiles >= 1 and d.wpack
+    assert d.BN in (16, 32, 64, 128)
+    chunks = 0
+    for i in range(d.nsrc):
+        s = d.src[i]
+        assert s.ptr and (s.pitch | s.c_off) % 8 == 0 and s.chunks >= 1
+        chunks += s.chunks
+    assert d.ntaps * chunks * 8 <= d.K_pad or d.halo          # generic packing: taps x channels fit the padded K
+    assert d.out or d.outf
+    if d.out:
+        assert d.out_pitch > 0 and d.out_ch >= 1     # unaligned channel offsets are legal (scalar store path), e.g. PWC up_flow slices
+    if d.halo:
+        assert d.sh == 1 and d.sw == 1 and 1 <= d.MT <= 4 and d.MT * d.BN <= 512 and d.dil >= 1
+        hp = (8 + d.ex) * (16 * d.MT + d.ey)
+        assert 2 * ((hp * 128 + 1023) // 1024 * 1024) + hp * 4 + 1024 + d.BN * 128 <= 227 * 1024      # at least one weight stage fits
+        hp0, wp0 = -(-d.OH // d.dil), -(-d.OW // d.dil)
+        util = hp0 * wp0 / float((-(-hp0 // (16 * d.MT))) * 16 * d.MT * (-(-wp0 // 8)) * 8)
+        assert util >= 0.5
+        for t in range(d.ntaps):
+            assert 0 <= d.dh[t] <= d.ey and 0 <= d.dw[t] <= d.ex                                   # taps are halo-relative
+    assert d.splits in (0, 1)                                                                      # split-K is off by default
+
+
+def test_every_conv_descriptor_is_launchable(graph):
+    n = 0
+    for plan in (graph.fwd, graph.bwd['G'], graph.bwd['R']):
+        for d in _convs(plan):
+            _check_conv(d)
+            n += 1
+    assert n > 250
+    for plan in (graph.bwd['G'], graph.bwd['R']):
+        for fn, a, name, fl, lane in plan.ops:
+            if name != 'cis_conv_wgrad':
+                continue
+            w = a[0]._obj
+            assert w.Cout <= 128 and w.K_pad % 64 == 0 and w.splits >= 1 and w.g and w.dwp and w.tma in (0, 1)
+            assert lane == 1                                                                       # weight gradients run on the side lane
+            if w.tma:
+                assert w.sh == 1 and all(w.src[i].chunks % 8 == 0 for i in range(w.nsrc - 1))
+
+
+def test_plan_bookkeeping(graph):
+    g = graph
+    assert g.param_count() == 18918722                      # "Number of params" the reference prints (adversarial_learner.py:338)
+    # the generator step back-propagates through the recover net's data path but only accumulates generator weight gradients
+    wg = {m: sum(1 for op in g.bwd[m].ops if op[2] == 'cis_conv_wgrad') for m in 'GR'}
+    assert wg['G'] == 17 and wg['R'] == 32
+    kinds = collections.Counter(op[2] for op in g.fwd.ops if op[0] is not None)
+    assert kinds['cis_warp_costvol'] == 5 and kinds['cis_cis_loss_fwd'] == 1 and kinds['cis_cis_loss_reduce'] == 1
+    assert g.launches_per_step('G') > 400 and g.launches_per_step('R') > 400
+    flops = sum(op[3] for op in g.fwd.ops)
+    assert flops > 0
+
+
+def test_experiment_switches_change_only_what_they_claim(monkeypatch):
+    """Two-launch split-K and the thin-layer switch are planner decisions: preview them without a GPU."""
+    base = CISGraph(64, 96, 1, device='cpu', global_batch=1)
+    nbase = base.fwd.count()
+    monkeypatch.setattr(engine, 'SPLITK', 2)
+    monkeypatch.setattr(engine, 'SPLITK_MAX', 16)
+    monkeypatch.setattr(engine, 'SPLITK_NCTA', 8)
+    monkeypatch.setattr(engine, 'SPLITK_MIN_UNITS', 16)
+    g = CISGraph(64, 96, 1, device='cpu', global_batch=1)
+    split = [d for d in _convs(g.fwd) if d.splits > 1]
+    assert split and all(not d.sk_counters and d.sk_scratch for d in split)        # NULL counters = two-launch mode
+    assert g.fwd.count() == nbase + len(split)                                     # the finish launch is counted
+    for d in split:
+        units = (-(-sum(d.src[i].chunks for i in range(d.nsrc)) // 8)) if d.halo else d.K_pad // 64
+        per = -(-units // d.splits)
+        assert (d.splits - 1) * per < units                                        # every split owns at least one unit (launcher check)
+    monkeypatch.setattr(engine, 'SPLITK', 0)
+    monkeypatch.setattr(engine, 'HALO_SKIP_THIN', 8)
+    g2 = CISGraph(64, 96, 1, device='cpu', global_batch=1)
+    changed = [(a.halo, b.halo) for a, b in zip(_convs(base.fwd), _convs(g2.fwd)) if a.halo != b.halo]
+    assert changed and all(a == 1 and b == 0 for a, b in changed)                  # only halo -> gather moves
+    assert all(sum(d.src[i].chunks for i in range(d.nsrc)) * 8 <= 8 and d.ntaps >= 16
+               for d, e in zip(_convs(base.fwd), _convs(g2.fwd)) if d.halo != e.halo)

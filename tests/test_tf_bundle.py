@@ -278,3 +278,48 @@ def test_learner_save_writes_saver_layout_and_reads_back(tmp_path, capsys):
     assert not AdversarialLearner._is_ckpt(os.path.join(d, 'model-6')) and not AdversarialLearner._is_ckpt('')
     with pytest.raises(KeyError):
         AdversarialLearner._read_ckpt(os.path.join(d, 'model-5'), ['MaskNet/conv1/kernel', 'pwcnet/nope/kernel'])
+
+
+# ----------------------------------------------------------------------------------------------------------- property tests
+from hypothesis import given, settings, strategies as st   # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(st.integers(min_value=0, max_value=(1 << 64) - 1), min_size=1, max_size=20))
+def test_varint_roundtrip(values):
+    buf = bytearray()
+    for v in values:
+        tb._put_varint(buf, v)
+    pos, out = 0, []
+    for _ in values:
+        v, pos = tb._get_varint(buf, pos)
+        out.append(v)
+    assert out == values and pos == len(buf)
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.dictionaries(st.binary(min_size=0, max_size=40), st.binary(min_size=0, max_size=200), min_size=1, max_size=60),
+       st.sampled_from([64, 300, 4096]))
+def test_table_roundtrip_random_keys(tmp_path_factory, kv, block_size):
+    items = sorted(kv.items())
+    p = str(tmp_path_factory.mktemp('tbl') / 'r.index')
+    tb.write_table(p, items, block_size=block_size)
+    assert tb.read_table(p) == items
+
+
+@settings(max_examples=20, deadline=None)
+@given(st.lists(st.tuples(st.sampled_from([np.float32, np.int32, np.int64, np.float64]),
+                          st.lists(st.integers(min_value=0, max_value=5), min_size=0, max_size=4)), min_size=1, max_size=8),
+       st.integers(min_value=0, max_value=2 ** 31 - 1))
+def test_bundle_roundtrip_random_tensors(tmp_path_factory, specs, seed):
+    rng = np.random.RandomState(seed)
+    t = {}
+    for i, (dt, shape) in enumerate(specs):
+        a = (rng.randn(*shape) * 100).astype(dt) if shape else np.asarray(rng.randint(-1000, 1000), dtype=dt)
+        t['scope_%d/var:%d' % (i % 3, i)] = a
+    prefix = str(tmp_path_factory.mktemp('bndl') / 'ck')
+    tb.write_bundle(prefix, t)
+    r = tb.read_bundle(prefix)
+    assert set(r) == set(t)
+    for k in t:
+        assert r[k].dtype == t[k].dtype and r[k].shape == t[k].shape and np.array_equal(r[k], t[k])

@@ -84,3 +84,30 @@ def test_test_iterator_order_and_boundaries(root):
     assert 5 < float(blue(i2)[0] - blue(i1)[0]) < 35 and -35 < float(blue(i2)[5] - blue(i1)[5]) < -5
     it2 = rd.test_inputs(partition='val', t_len=-2)
     assert it2.pairs[:2] == [(0, 1.0), (1, 1.0)] and it2.pairs[2] == (2, -1.0)
+
+
+def test_video_to_davis_layout_feeds_the_reader(tmp_path):
+    """scripts/create_data_frvideo.py: a short synthetic clip becomes a DAVIS-style tree the reader accepts."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('create_data_frvideo', os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), 'scripts', 'create_data_frvideo.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    clip = str(tmp_path / 'clip.avi')
+    vw = cv2.VideoWriter(clip, cv2.VideoWriter_fourcc(*'MJPG'), 12.0, (96, 64))
+    if not vw.isOpened():
+        pytest.skip('no MJPG video writer in this OpenCV build')
+    for i in range(10):
+        f = np.full((64, 96, 3), 40, np.uint8)
+        f[:, 8 * i:8 * i + 8] = 220
+        vw.write(f)
+    vw.release()
+    out = str(tmp_path / 'ds')
+    n = mod.convert(clip, out, fps=12.0, size=(80, 48))
+    assert n == 10 and len(os.listdir(os.path.join(out, 'JPEGImages/480p/clip'))) == 10
+    rd = D.Davis2016Reader(out, num_threads=1)
+    it = rd.test_inputs(batch_size=2, partition='val', t_len=1, test_crop=1.0)
+    i1, i2, seg, names = it.batch(3, pinned=False)
+    assert i1.shape == (3, 384, 640, 3) and float(seg.max()) == 0.0 and names[0].endswith('clip/00000.jpg')
+    with pytest.raises(IOError):
+        mod.convert(str(tmp_path / 'missing.mp4'), out)

@@ -188,6 +188,10 @@ int cis_pack_generator_input(const float* image, const float* flow, const double
 /* ---- mask (x) flow + Charbonnier contextual-information loss (adversarial_learner.py:107-110,141-204) ---- */
 /* recover inputs, batch 3B: [flow*(1-m),1,1-m | flow*m,1,m | 0,0,1,0] -> bf16 [3B,H,W,8] (nets.py:50-53) */
 int cis_mask_apply(const float* flow, const float* mask, int32_t B, int64_t hw, void* dst, cis_stream_t stream);
+/* stand-alone charbonnier_loss (loss_utils.py:34-51): sums[b] += sum over pixels and C channels of ((gt-pred)^2 + 1e-6)^cbn * mask;
+ * mask_c = 1 (one value per pixel) or C (one per element); sums = double [B], zeroed by the caller */
+int cis_charbonnier_sum(const float* gt, const float* pred, const float* mask, int32_t B, int64_t hw, int32_t C, int32_t mask_c, float cbn,
+                        double* sums, cis_stream_t stream);
 /* sums[b] = {rec, rec_c, prior, den, den_c} (fp32 via double atomics; zeroed).  flow1 = fp32 [3B,H/2,W/2,2] recover
  * outputs before the final bilinear x2 (nets.py:108), which is fused here. */
 int cis_cis_loss_fwd(const float* flow, const float* mask, const float* flow1, int32_t B, int32_t H, int32_t W, int32_t h1,

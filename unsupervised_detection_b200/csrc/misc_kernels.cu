@@ -579,6 +579,24 @@ __device__ __forceinline__ float dcharb_dpred(float d, float cbn) {  // d = gt -
   const float s = d * d + 1e-6f;
   return cbn == 0.5f ? -d * rsqrtf(s) : -2.f * cbn * d * powf(s, cbn - 1.f);
 }
+// Stand-alone charbonnier_loss (loss_utils.py:34-51) for the functional API: sums[b] = sum_{p,c} ((gt-pred)^2 + 1e-6)^cbn * mask.
+// mask_c = 1: one mask value per pixel (broadcast over the C channels), mask_c = C: one per element.  sums (double) must be zeroed.
+__global__ void charbonnier_sum_kernel(const float* __restrict__ gt, const float* __restrict__ pred, const float* __restrict__ mask, size_t hw,
+                                       int C, int mask_c, float cbn, double* __restrict__ sums) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y;
+  double acc = 0;
+  for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < hw; p += (size_t)gridDim.x * blockDim.x) {
+    const size_t base = ((size_t)b * hw + p);
+    for (int c = 0; c < C; ++c) {
+      const float m = mask[mask_c == 1 ? base : base * C + c];
+      acc += (double)(charb(gt[base * C + c] - pred[base * C + c], cbn) * m);
+    }
+  }
+  acc = warp_sum_d(acc);
+  if ((threadIdx.x & 31) == 0) atomicAdd(sums + b, acc);
+}
 __global__ void cis_loss_fwd_kernel(const float* __restrict__ flow, const float* __restrict__ mask, const float* __restrict__ flow1, int B, int H,
                                     int W, int h1, int w1, float cbn, double* __restrict__ sums, float* __restrict__ pred_out) {
   pdl_launch_dependents();
@@ -907,6 +925,13 @@ int cis_pack_generator_input(const float* image, const float* flow, const double
 int cis_mask_apply(const float* flow, const float* mask, int32_t B, int64_t hw, void* dst, cis_stream_t stream) {
   CIS_LAUNCH(mask_apply_kernel, nblk((size_t)B * hw), 256, 0, ST, flow, mask, (size_t)B * hw, (mbf)dst);
   return cis_check_launch("mask_apply");
+}
+int cis_charbonnier_sum(const float* gt, const float* pred, const float* mask, int32_t B, int64_t hw, int32_t C, int32_t mask_c, float cbn,
+                        double* sums, cis_stream_t stream) {
+  if (C < 1 || (mask_c != 1 && mask_c != C)) return cis_set_error(CIS_ERR_BAD_ARG, "cis_charbonnier_sum: mask must have 1 or C channels");
+  dim3 grid(64, B);
+  CIS_LAUNCH(charbonnier_sum_kernel, grid, 256, 0, ST, gt, pred, mask, (size_t)hw, C, mask_c, cbn, sums);
+  return cis_check_launch("charbonnier_sum");
 }
 int cis_cis_loss_fwd(const float* flow, const float* mask, const float* flow1, int32_t B, int32_t H, int32_t W, int32_t h1, int32_t w1, float cbn,
                      double* sums, float* pred_out, cis_stream_t stream) {

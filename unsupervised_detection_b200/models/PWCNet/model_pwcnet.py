@@ -56,6 +56,13 @@ class ModelPWCNet(object):
         return list(self.L.values())
 
     @staticmethod
+    def predict_from_img_pairs(img_1, img_2, params=None, name='pwcnet'):
+        """model_pwcnet.py:39-76 of the reference: flow img_1 -> img_2 for batches of NHWC images in [-0.5, 0.5] (function-level API,
+        see models/functional.py; the training step uses the `build` method below inside its static graph instead)."""
+        from .. import functional
+        return functional.predict_from_img_pairs(img_1, img_2, name, params)
+
+    @staticmethod
     def level_pitch(l):
         return A_TOTAL + CORR_PAD + (0 if l == PYR_LVLS else NUM_CHANN[l] + 8)
 

@@ -153,3 +153,15 @@ class RecoverNet(object):
         self.flow1 = B.conv(L['flow1'], concat1, outf=flow1_out)
         self.pyramid = dict(flow5=flow5, flow4=flow4, flow3=flow3, flow2=flow2, flow1=self.flow1)
         return self.flow1
+
+
+def generator_net(images, flows, scope='MaskNet', reuse=None, training=True, params=None):
+    """Function-level API of the reference (nets.py:4-42); see models/functional.py."""
+    from . import functional
+    return functional.generator_net(images, flows, scope, reuse, training, params)
+
+
+def recover_net(img1, flow_masked, mask, scope='FlownetS', reuse=None, f=0.25, training=True, params=None):
+    """Function-level API of the reference (nets.py:45-110); see models/functional.py."""
+    from . import functional
+    return functional.recover_net(img1, flow_masked, mask, scope, reuse, f, training, params)

@@ -217,6 +217,18 @@ def run_ours(args):
     ms_e2e = timed(lambda i: L.step(pool[(i + off) % 2], fetch_losses=True, next_batch=pool[(i + off + 1) % 2]), K)
     smp.stop_flag = True
     smp.join(timeout=2)
+    # each step kind on its own (SURVEY 8d asks for the 1R:3G cycle average AND the two kinds separately); single GPU only, after the
+    # headline measurements, and never allowed to take them down
+    by_kind = None
+    if world == 1:
+        try:
+            by_kind = {}
+            for mode in ('R', 'G'):
+                for _ in range(3):
+                    g.train_step(mode, allreduce=None, use_graph=True)
+                by_kind['recover' if mode == 'R' else 'generator'] = timed(lambda i, m=mode: g.train_step(m, allreduce=None, use_graph=True), 8) / 8
+        except Exception:
+            by_kind = None
     gb = BPG * world
     value = gb * K / (ms_dev / 1e3)
     e2e = gb * K / (ms_e2e / 1e3)
@@ -242,7 +254,7 @@ def run_ours(args):
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': {'workload': 'DAVIS2016-shaped adversarial train 256x448, batch 4/GPU, PWC-Net 384x640 in loop, 1 rec : 3 gen (configs[1])',
                        'global_batch': gb, 'parallelism': 'dp%d' % world, 'l2': 'per-step working set (activations) exceeds the 126 MB L2',
-                       'cuda_graph': True},
+                       'cuda_graph': True, 'ms_per_step_by_kind': by_kind},
             'e2e': {'value': e2e, 'unit': 'frame-pairs/s', 'h2d_bytes_per_step': 2 * BPG * 384 * 640 * 3 * 4, 'd2h_bytes_per_step': 32,
                     'ms_per_step': ms_e2e / K},
             'gpu_launches': launches,

@@ -111,3 +111,21 @@ def test_video_to_davis_layout_feeds_the_reader(tmp_path):
     assert i1.shape == (3, 384, 640, 3) and float(seg.max()) == 0.0 and names[0].endswith('clip/00000.jpg')
     with pytest.raises(IOError):
         mod.convert(str(tmp_path / 'missing.mp4'), out)
+
+
+def test_learner_wires_the_davis_reader(root):
+    """AdversarialLearner.load_training_data (adversarial_learner.py:22-70 / :454-470): train + validation iterators, inference iterator."""
+    from unsupervised_detection_b200.common_flags import Config
+    from unsupervised_detection_b200.models.adversarial_learner import AdversarialLearner
+    L = object.__new__(AdversarialLearner)
+    L.rank = 0
+    L.config = Config(dataset='DAVIS2016', root_dir=root, batch_size=2, train_partition='train', max_temporal_len=2, min_temporal_len=1)
+    L.load_training_data()
+    assert L.num_samples_val == 6 and len(L.reader.pairs) == 16 and len(L.val_reader.pairs) == 6
+    L._inference, L.aug_test = True, True
+    L.config = Config(dataset='DAVIS2016', root_dir=root, batch_size=1, test_partition='val', test_temporal_shift=1, test_crop=0.9)
+    L.load_training_data()
+    assert L.reader.val_samples == 6 and L.dataset_reader.test_crop == 1.0          # aug_test crops later (0.85..1.0), reader stays uncropped
+    with pytest.raises(IOError):
+        L.config = Config(dataset='DAVIS2016', root_dir='/nonexistent')
+        L.load_training_data()

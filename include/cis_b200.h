@@ -110,6 +110,11 @@ int cis_version(void);
  * tensorflow/core/lib/hash/crc32c.h (TensorFlow 1.13, third-party, not vendored in the reference) behind
  * tf.train.Saver (models/adversarial_learner.py:326-331).  Not a stream operation; no GPU needed. */
 uint32_t cis_crc32c(uint32_t crc, const void* data, size_t n);
+/* Host-side frame preprocessing for the dataset readers (no GPU, not stream operations; thread-safe, callers run them from a thread pool).
+ * tf.image.resize_images legacy bilinear on an HWC float image, and the fused decode-side step of preprocess_image
+ * (data/davis2016_data_utils.py:84-90 of the reference): BGR uint8 -> RGB float v/255-0.5 -> legacy bilinear to OH x OW. */
+int cis_host_resize_bilinear_legacy(const float* src, int32_t H, int32_t W, int32_t C, float* dst, int32_t OH, int32_t OW);
+int cis_host_bgr8_to_rgb_resized(const unsigned char* bgr, int32_t H, int32_t W, float* dst, int32_t OH, int32_t OW);
 
 int cis_conv_igemm(const CisConv* d, cis_stream_t stream);
 /* which launches use the persistent warp-specialised halo kernel: 0 none, 1 thin single-chunk layers (default), 2 all eligible,

@@ -129,3 +129,20 @@ def test_learner_wires_the_davis_reader(root):
     with pytest.raises(IOError):
         L.config = Config(dataset='DAVIS2016', root_dir='/nonexistent')
         L.load_training_data()
+
+
+def test_host_c_preprocessing_is_bit_identical_to_the_numpy_restatement(root):
+    """cis_host_resize_bilinear_legacy / cis_host_bgr8_to_rgb_resized (libcis_b200 host routines used by every reader) against the numpy
+    gather version and, through it, the oracle's legacy resize."""
+    rng = np.random.RandomState(5)
+    for (h, w, oh, ow, c) in [(48, 80, 384, 640, 3), (230, 390, 384, 640, 3), (7, 9, 12, 16, 3), (345, 576, 384, 640, 1), (5, 3, 11, 2, 2),
+                              (1, 1, 4, 4, 3), (20, 20, 7, 33, 4)]:
+        x = rng.rand(h, w, c).astype(np.float32) - 0.5
+        assert np.array_equal(D.legacy_resize(x, oh, ow), D.legacy_resize_numpy(x, oh, ow))
+        assert np.array_equal(D.legacy_resize(x[::-1, ::-1], oh, ow), D.legacy_resize_numpy(np.ascontiguousarray(x[::-1, ::-1]), oh, ow))
+    x = rng.rand(6, 7, 3).astype(np.float32)
+    assert np.abs(D.legacy_resize(x, 9, 5) - T.resize_bilinear_legacy(torch.from_numpy(x)[None], 9, 5)[0].numpy()).max() < 1e-6
+    path = os.path.join(root, 'JPEGImages/480p/bear/00002.jpg')
+    bgr = cv2.imread(path)
+    rgb = cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB).astype(np.float32) / np.float32(255.0) - np.float32(0.5)
+    assert np.array_equal(D.Davis2016Reader.preprocess_image(path), D.legacy_resize_numpy(rgb, 384, 640))

@@ -82,7 +82,8 @@ _PROTOS = {
     'cis_cast_f32_to_bf16': [_p, _i64, _p],
     'cis_cast_bf16_to_f32': [_p, _i64, _i32, _i32, _i32, _p],
 }
-EXPORTS = sorted(list(_PROTOS) + ['cis_last_error', 'cis_version', 'cis_set_persist_mode', 'cis_crc32c'])
+EXPORTS = sorted(list(_PROTOS) + ['cis_last_error', 'cis_version', 'cis_set_persist_mode', 'cis_crc32c', 'cis_host_resize_bilinear_legacy',
+                                  'cis_host_bgr8_to_rgb_resized'])
 
 _lib = None
 
@@ -101,6 +102,10 @@ def load():
         lib.cis_set_persist_mode.restype = C.c_int
         lib.cis_crc32c.argtypes = [C.c_uint32, C.c_void_p, C.c_size_t]
         lib.cis_crc32c.restype = C.c_uint32
+        lib.cis_host_resize_bilinear_legacy.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]
+        lib.cis_host_resize_bilinear_legacy.restype = C.c_int
+        lib.cis_host_bgr8_to_rgb_resized.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_int32]
+        lib.cis_host_bgr8_to_rgb_resized.restype = C.c_int
         for name, args in _PROTOS.items():
             fn = getattr(lib, name)
             fn.argtypes = list(args) + [C.c_void_p]

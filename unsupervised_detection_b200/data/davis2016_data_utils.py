@@ -14,6 +14,8 @@ import cv2
 import numpy as np
 import torch
 
+from .. import _lib
+
 ORIG_H, ORIG_W = 384, 640   # preprocess_image :87-90
 
 
@@ -57,7 +59,21 @@ class DirectoryIterator(object):
 
 
 def legacy_resize(x, oh, ow):
-    """tf.image.resize_images (legacy bilinear, App. A.6) on an HWC float32 array."""
+    """tf.image.resize_images (legacy bilinear, App. A.6) on an HWC float32 array -- libcis_b200's host routine
+    (cis_host_resize_bilinear_legacy, ~2 ms per 384x640x3 frame, GIL released); bit-identical to `legacy_resize_numpy`."""
+    h, w = x.shape[:2]
+    if (h, w) == (oh, ow):
+        return x
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if x.ndim == 2:
+        x = x[..., None]
+    out = np.empty((oh, ow, x.shape[2]), np.float32)
+    _lib.check(_lib.load().cis_host_resize_bilinear_legacy(x.ctypes.data, h, w, x.shape[2], out.ctypes.data, oh, ow), 'host resize')
+    return out
+
+
+def legacy_resize_numpy(x, oh, ow):
+    """The same resize written with numpy gathers (about 15x slower): the restatement the C routine is tested against."""
     h, w = x.shape[:2]
     if (h, w) == (oh, ow):
         return x
@@ -143,8 +159,12 @@ class Davis2016Reader(object):
         bgr = cv2.imread(path, cv2.IMREAD_COLOR)
         if bgr is None:
             raise IOError("Could not read image %s" % path)
-        rgb = cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB).astype(np.float32) / np.float32(255.0) - np.float32(0.5)
-        return legacy_resize(rgb, ORIG_H, ORIG_W)
+        # BGR uint8 -> RGB float (v/255 - 0.5) -> legacy bilinear 384x640 in one pass of libcis_b200's host routine
+        bgr = np.ascontiguousarray(bgr)
+        out = np.empty((ORIG_H, ORIG_W, 3), np.float32)
+        _lib.check(_lib.load().cis_host_bgr8_to_rgb_resized(bgr.ctypes.data, bgr.shape[0], bgr.shape[1], out.ctypes.data, ORIG_H, ORIG_W),
+                   'host preprocess')
+        return out
 
     @staticmethod
     def preprocess_mask(path):

@@ -146,3 +146,29 @@ def test_host_c_preprocessing_is_bit_identical_to_the_numpy_restatement(root):
     bgr = cv2.imread(path)
     rgb = cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB).astype(np.float32) / np.float32(255.0) - np.float32(0.5)
     assert np.array_equal(D.Davis2016Reader.preprocess_image(path), D.legacy_resize_numpy(rgb, 384, 640))
+
+
+def test_prefetching_iterator_yields_the_same_stream(root):
+    """Background prefetch (dataset.prefetch of the reference) changes neither order nor content, survives a batch-size change and
+    propagates reader errors to the consumer."""
+    def stream(prefetch):
+        rd = D.Davis2016Reader(root, max_temporal_len=2, min_temporal_len=1, num_threads=3, seed=11)
+        rd.prefetch = prefetch
+        it = rd.image_inputs(batch_size=2, partition='train', train_crop=0.8)
+        out = [it.batch(2, pinned=False) for _ in range(5)] + [it.batch(3, pinned=False) for _ in range(2)]
+        it.close()
+        return out
+    a, b = stream(0), stream(3)
+    for x, y in zip(a[:5], b[:5]):                                  # constant batch size: identical stream
+        assert x[3] == y[3] and torch.equal(x[0], y[0]) and torch.equal(x[1], y[1])
+    # a batch-size change restarts the producer; batches it had decoded ahead are dropped, so only the shapes are comparable
+    assert a[0][0].shape == (2, 384, 640, 3) and a[-1][0].shape == (3, 384, 640, 3)
+    rd = D.Davis2016Reader(root, num_threads=2, seed=1)
+    rd.prefetch = 2
+    it = rd.image_inputs(batch_size=2, partition='train', train_crop=0.9)
+    it.batch(2, pinned=False)
+    rd.filenames = ['/nonexistent.jpg'] * len(rd.filenames)           # every later sample fails to decode
+    with pytest.raises(IOError):
+        for _ in range(6):
+            it.batch(2, pinned=False)
+    it.close()

@@ -6,8 +6,11 @@ Same folder contract (`ImageSets/480p/{train,val,trainval}.txt` listing `/JPEGIm
 the head of a sequence / backward from its tail), same preprocessing (x/255-0.5, legacy-bilinear resize to 384x640, random
 flips applied to both frames, random / central crop resized back).  JPEG decoding and augmentation stay on the CPU.
 """
+import collections
 import os
+import queue
 import random
+import threading
 from concurrent.futures import ThreadPoolExecutor
 
 import cv2
@@ -107,34 +110,96 @@ def central_crop_box(h, w, frac):
 
 
 class _Iter(object):
-    """Endless batch iterator with the interface AdversarialLearner uses: .batch(n) -> (img1, img2, seg1, fnames)."""
+    """Endless batch iterator with the interface AdversarialLearner uses: .batch(n) -> (img1, img2, seg1, fnames).
 
-    def __init__(self, reader, pairs, train, shuffle, num_threads):
+    `prefetch` > 0 keeps that many batches decoded ahead of the consumer in a background thread (the reference's
+    `dataset.prefetch(3 * batch_size)`, davis2016_data_utils.py:226): host decoding / augmentation of the next batches overlaps the
+    GPU step that consumes the current one.  For a constant batch size, order and content are the same with or without prefetching
+    (one producer, FIFO queue, iterator-private random stream); changing the batch size restarts the producer and drops what it had
+    decoded ahead."""
+
+    def __init__(self, reader, pairs, train, shuffle, num_threads, prefetch=0):
         self.reader, self.pairs, self.train, self.shuffle = reader, list(pairs), train, shuffle
         self.pool = ThreadPoolExecutor(max_workers=max(1, num_threads))
+        self.rng = random.Random(reader.rng.getrandbits(64))     # private stream: iterators of one reader do not interleave draws
         self.pos = 0
         self.order = list(range(len(self.pairs)))
         if shuffle:
-            reader.rng.shuffle(self.order)
+            self.rng.shuffle(self.order)
+        self.prefetch = prefetch
+        self._q = self._thread = self._qn = None
+        self._stop = threading.Event()
 
     def _next_index(self):
         if self.pos >= len(self.order):          # dataset.repeat(None) (+ reshuffle_each_iteration)
             self.pos = 0
             if self.shuffle:
-                self.reader.rng.shuffle(self.order)
+                self.rng.shuffle(self.order)
         i = self.order[self.pos]
         self.pos += 1
         return i
 
-    def batch(self, n, pinned=True):
+    def _submit(self, n):
+        """Draw the next n samples (indices + augmentation seeds, in stream order) and hand them to the thread pool."""
         idx = [self._next_index() for _ in range(n)]
         fn = self.reader._train_sample if self.train else self.reader._test_sample
-        seeds = [self.reader.rng.getrandbits(32) for _ in idx]
-        res = list(self.pool.map(lambda a: fn(self.pairs[a[0]], a[1]), zip(idx, seeds)))
-        out = [torch.from_numpy(np.stack([r[k] for r in res])) for k in range(3)]
+        seeds = [self.rng.getrandbits(32) for _ in idx]
+        return [self.pool.submit(fn, self.pairs[i], sd) for i, sd in zip(idx, seeds)]
+
+    @staticmethod
+    def _collect(futs):
+        res = [f.result() for f in futs]
+        return [torch.from_numpy(np.stack([r[k] for r in res])) for k in range(3)] + [[r[3] for r in res]]
+
+    def _make(self, n):
+        return self._collect(self._submit(n))
+
+    def _producer(self, n, q, stop):
+        inflight = collections.deque()           # several batches are decoded concurrently so all pool threads stay busy
+        while not stop.is_set():
+            while len(inflight) < max(1, self.prefetch):
+                inflight.append(self._submit(n))
+            try:
+                item = self._collect(inflight.popleft())
+            except Exception as e:               # surfaces in the consumer's batch() call
+                item = e
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.1)
+                    break
+                except queue.Full:
+                    continue
+            if isinstance(item, Exception):
+                break
+        for futs in inflight:
+            for f in futs:
+                f.cancel()
+
+    def close(self):
+        """Stop the background producer (batches already decoded ahead are dropped)."""
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=5)
+            self._q = self._thread = self._qn = None
+            self._stop = threading.Event()
+
+    def batch(self, n, pinned=True):
+        if self.prefetch > 0:
+            if self._qn != n:                    # (re)start the producer for this batch size
+                self.close()
+                self._q, self._qn = queue.Queue(maxsize=self.prefetch), n
+                self._thread = threading.Thread(target=self._producer, args=(n, self._q, self._stop), daemon=True)
+                self._thread.start()
+            out = self._q.get()
+            if isinstance(out, Exception):
+                self.close()
+                raise out
+        else:
+            out = self._make(n)
+        ts = out[:3]
         if pinned and torch.cuda.is_available():
-            out = [t.pin_memory() for t in out]
-        return out[0], out[1], out[2], [r[3] for r in res]
+            ts = [t.pin_memory() for t in ts]
+        return ts[0], ts[1], ts[2], out[3]
 
 
 class Davis2016Reader(object):
@@ -147,6 +212,7 @@ class Davis2016Reader(object):
         assert min_temporal_len > 0, "Min temporal len should be positive"
         self.num_threads = num_threads
         self.rng = random.Random(seed)
+        self.prefetch = int(os.environ.get('CIS_READER_PREFETCH', '3'))     # training batches decoded ahead (0 = synchronous)
 
     def get_filenames_list(self, partition):
         it = DirectoryIterator(self.root_dir, partition)
@@ -228,7 +294,7 @@ class Davis2016Reader(object):
             pairs += [(i, -1.0) for i in range(N + t_len, N + len(fnames))]      # backward from the tail
             N += len(fnames)
         self.filenames = [f for fl in file_list for f in fl]
-        return _Iter(self, pairs, train=True, shuffle=True, num_threads=self.num_threads)
+        return _Iter(self, pairs, train=True, shuffle=True, num_threads=self.num_threads, prefetch=self.prefetch)
 
     def test_inputs(self, batch_size=32, partition='val', t_len=2, with_fname=False, test_crop=1.0):
         """:233-290 -> ordered iterator (img_1, img_2, seg_1, fname); time(img2)-time(img1) = t_len except at sequence ends."""

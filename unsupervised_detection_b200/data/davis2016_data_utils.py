@@ -183,6 +183,12 @@ class _Iter(object):
             self._q = self._thread = self._qn = None
             self._stop = threading.Event()
 
+    def __del__(self):
+        try:
+            self._stop.set()
+        except Exception:
+            pass
+
     def batch(self, n, pinned=True):
         if self.prefetch > 0:
             if self._qn != n:                    # (re)start the producer for this batch size
@@ -313,4 +319,5 @@ class Davis2016Reader(object):
         self.filenames = [f for fl in file_list for f in fl]
         self.annotation_filenames = [f for fl in ann_list for f in fl]
         pairs = [(i, 1.0) for i in first] + [(i, -1.0) for i in last]
-        return _Iter(self, pairs, train=False, shuffle=False, num_threads=1)
+        # ordered: the FIFO prefetch queue keeps the list order even with several decoding threads (the reference pins num_threads=1 for that)
+        return _Iter(self, pairs, train=False, shuffle=False, num_threads=self.num_threads, prefetch=self.prefetch)

@@ -141,8 +141,7 @@ class FBMS59Reader(Davis2016Reader):
         """:311-335 -> ordered iterator over the annotated frames of every category."""
         tuples = self.get_test_tuples(partition, t_len)
         self.test_crop = test_crop
-        self.num_threads = 1
-        return _Iter(self, tuples, train=False, shuffle=False, num_threads=1)
+        return _Iter(self, tuples, train=False, shuffle=False, num_threads=self.num_threads, prefetch=self.prefetch)
 
     def batch_samples_per_cat(self, fnames):
         """The 5th element of the reference's test batch: number of annotated frames of each sample's category."""

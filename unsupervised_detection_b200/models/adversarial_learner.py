@@ -321,9 +321,14 @@ class AdversarialLearner(object):
             print("Training {} Recover and {} Generator".format(config.iters_rec, config.iters_gen))
             print("-------------------------------------")
         self.collect_summaries()
+        batch = self.reader.batch(self.local_batch)
         for step in count(start=1):
             start_time = time.time()
-            results = self.step(summarize=True)
+            # the next batch (already decoded by the reader's background prefetch) is copied to the device on the side stream while this
+            # step computes -- the same step(batch, next_batch=...) pattern bench.py's end-to-end arm measures
+            nxt = self.reader.batch(self.local_batch)
+            results = self.step(batch, summarize=True, next_batch=nxt)
+            batch = nxt
             if step % config.summary_freq == 0 and self.rank == 0:
                 train_epoch = math.ceil(step / self.train_steps_per_epoch)
                 train_step = step - (train_epoch - 1) * self.train_steps_per_epoch

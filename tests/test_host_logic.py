@@ -176,3 +176,45 @@ def test_learner_error_conventions():
     L.config = Config(dataset='DAVIS2016', root_dir='/nonexistent')
     with pytest.raises(IOError):
         L.load_training_data()
+
+
+def test_train_loop_control_flow_on_cpu(capsys):
+    """AdversarialLearner.train (adversarial_learner.py:376-420) with the GPU parts stubbed: every batch is consumed once and in order,
+    the NEXT batch is handed to step() for the overlapped host->device copy, epochs end after num_samples_train/batch_size steps and
+    training stops after max_epochs."""
+    from unsupervised_detection_b200.common_flags import Config
+    from unsupervised_detection_b200.models.adversarial_learner import AdversarialLearner
+
+    class Reader(object):
+        def __init__(self):
+            self.n = 0
+
+        def batch(self, b):
+            self.n += 1
+            return ('img1_%d' % self.n, 'img2_%d' % self.n, None, [])
+
+    class Graph(object):
+        def param_count(self):
+            return 123
+
+    class Stub(AdversarialLearner):
+        def build_train_graph(self):
+            self.rank, self.world, self.local_batch = 0, 1, 2
+            self.reader, self.graph = Reader(), Graph()
+            self.train_steps_per_epoch = 3
+            self.calls, self.epochs = [], []
+
+        def step(self, batch=None, fetch_losses=None, use_graph=True, next_batch=None, summarize=False):
+            self.calls.append((batch[0], next_batch[0], summarize))
+            return {'global_step': len(self.calls) // 4, 'train_op': 'G', 'loss_generator': 1.0, 'loss_recover': 2.0}
+
+        def epoch_end_callback(self, sess, sv, epoch_num):
+            self.epochs.append((epoch_num, len(self.calls)))
+
+    L = Stub()
+    L.train(Config(max_epochs=2, summary_freq=2, checkpoint_dir=''))
+    assert [c[0] for c in L.calls] == ['img1_%d' % i for i in range(1, 7)]            # 2 epochs x 3 steps, each batch used once, in order
+    assert [c[1] for c in L.calls] == ['img1_%d' % i for i in range(2, 8)]            # step k is given batch k+1 to prefetch
+    assert all(c[2] for c in L.calls) and L.epochs == [(1, 3), (2, 6)]
+    out = capsys.readouterr().out
+    assert 'Number of params: 123' in out and 'Training completed successfully' in out and out.count('loss_generator') == 3

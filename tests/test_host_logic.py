@@ -218,3 +218,57 @@ def test_train_loop_control_flow_on_cpu(capsys):
     assert all(c[2] for c in L.calls) and L.epochs == [(1, 3), (2, 6)]
     out = capsys.readouterr().out
     assert 'Number of params: 123' in out and 'Training completed successfully' in out and out.count('loss_generator') == 3
+
+
+def test_epoch_end_callback_validation_and_saving_on_cpu(tmp_path):
+    """adversarial_learner.py:422-448: validation IoU = sum over batches / (steps * batch_size); model.best on improvement, model-<epoch>
+    every save_freq epochs; the IoU goes to the event file."""
+    import numpy as np
+    import torch
+    from unsupervised_detection_b200.common_flags import Config
+    from unsupervised_detection_b200.models.adversarial_learner import AdversarialLearner
+    from unsupervised_detection_b200.summary import SummaryWriter, read_events
+
+    gt = torch.zeros(2, 16, 24, 1)
+    gt[:, 4:12, 6:18] = 1.0
+
+    class Graph(object):
+        def __init__(self):
+            self.mask = None
+            self.quality = 0
+
+        def forward(self):
+            m = torch.zeros(2, 8, 12, 1)
+            if self.quality == 1:                      # half of the object
+                m[:, 2:6, 3:6] = 0.9
+            elif self.quality == 2:                    # the whole object (ground truth is NN-resized to the mask size)
+                m[:, 2:6, 3:9] = 0.9
+            self.mask = m
+
+    class ValReader(object):
+        def batch(self, b):
+            return torch.zeros(2, 384, 640, 3), torch.zeros(2, 384, 640, 3), gt, ['a', 'b']
+
+    class Stub(AdversarialLearner):
+        def feed(self, img1, img2):
+            self.fed = getattr(self, 'fed', 0) + 1
+
+        def save(self, sess, checkpoint_dir, step):
+            self.saved.append(step)
+
+    L = Stub()
+    L.rank, L.world, L.local_batch, L.device = 0, 1, 2, 'cpu'
+    L.config = Config(batch_size=2, save_freq=2, checkpoint_dir=str(tmp_path))
+    L.graph, L.val_reader, L.reader = Graph(), ValReader(), None
+    L.val_steps_per_epoch, L.min_val_iou, L.saved = 3, -1.0e12, []
+    L.summary_writer = SummaryWriter(str(tmp_path))
+    for epoch, q in ((1, 1), (2, 0), (3, 2), (4, 2)):
+        L.graph.quality = q
+        L.epoch_end_callback(None, None, epoch)
+    assert L.fed == 12
+    # epoch 1: first result is the best so far; epoch 2: worse, but save_freq; epoch 3: better; epoch 4: equal -> only save_freq
+    assert L.saved == ['best', 2, 'best', 4]
+    L.summary_writer.close()
+    ious = [e['values'][0]['simple_value'] for e in read_events(L.summary_writer.path)[1:]]
+    assert [e['step'] for e in read_events(L.summary_writer.path)[1:]] == [1, 2, 3, 4]
+    assert abs(ious[0] - 0.5) < 1e-6 and ious[1] == 0.0 and abs(ious[2] - 1.0) < 1e-6 and abs(ious[3] - 1.0) < 1e-6

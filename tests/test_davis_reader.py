@@ -172,3 +172,21 @@ def test_prefetching_iterator_yields_the_same_stream(root):
         for _ in range(6):
             it.batch(2, pinned=False)
     it.close()
+
+
+def test_multi_crop_matches_the_readers_central_cropping():
+    """data/crops.py (aug_test path of AdversarialLearner.inference) cuts and resizes exactly like Davis2016Reader.central_cropping,
+    i.e. with tf.image.central_crop's geometry, for images and masks."""
+    from unsupervised_detection_b200.data.crops import central_crops
+    rng = np.random.RandomState(9)
+    img1, img2 = (rng.rand(1, 48, 80, 3).astype(np.float32) - 0.5 for _ in range(2))
+    gt = (rng.rand(1, 48, 80, 1) > 0.5).astype(np.float32)
+    crops = [0.85, 0.9, 0.95, 1.0]
+    o1, o2, og = central_crops(torch.from_numpy(img1), torch.from_numpy(img2), torch.from_numpy(gt), crops)
+    assert o1.shape == (4, 48, 80, 3) and og.shape == (4, 48, 80, 1)
+    for i, c in enumerate(crops):
+        assert np.abs(o1[i].numpy() - D.Davis2016Reader.central_cropping(img1[0], c)).max() < 1e-6
+        assert np.abs(o2[i].numpy() - D.Davis2016Reader.central_cropping(img2[0], c)).max() < 1e-6
+        assert np.abs(og[i].numpy() - D.Davis2016Reader.central_cropping(gt[0], c)).max() < 1e-6
+    assert torch.equal(o1[3], torch.from_numpy(img1[0]))                     # crop 1.0 is the identity
+    assert D.central_crop_box(384, 640, 0.85) == (28, 48, 328, 544)          # int((384 - 326.4) / 2) = 28, not (384 - 326) // 2 = 29

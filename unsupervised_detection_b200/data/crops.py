@@ -1,7 +1,6 @@
 """Central multi-crop of a frame pair (data/davis2016_data_utils.py:328-354 augmented_inputs): each crop fraction is cut
 from the centre and resized back to the working resolution with the legacy bilinear rule.  Host side."""
 import torch
-import torch.nn.functional as F
 
 
 def _legacy_resize(x, oh, ow):
@@ -22,13 +21,16 @@ def _legacy_resize(x, oh, ow):
 
 
 def central_crops(img1, img2, gt, crops):
+    """img1, img2 [N,H,W,3], gt [N,H,W,1] -> the crops stacked along the batch axis.  Geometry of tf.image.central_crop
+    (offset = int((dim - dim*frac)/2), size = dim - 2*offset); all three tensors go back to HxW with the legacy bilinear rule --
+    the reference's `central_cropping` resizes the mask bilinearly as well (davis2016_data_utils.py:130-134)."""
+    from .davis2016_data_utils import central_crop_box
     n, h, w, _ = img1.shape
     o1, o2, og = [], [], []
     for c in crops:
-        ch, cw = int(h * c), int(w * c)
-        y0, x0 = (h - ch) // 2, (w - cw) // 2
+        y0, x0, ch, cw = central_crop_box(h, w, c)
         sl = (slice(None), slice(y0, y0 + ch), slice(x0, x0 + cw))
         o1.append(_legacy_resize(img1[sl], h, w))
         o2.append(_legacy_resize(img2[sl], h, w))
-        og.append(F.interpolate(gt[sl].permute(0, 3, 1, 2), size=(h, w), mode='nearest').permute(0, 2, 3, 1))
+        og.append(_legacy_resize(gt[sl], h, w))
     return torch.cat(o1), torch.cat(o2), torch.cat(og)

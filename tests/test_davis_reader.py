@@ -190,3 +190,20 @@ def test_multi_crop_matches_the_readers_central_cropping():
         assert np.abs(og[i].numpy() - D.Davis2016Reader.central_cropping(gt[0], c)).max() < 1e-6
     assert torch.equal(o1[3], torch.from_numpy(img1[0]))                     # crop 1.0 is the identity
     assert D.central_crop_box(384, 640, 0.85) == (28, 48, 328, 544)          # int((384 - 326.4) / 2) = 28, not (384 - 326) // 2 = 29
+
+
+def test_validation_iterator_shards_across_ranks(root):
+    """DP validation: with world_size 2 and a global batch of 4 the two ranks read complementary halves of every global batch."""
+    names = {}
+    for rank in (0, 1):
+        rd = D.Davis2016Reader(root, num_threads=1, seed=8964 + rank)
+        it = rd.test_inputs(batch_size=4, partition='val', t_len=1, test_crop=1.0).shard(rank, 2, 4)
+        names[rank] = [os.path.basename(n) for _ in range(2) for n in it.batch(2, pinned=False)[3]]
+        it.close()
+    rd = D.Davis2016Reader(root, num_threads=1)
+    full = rd.test_inputs(batch_size=4, partition='val', t_len=1, test_crop=1.0)
+    glob = [os.path.basename(n) for _ in range(2) for n in full.batch(4, pinned=False)[3]]
+    full.close()
+    # val has 6 frames: global batches [0..3] and [4,5,0,1] (wrap like dataset.repeat)
+    assert names[0] == [glob[0], glob[1], glob[4], glob[5]] and names[1] == [glob[2], glob[3], glob[6], glob[7]]
+    assert full.shard(0, 1, 4) is full

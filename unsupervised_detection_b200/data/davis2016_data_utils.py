@@ -130,6 +130,20 @@ class _Iter(object):
         self._q = self._thread = self._qn = None
         self._stop = threading.Event()
 
+    def shard(self, rank, world, global_batch):
+        """Data-parallel evaluation: global batch k is samples [k*B, (k+1)*B) of the ordered list (wrapping at the end, like
+        dataset.repeat); rank r reads its contiguous slice of every global batch, so the ranks together see each global batch exactly
+        once.  Ordered iterators only (training iterators are shuffled per rank instead)."""
+        if world <= 1:
+            return self
+        assert not self.shuffle and global_batch % world == 0
+        lb, n = global_batch // world, len(self.pairs)
+        steps = -(-n // global_batch)
+        self.close()
+        self.order = [(k * global_batch + rank * lb + j) % n for k in range(steps) for j in range(lb)]
+        self.pos = 0
+        return self
+
     def _next_index(self):
         if self.pos >= len(self.order):          # dataset.repeat(None) (+ reshuffle_each_iteration)
             self.pos = 0

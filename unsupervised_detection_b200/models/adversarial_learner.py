@@ -61,7 +61,7 @@ class AdversarialLearner(object):
                 self.reader.val_samples = rd.val_samples
             else:
                 self.val_reader = rd.test_inputs(batch_size=cfg.batch_size, t_len=cfg.test_temporal_shift, test_crop=cfg.test_crop,
-                                                 partition='val')
+                                                 partition='val').shard(self.rank, getattr(self, 'world', 1), cfg.batch_size)
                 self.num_samples_val = rd.val_samples
                 self.reader = rd.image_inputs(batch_size=cfg.batch_size, train_crop=cfg.train_crop, partition=cfg.train_partition)
                 self.reader.val_samples = self.num_samples_val

@@ -11,7 +11,6 @@ channels, and the 4x4 stride-2 transposed convs of the level above write up_flow
 """
 import torch
 
-from ... import _lib
 from ...engine import ConvLayer, Act, ACT_NONE, ACT_LEAKY, small_bn_cap
 
 NUM_CHANN = [None, 16, 32, 64, 96, 128, 196]       # model_pwcnet.py:151

@@ -5,7 +5,7 @@ models/utils/convolution_utils.py (gen_conv :26-53, gen_deconv :55-75, conv :77-
 shapes and concat orders.  Activations are bf16 NHWC in HBM, every layer is one cis_conv_igemm launch with
 bias / BN-affine / ELU / leaky / skip-add fused into the epilogue.
 """
-from ..engine import ConvLayer, Act, ACT_NONE, ACT_ELU, ACT_LEAKY
+from ..engine import ConvLayer, ACT_NONE, ACT_ELU, ACT_LEAKY
 
 # name, cin, cout, ksize, stride, rate   (nets.py:19-36)
 GEN_LAYERS = [

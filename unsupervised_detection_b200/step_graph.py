@@ -4,7 +4,6 @@ One `CISGraph` owns the parameters (flat fp32 master copies per scope), all acti
 (batch, 384x640 -> HxW) geometry, and the launch lists: forward (PWC-Net -> resize -> generator -> mask (x) flow ->
 3x recover -> Charbonnier losses), backward for the recover step, backward for the generator step, and clip + TF-Adam.
 """
-import math
 import torch
 
 from . import _lib

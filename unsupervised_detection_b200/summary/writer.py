@@ -28,7 +28,7 @@ import time
 
 import numpy as np
 
-from ..checkpoint.tf_bundle import crc32c, mask_crc, unmask_crc, _get_varint, _parse_proto, _put_varint
+from ..checkpoint.tf_bundle import crc32c, mask_crc, unmask_crc, _parse_proto, _put_varint
 
 
 # ------------------------------------------------------------------------------------------------------------------ protobuf

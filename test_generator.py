@@ -59,13 +59,56 @@ def _test_masks():
     print("Success: Processed {} frames".format(i))
 
 
+def _test_masks_dp():
+    """Batch-sharded variant used under torchrun: every rank evaluates its slice of each global batch of `batch_size * world` frames;
+    scores are merged with one all_gather_object and rank 0 prints the report.  Same per-frame work and file names as `_test_masks`."""
+    from unsupervised_detection_b200 import eval_dp
+    learner = AdversarialLearner()
+    learner.setup_inference(FLAGS, aug_test=False)
+    if not FLAGS.ckpt_file:
+        raise IOError("Checkpoint file not found")
+    learner.restore(FLAGS.ckpt_file)
+    rank, world, total, b = learner.rank, learner.world, int(learner.test_samples), int(FLAGS.batch_size)
+    names = learner.test_iterator.global_names
+    counters = eval_dp.category_counters(names)
+    local = []
+    for step in range(eval_dp.steps_for(total, b, world)):
+        inference = learner.inference(None)
+        for j, gidx in enumerate(eval_dp.owned_indices(step, b, rank, world, total)):
+            if gidx >= total or j >= inference['input_image'].shape[0]:
+                continue
+            gt_mask = inference['gt_masks'][j]
+            iou, out_mask = compute_IoU(gt_mask=gt_mask, pred_mask_f=inference['gen_masks'][j])
+            mae = compute_mae(gt_mask=gt_mask, pred_mask_f=out_mask)
+            category = names[gidx].split('/')[-2]
+            local.append((gidx, category, float(iou), float(mae)))
+            if FLAGS.generate_visualization:
+                import cv2
+                import scipy.io as sio
+                save_dir = os.path.join(FLAGS.test_save_dir, category)
+                os.makedirs(save_dir, exist_ok=True)
+                k = counters[gidx]
+                bgr = postprocess_image(inference['input_image'][j])
+                red = postprocess_mask(out_mask.astype(np.float32))
+                cv2.imwrite(os.path.join(save_dir, "frame_{:08d}.png".format(k)),
+                            cv2.resize(cv2.addWeighted(bgr, 0.5, red, 0.4, 0), (des_width, des_height)))
+                sio.savemat(os.path.join(save_dir, 'result_{}.mat'.format(k)),
+                            {'flow': inference['gt_flow'][j], 'img1': cv2.cvtColor(bgr, cv2.COLOR_BGR2RGB), 'pred_mask': out_mask,
+                             'gt_mask': inference['gt_masks'][j]})
+    scores = eval_dp.merge_scores(local)
+    if rank == 0:
+        eval_dp.report(scores, sequence_average=True)
+    return scores
+
+
 def main(argv):
     try:
         argv = FLAGS(argv)
     except gflags.Error:
         print('Usage: %s ARGS\n%s' % (sys.argv[0], FLAGS))
         sys.exit(1)
-    _test_masks()
+    from unsupervised_detection_b200 import eval_dp
+    _test_masks_dp() if eval_dp.is_distributed_launch() else _test_masks()
 
 
 if __name__ == "__main__":

@@ -65,13 +65,64 @@ def _test_masks():
     print("Success: Processed {} frames".format(i))
 
 
+def _test_masks_dp():
+    """Batch-sharded variant used under torchrun (BASELINE config 4): rank r evaluates frames r, r + world, ...; scores are merged
+    with one all_gather_object and rank 0 prints the report.  Same per-frame work and file names as `_test_masks`."""
+    from unsupervised_detection_b200 import eval_dp
+    learner = AdversarialLearner()
+    learner.setup_inference(FLAGS, aug_test=True)
+    if not FLAGS.ckpt_file:
+        raise IOError("Checkpoint file not found")
+    learner.restore(FLAGS.ckpt_file)
+    rank, world, total = learner.rank, learner.world, int(learner.test_samples)
+    names = learner.test_iterator.global_names
+    counters = eval_dp.category_counters(names)
+    test_crops = learner.test_crops
+    local = []
+    for step in range(eval_dp.steps_for(total, 1, world)):
+        inference = learner.inference(None)                # every rank steps its iterator every time: the shards stay aligned
+        gidx = eval_dp.owned_indices(step, 1, rank, world, total)[0]
+        if gidx >= total:
+            continue                                       # wrap-around duplicate of the endless iterator
+        outputs = inference['outs']
+        cropped_iou, cropped_mae = [], []
+        for crop in test_crops:
+            iou, out_mask = compute_IoU(gt_mask=outputs['gt_masks'][crop], pred_mask_f=outputs['pred_masks'][crop])
+            outputs['pred_masks'][crop] = out_mask
+            cropped_iou.append(iou)
+            cropped_mae.append(compute_mae(gt_mask=outputs['gt_masks'][crop], pred_mask_f=out_mask))
+        category = names[gidx].split('/')[-2]
+        local.append((gidx, category, float(np.mean(cropped_iou)), float(np.mean(cropped_mae))))
+        if FLAGS.generate_visualization:
+            import cv2
+            import scipy.io as sio
+            save_dir = os.path.join(FLAGS.test_save_dir, category)
+            os.makedirs(save_dir, exist_ok=True)
+            k = counters[gidx]                             # the frame's running index inside its category in list order
+            bgr = postprocess_image(outputs['img_1s'][test_crops[-1]])
+            red = postprocess_mask(outputs['pred_masks'][test_crops[-1]].astype(np.float32))
+            cv2.imwrite(os.path.join(save_dir, "frame_{:08d}.png".format(k)),
+                        cv2.resize(cv2.addWeighted(bgr, 0.5, red, 0.4, 0), (des_width, des_height)))
+            matlab_out = {}
+            for crop in test_crops:
+                matlab_out['img_1_{:03d}'.format(int(crop * 100))] = outputs['img_1s'][crop]
+                matlab_out['pred_mask_{:03d}'.format(int(crop * 100))] = outputs['pred_masks'][crop]
+                matlab_out['gt_mask_{:03d}'.format(int(crop * 100))] = outputs['gt_masks'][crop]
+            sio.savemat(os.path.join(save_dir, 'result_{}.mat'.format(k)), matlab_out)
+    scores = eval_dp.merge_scores(local)
+    if rank == 0:
+        eval_dp.report(scores)
+    return scores
+
+
 def main(argv):
     try:
         argv = FLAGS(argv)
     except gflags.Error:
         print('Usage: %s ARGS\n%s' % (sys.argv[0], FLAGS))
         sys.exit(1)
-    _test_masks()
+    from unsupervised_detection_b200 import eval_dp
+    _test_masks_dp() if eval_dp.is_distributed_launch() else _test_masks()
 
 
 if __name__ == "__main__":

@@ -134,6 +134,7 @@ class _Iter(object):
         """Data-parallel evaluation: global batch k is samples [k*B, (k+1)*B) of the ordered list (wrapping at the end, like
         dataset.repeat); rank r reads its contiguous slice of every global batch, so the ranks together see each global batch exactly
         once.  Ordered iterators only (training iterators are shuffled per rank instead)."""
+        self.global_names = [self._name_of(pr) for pr in self.pairs]      # first-frame file name of every list position
         if world <= 1:
             return self
         assert not self.shuffle and global_batch % world == 0
@@ -143,6 +144,9 @@ class _Iter(object):
         self.order = [(k * global_batch + rank * lb + j) % n for k in range(steps) for j in range(lb)]
         self.pos = 0
         return self
+
+    def _name_of(self, pair):
+        return pair[0] if isinstance(pair[0], str) else self.reader.filenames[int(pair[0])]
 
     def _next_index(self):
         if self.pos >= len(self.order):          # dataset.repeat(None) (+ reshuffle_each_iteration)

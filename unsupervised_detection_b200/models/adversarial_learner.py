@@ -59,6 +59,10 @@ class AdversarialLearner(object):
                 self.reader = rd.test_inputs(batch_size=cfg.batch_size, t_len=cfg.test_temporal_shift, with_fname=True,
                                              test_crop=(1.0 if self.aug_test else cfg.test_crop), partition=cfg.test_partition)
                 self.reader.val_samples = rd.val_samples
+                world = getattr(self, 'world', 1)
+                if world > 1:      # batch-sharded evaluation (eval_dp.py): rank r reads its slice of every global batch
+                    per_rank = 1 if self.aug_test else cfg.batch_size
+                    self.reader.shard(self.rank, world, per_rank * world)
             else:
                 self.val_reader = rd.test_inputs(batch_size=cfg.batch_size, t_len=cfg.test_temporal_shift, test_crop=cfg.test_crop,
                                                  partition='val').shard(self.rank, getattr(self, 'world', 1), cfg.batch_size)

@@ -69,7 +69,7 @@ def _test_masks_dp():
         raise IOError("Checkpoint file not found")
     learner.restore(FLAGS.ckpt_file)
     rank, world, total, b = learner.rank, learner.world, int(learner.test_samples), int(FLAGS.batch_size)
-    names = learner.test_iterator.global_names
+    names = eval_dp.global_names(learner)
     counters = eval_dp.category_counters(names)
     local = []
     for step in range(eval_dp.steps_for(total, b, world)):

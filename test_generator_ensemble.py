@@ -75,7 +75,7 @@ def _test_masks_dp():
         raise IOError("Checkpoint file not found")
     learner.restore(FLAGS.ckpt_file)
     rank, world, total = learner.rank, learner.world, int(learner.test_samples)
-    names = learner.test_iterator.global_names
+    names = eval_dp.global_names(learner)
     counters = eval_dp.category_counters(names)
     test_crops = learner.test_crops
     local = []

@@ -75,5 +75,14 @@ def report(scores, sequence_average=False, out=print):
     return tot_i / float(n), tot_m / float(n)
 
 
+def global_names(learner):
+    """First-frame file names of the whole ordered test list (set by the reader's shard())."""
+    names = getattr(learner.test_iterator, 'global_names', None)
+    if not names:
+        raise RuntimeError('batch-sharded evaluation needs an ordered dataset reader (DAVIS2016 / FBMS / SEGTRACK); the %s reader has no '
+                           'fixed sample list' % type(learner.test_iterator).__name__)
+    return names
+
+
 def is_distributed_launch():
     return int(os.environ.get('WORLD_SIZE', '1')) > 1

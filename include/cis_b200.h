@@ -84,7 +84,9 @@ typedef struct {
                           * a second (parallel) kernel launched by the same call sums them in the same fixed order + runs the epilogue */
 } CisConv;
 
-/* Weight gradient of the same convolution: dWp[co][(t,c)] += sum_rows g[row][co] * A[row][(t,c)]  (fp32, split-K atomics).
+/* Weight gradient of the same convolution: dWp[co][(t,c)] = sum_rows g[row][co] * A[row][(t,c)]  (fp32).  The reduction over rows
+ * is split over `splits` CTAs per column tile; every split writes its own private slice dwp[split][co][K_pad] with plain stores
+ * (no atomics, nothing to zero) and cis_unpack_wgrad sums the slices in a fixed order -- the weight gradient is bit-reproducible.
  * Replaces the conv2d backprop-filter ops TF1 emits for tf.gradients (loss_utils.py:17). */
 typedef struct {
   int32_t N, H, W, OH, OW, sh, sw, ntaps;
@@ -94,7 +96,7 @@ typedef struct {
   CisSrc src[CIS_MAX_SRC];
   const void* g;     /* bf16 gradient w.r.t. the pre-activation output on the (n,oh,ow) row grid */
   int32_t g_pitch, g_coff, g_chunks;
-  float* dwp;        /* fp32 [Cout][K_pad], must be zeroed by the caller before the first launch of a step */
+  float* dwp;        /* fp32 [splits][Cout][K_pad] private slices; every split must own >= 1 reduction block (ceil-division on the host) */
   int32_t Cout;      /* <= 128 */
   int32_t K_pad;
   int32_t splits;    /* split-K factor (grid.y) */
@@ -131,8 +133,10 @@ int cis_pack_weights(const float* w, const int32_t* kmap, int32_t K_pad, int32_t
  * same tap-major map (k = tap*cin8 + channel). */
 int cis_pack_weights_tiled(const float* w, const int32_t* kmap, int32_t cin8, int32_t ntaps, int32_t n_tiles, int32_t BN, int32_t cout,
                            int32_t sn, const int32_t* nmap, void* out, cis_stream_t stream);
-/* dw[kmap[k] + n] (=|+=) dwp[n][k] for kmap[k] >= 0, n < cout  (forward orientation, sn = 1). */
-int cis_unpack_wgrad(const float* dwp, const int32_t* kmap, int32_t K_pad, int32_t cout, float* dw, cis_stream_t stream);
+/* dw[kmap[k] + n] = sum_{s < nsplit} dwp[s][n][k] for kmap[k] >= 0, n < cout (fixed summation order; forward orientation, sn = 1);
+ * and, when colpart != NULL, the bias gradient db[c] = sum_{b < nblocks} colpart[b][c], c < nch (the partials of cis_colsum). */
+int cis_unpack_wgrad(const float* dwp, const int32_t* kmap, int32_t K_pad, int32_t cout, int32_t nsplit, float* dw, const float* colpart,
+                     int32_t nblocks, int32_t nch, float* db, cis_stream_t stream);
 /* tf.layers.batch_normalization in inference mode folded into the conv (convolution_utils.py:46-51):
  * w_eff = w * gamma/sqrt(1+1e-3); b_eff = bias*gamma/sqrt(1+1e-3) + beta. */
 int cis_bn_fold(const float* w, const float* bias, const float* gamma, const float* beta, int64_t nw, int32_t cout, float* w_eff,
@@ -148,8 +152,9 @@ int cis_dact_mul(void* g, int32_t g_pitch, int32_t g_coff, const void* y, int32_
 /* dst (=|+=) sum_{j<reps} src[(pix + j*npix_dst)]  : gradient accumulation and the 3-call fold of shared features */
 int cis_add_slice(void* dst, int32_t dst_pitch, int32_t dst_coff, const void* src, int32_t src_pitch, int32_t src_coff,
                   int64_t npix_dst, int32_t chunks, int32_t reps, int32_t accumulate, cis_stream_t stream);
-/* db[c] = sum_pix g[pix][c], c < nch (fp32, atomics; db must be zeroed) */
-int cis_colsum(const void* g, int32_t g_pitch, int32_t g_coff, int64_t npix, int32_t nch, float* db, cis_stream_t stream);
+/* part[b][c] = sum over the pixels of block b of g[pix][c], c < nch, b < nblocks (<= 592): per-block partial column sums, no atomics;
+ * cis_unpack_wgrad adds them up in block order (deterministic bias gradient). */
+int cis_colsum(const void* g, int32_t g_pitch, int32_t g_coff, int64_t npix, int32_t nch, float* part, int32_t nblocks, cis_stream_t stream);
 
 /* ---- resampling (App. A.5/A.6 semantics) ---- */
 /* tf.image.resize_images / resize_bilinear legacy (convolution_utils.py:88, nets.py:108) on a bf16 slice */

@@ -131,6 +131,27 @@ def test_learner_wires_the_davis_reader(root):
         L.load_training_data()
 
 
+def test_validation_iterator_keeps_its_own_file_list_after_the_training_iterator_is_built(root):
+    """load_training_data builds the validation iterator first and the training iterator (another partition) second on the SAME
+    reader: validation batches must still come from the validation list, frames and annotations alike."""
+    from unsupervised_detection_b200.common_flags import Config
+    from unsupervised_detection_b200.models.adversarial_learner import AdversarialLearner
+    L = object.__new__(AdversarialLearner)
+    L.rank = 0
+    L.config = Config(dataset='DAVIS2016', root_dir=root, batch_size=2, train_partition='train', test_partition='val', max_temporal_len=2,
+                      min_temporal_len=1)
+    L.load_training_data()
+    i1, i2, seg, names = L.val_reader.batch(6, pinned=False)
+    assert all('/cows/' in n for n in names), names
+    assert float(seg.max()) > 0.5                                           # the cows annotations, decoded with the cows frames
+    ref = D.Davis2016Reader(root, num_threads=1).test_inputs(batch_size=2, partition='val', t_len=L.config.test_temporal_shift,
+                                                             test_crop=L.config.test_crop)
+    r1, r2, rseg, rnames = ref.batch(6, pinned=False)
+    assert names == rnames and torch.equal(i1, r1) and torch.equal(i2, r2) and torch.equal(seg, rseg)
+    t1, _, _, tnames = L.reader.batch(4, pinned=False)
+    assert all('/bear/' in n or '/bus/' in n for n in tnames), tnames
+
+
 def test_host_c_preprocessing_is_bit_identical_to_the_numpy_restatement(root):
     """cis_host_resize_bilinear_legacy / cis_host_bgr8_to_rgb_resized (libcis_b200 host routines used by every reader) against the numpy
     gather version and, through it, the oracle's legacy resize."""
@@ -167,7 +188,7 @@ def test_prefetching_iterator_yields_the_same_stream(root):
     rd.prefetch = 2
     it = rd.image_inputs(batch_size=2, partition='train', train_crop=0.9)
     it.batch(2, pinned=False)
-    rd.filenames = ['/nonexistent.jpg'] * len(rd.filenames)           # every later sample fails to decode
+    it.view.filenames = ['/nonexistent.jpg'] * len(rd.filenames)      # every later sample of THIS iterator fails to decode
     with pytest.raises(IOError):
         for _ in range(6):
             it.batch(2, pinned=False)

@@ -1,0 +1,277 @@
+"""Parity of the CUDA path against the CPU oracle AT THE SIZES THAT ARE BENCHMARKED (BASELINE.json configs), not only at toy sizes.
+
+  config 1  generator forward, one 128x224 pair (test_generator.py:42-132 of the reference)
+  config 2  the whole train graph at 256x448, batch 4, PWC-Net at 384x640 (adversarial_learner.py:72-258): flow pyramid per level,
+            final flow, masks, the three recovered flows, all loss scalars, per-variable gradients of both steps
+  defaults  the reference's default geometry 192x384 (common_flags.py:6-8), batch 16
+  horizon   16 alternating steps = four full 1R:3G cycles (adversarial_learner.py:380-397) against the oracle's TF-Adam
+
+Stated tolerances (bf16 tensor-core operands and bf16 activations in HBM, fp32 accumulation; the oracle is fp32 end to end):
+  masks: <= 1e-3 mean-abs and identical threshold-0.1 segmentation outside a +-2e-3 band (north_star);
+  recovered flows: <= 5e-3 mean-abs; loss scalars: <= 2e-3 relative (recover) / 2e-3 absolute (generator, red_rate*);
+  PWC-Net: features <= 4e-3 mean-abs, flow pyramid <= 5e-3 * max(1, mean|flow|), final flow <= 1e-2 * max(1, mean|flow|);
+  gradients: see GRAD_TOL below (relative L2 per variable, norm-weighted).
+Every measured figure is also written to gpurun_out/parity_r02.json so BASELINE.md's parity column can be filled from a run."""
+import json
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import params as OP, losses as OL, pwcnet as OW, nets as ON
+from unsupervised_detection_b200.step_graph import CISGraph
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPORT = {}
+
+# relative-L2 bound of the whole gradient vector of a scope and the norm-weighted share of variables allowed above VAR_TOL
+GRAD_TOL = {'R': 0.05, 'G': 0.12}
+VAR_TOL = {'R': 0.10, 'G': 0.25}
+
+
+def _dump():
+    try:
+        d = os.path.join(ROOT, 'gpurun_out')
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, 'parity_r02.json'), 'w') as f:
+            json.dump(REPORT, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def smooth(B, H, W, C, amp, gen, div=16):
+    lo = torch.randn(B, C, max(H // div, 2), max(W // div, 2), generator=gen)
+    return (F.interpolate(lo, size=(H, W), mode='bicubic', align_corners=False) * amp).permute(0, 2, 3, 1).contiguous()
+
+
+def mask_checks(m, ref, key):
+    mad = float((m - ref).abs().mean())
+    band = (ref - 0.1).abs() > 2e-3
+    flips = int(((m > 0.1) != (ref > 0.1))[band].sum())
+    flips_all = int(((m > 0.1) != (ref > 0.1)).sum())
+    REPORT[key] = dict(mask_mean_abs=mad, mask_max_abs=float((m - ref).abs().max()), threshold_flips_outside_band=flips,
+                       threshold_flips_total=flips_all, pixels=int(ref.numel()), frac_mask_above_thr=float((ref > 0.1).float().mean()))
+    _dump()
+    assert mad <= 1e-3, mad
+    assert flips == 0, flips
+
+
+def test_config1_generator_forward_128x224():
+    """BASELINE config 1: mask-net forward on a single 128x224 frame pair with a precomputed flow."""
+    gen = torch.Generator().manual_seed(11)
+    B, H, W = 1, 128, 224
+    p = OP.make_params(seed=2, jitter=0.1, nets=('MaskNet', 'FlownetS'))
+    g = CISGraph(H, W, B, with_pwc=False, train=False)
+    g.load_params(p)
+    image = torch.rand(B, H, W, 3, generator=gen) - 0.5
+    flow = smooth(B, H, W, 2, 0.3, gen)
+    g.image.copy_(image)
+    g.flow.copy_(flow)
+    g.forward()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = ON.generator_net(image, OL.preprocess_flow_batch(flow), p)
+    mask_checks(g.mask.cpu(), ref, 'config1_128x224_b1')
+
+
+@pytest.fixture(scope='module')
+def cfg2():
+    """Config 2 graph (256x448, batch 4, PWC-Net at 384x640) run once on the GPU and once through the oracle."""
+    gen = torch.Generator().manual_seed(7)
+    B, H, W, ph, pw = 4, 256, 448, 384, 640
+    p = OP.make_params(seed=1, jitter=0.1)
+    g = CISGraph(H, W, B, with_pwc=True, train=True)
+    g.load_params(p)
+    img1 = smooth(B, ph, pw, 3, 0.25, gen).clamp(-0.5, 0.5)
+    img2 = torch.roll(img1, shifts=(2, 3), dims=(1, 2)) + 0.01 * torch.randn(B, ph, pw, 3, generator=gen)
+    g.img1.copy_(img1)
+    g.img2.copy_(img2)
+    g.forward()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        fo, pyr, c1, c2 = OW.predict_from_img_pairs(img1, img2, p, return_pyr=True)
+    # generator / recover / loss parity is stated on IDENTICAL (image, flow) inputs (north_star): the oracle consumes the very
+    # image and flow tensors the CUDA graph fed to its generator
+    image, flow = g.image.cpu().clone(), g.flow.cpu().clone()
+    pr = {k: v.clone().requires_grad_(not k.startswith('pwcnet')) for k, v in p.items()}
+    L = OL.adversarial_losses(image, flow, pr)
+    return dict(g=g, p=p, pr=pr, L=L, fo=fo, pyr=pyr, c1=c1, c2=c2, img1=img1, B=B, H=H, W=W)
+
+
+def test_config2_pwcnet_384x640(cfg2):
+    g, fo, pyr, c1, c2 = cfg2['g'], cfg2['fo'], cfg2['pyr'], cfg2['c1'], cfg2['c2']
+    rep = {}
+    for l in range(1, 7):
+        rep['c1_l%d' % l] = float((g.pwc.c1[l].float().cpu() - c1[l]).abs().mean())
+        rep['c2_l%d' % l] = float((g.pwc.c2[l].float().cpu() - c2[l]).abs().mean())
+    for i, l in enumerate(range(6, 1, -1)):
+        rep['flow_l%d' % l] = float((g.pwc.flows[l].cpu() - pyr[i]).abs().mean())
+        rep['flow_l%d_mag' % l] = float(pyr[i].abs().mean())
+    rep['final_flow'] = float((g.flow_full.cpu() - fo).abs().mean())
+    rep['final_flow_mag'] = float(fo.abs().mean())
+    im, fl = OL.resize_inputs(cfg2['img1'], fo, cfg2['H'], cfg2['W'])
+    rep['resized_image_max_abs'] = float((g.image.cpu() - im).abs().max())
+    rep['resized_flow_mean_abs'] = float((g.flow.cpu() - fl).abs().mean())
+    REPORT['config2_pwcnet_384x640_b4'] = rep
+    _dump()
+    for l in range(1, 7):
+        assert rep['c1_l%d' % l] <= 4e-3 and rep['c2_l%d' % l] <= 4e-3, (l, rep)
+    for l in range(6, 1, -1):
+        assert rep['flow_l%d' % l] <= 5e-3 * max(1.0, rep['flow_l%d_mag' % l]), (l, rep)
+    assert rep['final_flow'] <= 1e-2 * max(1.0, rep['final_flow_mag']), rep
+    assert rep['resized_image_max_abs'] <= 1e-6
+
+
+def test_config2_masks_256x448(cfg2):
+    mask_checks(cfg2['g'].mask.cpu(), cfg2['L']['masks'].detach(), 'config2_256x448_b4')
+
+
+def test_config2_recovered_flows_and_all_loss_scalars(cfg2):
+    g, L, B = cfg2['g'], cfg2['L'], cfg2['B']
+    rep = {}
+    for j, k in enumerate(('pred', 'pred_c', 'pred_i')):
+        rep[k + '_mean_abs'] = float((g.pred[j * B:(j + 1) * B].cpu() - L[k].detach()).abs().mean())
+    ls = g.losses(full=True)
+    ref = dict(generator=float(L['generator']), recover=float(L['recover']), red_rate=float(L['red_rate']),
+               red_rate_compl=float(L['red_rate_compl']), reconstruction_loss=float(L['rec'][0]),
+               reconstruction_compl_loss=float(L['rec_c'][0]), denominator_red_rate=float(L['den'][0]),
+               denominator_red_rate_compl=float(L['den_c'][0]))
+    for k, v in ref.items():
+        rep['loss_' + k] = dict(cuda=ls[k], oracle=v)
+    REPORT['config2_losses'] = rep
+    _dump()
+    for k in ('pred', 'pred_c', 'pred_i'):
+        assert rep[k + '_mean_abs'] <= 5e-3, rep
+    for k in ('recover', 'reconstruction_loss', 'reconstruction_compl_loss', 'denominator_red_rate', 'denominator_red_rate_compl'):
+        assert abs(ls[k] - ref[k]) <= 2e-3 * max(1.0, abs(ref[k])), (k, ls[k], ref[k])
+    for k in ('generator', 'red_rate', 'red_rate_compl'):
+        assert abs(ls[k] - ref[k]) <= 2e-3, (k, ls[k], ref[k])
+
+
+@pytest.mark.parametrize('mode,key,scope', [('R', 'recover', 'FlownetS/'), ('G', 'generator', 'MaskNet/')])
+def test_config2_gradients_per_variable(cfg2, mode, key, scope):
+    """Relative L2 error of the gradient of every variable of the scope that the step trains; asserted on the whole vector and on
+    the norm-weighted share of variables above VAR_TOL (tiny-norm variables are dominated by bf16 rounding of the activations)."""
+    g, pr, L = cfg2['g'], cfg2['pr'], cfg2['L']
+    names = [n for n in pr if n.startswith(scope)]
+    grads = torch.autograd.grad(L[key], [pr[n] for n in names], retain_graph=True)
+    g.bwd[mode].run()
+    torch.cuda.synchronize()
+    store = g.rec_store if mode == 'R' else g.gen_store
+    per, tot_ref, tot_err, bad_w = {}, 0.0, 0.0, 0.0
+    for n, gr in zip(names, grads):
+        a = store.view(n, 'grad').cpu().reshape(-1)
+        b = gr.reshape(-1)
+        e, r = float((a - b).norm()), float(b.norm())
+        per[n] = dict(rel_l2=e / max(r, 1e-30), ref_norm=r)
+        tot_ref += r * r
+        tot_err += e * e
+    whole = (tot_err / tot_ref) ** 0.5
+    for n, v in per.items():
+        if v['rel_l2'] > VAR_TOL[mode]:
+            bad_w += v['ref_norm'] ** 2 / tot_ref
+    fa = torch.cat([store.view(n, 'grad').cpu().reshape(-1) for n in names])
+    fb = torch.cat([x.reshape(-1) for x in grads])
+    cos = float(torch.dot(fa, fb) / (fa.norm() * fb.norm()))
+    REPORT['config2_grad_' + mode] = dict(whole_rel_l2=whole, cosine=cos, norm_weight_above_var_tol=bad_w, per_variable=per)
+    _dump()
+    assert whole <= GRAD_TOL[mode], (whole, cos)
+    assert bad_w <= 0.02, bad_w
+
+
+def test_defaults_192x384_batch16():
+    """common_flags.py:6-8 of the reference: img_height 192, img_width 384, batch_size 16 (generator + 3x recover + losses)."""
+    gen = torch.Generator().manual_seed(3)
+    B, H, W = 16, 192, 384
+    p = OP.make_params(seed=4, jitter=0.1, nets=('MaskNet', 'FlownetS'))
+    g = CISGraph(H, W, B, with_pwc=False, train=False)
+    g.load_params(p)
+    image = torch.rand(B, H, W, 3, generator=gen) - 0.5
+    flow = smooth(B, H, W, 2, 0.3, gen)
+    g.image.copy_(image)
+    g.flow.copy_(flow)
+    g.forward()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        L = OL.adversarial_losses(image, flow, p)
+    mask_checks(g.mask.cpu(), L['masks'], 'defaults_192x384_b16')
+    ls = g.losses()
+    REPORT['defaults_192x384_b16'].update(recover=dict(cuda=ls['recover'], oracle=float(L['recover'])),
+                                          generator=dict(cuda=ls['generator'], oracle=float(L['generator'])))
+    _dump()
+    for j, k in enumerate(('pred', 'pred_c', 'pred_i')):
+        assert float((g.pred[j * B:(j + 1) * B].cpu() - L[k]).abs().mean()) <= 5e-3, k
+    assert abs(ls['recover'] - float(L['recover'])) <= 2e-3 * max(1.0, abs(float(L['recover'])))
+    assert abs(ls['generator'] - float(L['generator'])) <= 2e-3
+
+
+def test_sixteen_steps_track_the_oracle():
+    """Four full 1R:3G cycles (adversarial_learner.py:380-397), CUDA-graph replay from step 3 on: the parameters stay within a few
+    Adam step sizes of the oracle's fp32 trajectory and the losses keep agreeing."""
+    gen = torch.Generator().manual_seed(0)
+    B, H, W = 2, 64, 96
+    p = OP.make_params(seed=1, jitter=0.1, nets=('MaskNet', 'FlownetS'))
+    image = torch.rand(B, H, W, 3, generator=gen) - 0.5
+    flow = smooth(B, H, W, 2, 0.3, gen)
+    g = CISGraph(H, W, B, with_pwc=False)
+    g.load_params(p)
+    g.image.copy_(image)
+    g.flow.copy_(flow)
+    pt = {k: v.clone() for k, v in p.items()}
+    opt = OL.TFAdam()
+    drift = []
+    for step in range(1, 17):
+        rec = OL.is_recover_step(step)
+        scope = 'FlownetS/' if rec else 'MaskNet/'
+        names = [n for n in pt if n.startswith(scope)]
+        for n in names:
+            pt[n].requires_grad_(True)
+        Ls = OL.adversarial_losses(image, flow, pt)
+        grads = torch.autograd.grad(Ls['recover'] if rec else Ls['generator'], [pt[n] for n in names])
+        for n in names:
+            pt[n].requires_grad_(False)
+        clipped, _ = OL.clip_or_noise(list(grads), 0.2, can_change=not rec)
+        opt.apply(pt, names, clipped)
+        g.train_step('R' if rec else 'G', use_graph=(step >= 3))
+        torch.cuda.synchronize()
+        ls = g.losses()
+        ex = g.export_params()
+        worst = max(float((ex[n].cpu() - pt[n]).abs().max()) for n in names)
+        mean = float(torch.cat([(ex[n].cpu() - pt[n]).abs().reshape(-1) for n in names]).mean())
+        drift.append(dict(step=step, kind='R' if rec else 'G', worst=worst, mean=mean, recover=(ls['recover'], float(Ls['recover'])),
+                          generator=(ls['generator'], float(Ls['generator']))))
+        REPORT['sixteen_steps_64x96_b2'] = drift
+        _dump()
+        assert abs(ls['recover'] - float(Ls['recover'])) <= 3e-3 * max(1.0, abs(float(Ls['recover']))), drift[-1]
+        assert abs(ls['generator'] - float(Ls['generator'])) <= 3e-3, drift[-1]
+        assert worst <= 2.5e-4 * step, drift[-1]        # |Adam update| <= ~lr = 1e-4 per step and element
+        assert mean <= 1e-5 * (step + 1), drift[-1]
+    assert int(g.step_state.item()) == 16
+
+
+def test_two_identical_steps_give_bit_identical_weights():
+    """The weight gradient is reduced over fixed-order private split-K slices and the bias gradient over per-block partials (no
+    atomics), so training is reproducible run to run: two graphs fed the same inputs end with bit-identical parameters."""
+    gen = torch.Generator().manual_seed(5)
+    B, H, W = 2, 128, 192
+    p = OP.make_params(seed=6, jitter=0.1, nets=('MaskNet', 'FlownetS'))
+    image = torch.rand(B, H, W, 3, generator=gen) - 0.5
+    flow = smooth(B, H, W, 2, 0.3, gen)
+    outs = []
+    for _ in range(2):
+        g = CISGraph(H, W, B, with_pwc=False)
+        g.load_params(p)
+        g.image.copy_(image)
+        g.flow.copy_(flow)
+        for mode in 'RGGG':
+            g.train_step(mode)
+        torch.cuda.synchronize()
+        outs.append({k: v.cpu() for k, v in g.export_params().items()})
+        grads = (g.gen_store.grad.cpu().clone(), g.rec_store.grad.cpu().clone())
+        outs[-1]['__gen_grad'], outs[-1]['__rec_grad'] = grads
+    diff = [k for k in outs[0] if not torch.equal(outs[0][k], outs[1][k])]
+    REPORT['determinism_128x192_b2'] = dict(differing_tensors=diff)
+    _dump()
+    assert not diff, diff[:5]

@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libcis_b200.so')
+# CIS_LIB_NAME: developer switch to the trace build (make -C csrc trace); the default is the product library
+LIB_PATH = os.path.join(_HERE, os.environ.get('CIS_LIB_NAME', 'libcis_b200.so'))
 
 MAX_TAPS, MAX_SRC = 49, 4
 ACT_NONE, ACT_ELU, ACT_LEAKY = 0, 1, 2
@@ -52,12 +53,12 @@ _PROTOS = {
     'cis_conv_wgrad': [C.POINTER(CisWgrad)],
     'cis_pack_weights': [_p, _p, _i32, _i32, _i32, _i32, _p, _p],
     'cis_pack_weights_tiled': [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
-    'cis_unpack_wgrad': [_p, _p, _i32, _i32, _p],
+    'cis_unpack_wgrad': [_p, _p, _i32, _i32, _i32, _p, _p, _i32, _i32, _p],
     'cis_bn_fold': [_p, _p, _p, _p, _i64, _i32, _p, _p],
     'cis_bn_chain': [_p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p],
     'cis_dact_mul': [_p, _i32, _i32, _p, _i32, _i32, _p, _i32, _i32, _i64, _i32, _i32, _f32],
     'cis_add_slice': [_p, _i32, _i32, _p, _i32, _i32, _i64, _i32, _i32, _i32],
-    'cis_colsum': [_p, _i32, _i32, _i64, _i32, _p],
+    'cis_colsum': [_p, _i32, _i32, _i64, _i32, _p, _i32],
     'cis_resize_bilinear_bf16': [_p, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _i32, _i32, _i32],
     'cis_resize_bilinear_bf16_bwd': [_p, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _i32, _i32, _i32, _i32],
     'cis_resize_bilinear_f32': [_p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _f32],

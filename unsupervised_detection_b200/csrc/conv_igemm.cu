@@ -17,24 +17,30 @@
 #include <stdlib.h>
 #include <string.h>
 
-// cp.async (LDGSTS) data is published to the MMA warp through the mbarrier that cp.async.mbarrier.arrive.noinc signals; the
-// tensor core then reads it through the async proxy.  A consumer-side fence.proxy.async per pipeline step costs > 1000 clk of
-// serial latency in the single issuing warp (ncu r01c), so it is compiled out by default -- the same protocol CUTLASS uses for
-// its cp.async + UMMA/GMMA mainloops; every launch configuration is covered by the bit-sensitive parity tests.
-#ifdef CIS_PARANOID_PROXY_FENCE
-#define CIS_CONSUMER_PROXY_FENCE() fence_proxy_async()
-#else
-#define CIS_CONSUMER_PROXY_FENCE() ((void)0)
-#endif
+// cp.async (LDGSTS) writes shared memory through the generic proxy while tcgen05.mma reads it through the async proxy.  Every
+// cp.async producer therefore publishes a stage itself: commit_group, wait_group<lag> (its own copies of the stage landed),
+// fence.proxy.async, then a plain mbarrier.arrive -- the MMA warp needs no fence.  The lag keeps (stages - 1) groups in flight.
 
 namespace cis {
+
+// Developer-only pipeline trace (make trace -> libcis_b200_trace.so, tools/trace_conv.py): CTA (0,0,0) records SM-clock stamps of its
+// MMA-issue loop so per-step wait / issue time can be read back.  Compiled out of the product library.
+#ifdef CIS_TRACE
+__device__ unsigned long long* g_trace = nullptr;
+__device__ int g_trace_cap = 0;
+#define CIS_TRACE_AT(slot)                                                                                         \
+  do {                                                                                                             \
+    if (g_trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (slot) < g_trace_cap) g_trace[(slot)] = clock64(); \
+  } while (0)
+#else
+#define CIS_TRACE_AT(slot) ((void)0)
+#endif
 
 static constexpr int kBM = 128;       // GEMM rows per CTA
 static constexpr int kBK = 64;        // bf16 K elements per stage (128-byte swizzled rows)
 static constexpr int kAStage = kBM * 128;
 static constexpr int kProducerThreads = 128;
 static constexpr int kThreads = 160;  // 4 producer/epilogue warps + 1 MMA warp
-static constexpr int kLag = 2;        // cp.async groups kept in flight per producer thread
 
 struct SrcS {
   const __nv_bfloat16* ptr;
@@ -349,6 +355,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (tid == 0) CIS_TRACE_AT(0);
 
   if (warp < 4) {
     // ------------------------------------------------------------------ producers
@@ -409,12 +416,21 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
       const uint32_t b_dst = b_base + s * Cfg::kBStage + rl * 128 + sw_off;
 #pragma unroll
       for (int i = 0; i < BN / 16; ++i) cp_async16(b_dst + i * 16 * 128, wrow + (size_t)i * 16 * p.K_pad + (kb_lo + kb) * kBK, 16u);
-      cp_async_mbar_arrive_noinc(bar_full + 8 * s);
+      cp_async_commit();
+      if (kb >= S - 1) {             // publish block kb-(S-1): this thread's copies of it have landed
+        cp_async_wait<S - 1>();
+        fence_proxy_async();
+        mbar_arrive(bar_full + 8 * ((kb - (S - 1)) % S));
+      }
     }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int kb = nkb > S - 1 ? nkb - (S - 1) : 0; kb < nkb; ++kb) mbar_arrive(bar_full + 8 * (kb % S));
 
     // ------------------------------------------------------------------ epilogue
     mbar_wait(bar_accum, 0);
     tc_fence_after();
+    if (tid == 0) CIS_TRACE_AT(2);
     const int row = warp * 32 + lane;
     const int g = blockIdx.x * kBM + row;
     const bool valid = g < M;
@@ -452,21 +468,23 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
       const int s = kb % S;
       const uint32_t ph = (uint32_t)((kb / S) & 1);
       mbar_wait(bar_full + 8 * s, ph);
-      CIS_CONSUMER_PROXY_FENCE();
       tc_fence_after();
       if (elect_one()) {
+        CIS_TRACE_AT(8 + 2 * kb);
         const uint32_t alo = desc_lo(a_base + s * kAStage, 16), blo = desc_lo(b_base + s * Cfg::kBStage, 16);
         const uint32_t dhi = desc_hi(1024);
 #pragma unroll
         for (int k = 0; k < kBK / 16; ++k) umma_bf16_lh(tmem, alo + 2 * k, dhi, blo + 2 * k, dhi, idesc, (uint32_t)((kb | k) != 0));
         umma_commit(bar_empty + 8 * s);
         if (kb == nkb - 1) umma_commit(bar_accum);
+        CIS_TRACE_AT(9 + 2 * kb);
       }
       __syncwarp();
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) CIS_TRACE_AT(3);
   if (warp == 4) tmem_dealloc<Cfg::kTmemCols>(tmem);
 }
 
@@ -572,6 +590,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   if (cl > 1) cluster_sync_all();   // the peer's barriers must be initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (tid == 0) CIS_TRACE_AT(0);
 
   if (warp < 4) {
     // ------------------------------------------------------------------ producers
@@ -627,7 +646,21 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
                        ok ? 16u : 0u);
           }
         }
-        cp_async_mbar_arrive_noinc(bar_hfull + 8 * hs);
+        cp_async_commit();
+        if (NHS == 1) {
+          cp_async_wait<0>();
+          fence_proxy_async();
+          mbar_arrive(bar_hfull);
+        } else if (cc >= 1) {        // two stages: publish chunk cc-1 while chunk cc is in flight
+          cp_async_wait<1>();
+          fence_proxy_async();
+          mbar_arrive(bar_hfull + 8 * ((cc - 1) % NHS));
+        }
+      }
+      if (NHS > 1) {
+        cp_async_wait<0>();
+        fence_proxy_async();
+        mbar_arrive(bar_hfull + 8 * ((nchunks - 1) % NHS));
       }
     }
     if (tid == 64) {
@@ -653,6 +686,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     // ------------------------------------------------------------------ epilogue
     mbar_wait(bar_accum, 0);
     tc_fence_after();
+    if (tid == 0) CIS_TRACE_AT(2);
     const int r = warp * 32 + lane;
     const int cbase = ny * BN;
     const int tile_id = blockIdx.x * gridDim.y + ny;
@@ -700,14 +734,14 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
       const int rem = m_chunks - (cc_lo + cc) * 8;
       const int nk16 = rem >= 8 ? 4 : (rem + 1) / 2;
       mbar_wait(bar_hfull + 8 * hs, (uint32_t)((cc / NHS) & 1));
-      CIS_CONSUMER_PROXY_FENCE();
+      if (cc == 0 && lane == 0) CIS_TRACE_AT(1);
       const uint32_t hsrc = h_base + hs * halo_stage_bytes;
       for (int t = 0; t < p.ntaps; ++t, ++it) {
         const int bs = it % BS;
         mbar_wait(bar_bfull + 8 * bs, (uint32_t)((it / BS) & 1));
-        CIS_CONSUMER_PROXY_FENCE();
         tc_fence_after();
         if (elect_one()) {
+          CIS_TRACE_AT(8 + 2 * it);
           const uint32_t blo = desc_lo(b_base + bs * kBStage, 16);
           uint32_t alo = desc_lo(hsrc + (uint32_t)((s_dh[t] * Wh + s_dw[t]) * 128), 16);
           const uint32_t acc0 = (uint32_t)(it != 0);
@@ -725,6 +759,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
           if (cl > 1) umma_commit_mc(bar_bempty + 8 * bs, (uint16_t)3); else umma_commit(bar_bempty + 8 * bs);
           if (t == p.ntaps - 1) umma_commit(bar_hempty + 8 * hs);
           if (cc == nchunks - 1 && t == p.ntaps - 1) umma_commit(bar_accum);
+          CIS_TRACE_AT(9 + 2 * it);
         }
         __syncwarp();
       }
@@ -732,6 +767,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) CIS_TRACE_AT(3);
   if (cl > 1) cluster_sync_all();   // the peer may still be arriving on this CTA's bempty barriers
   if (warp == 4) tmem_dealloc_dyn(tmem, ncols);
 }
@@ -1015,7 +1051,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
   const int kb0 = blockIdx.y * per;
   const int kb1 = min(kb0 + per, nkb_total);
   const int nkb = kb1 - kb0;
-  if (nkb <= 0) return;  // uniform per CTA: safe before any barrier / TMEM allocation
+  if (nkb <= 0) return;  // never taken: cis_conv_wgrad rejects split counts that leave a split without work (its slice would be garbage)
 
   if (warp == 4) {
     if (lane == 0) {
@@ -1152,8 +1188,16 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
           cp_async16(dst + (2 + u) * kWTile, bptr[u] + off, ok ? 16u : 0u);
         }
       }
-      cp_async_mbar_arrive_noinc(bar_full + 8 * s);
+      cp_async_commit();
+      if (it >= S - 1) {
+        cp_async_wait<S - 1>();
+        fence_proxy_async();
+        mbar_arrive(bar_full + 8 * ((it - (S - 1)) % S));
+      }
     }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    for (int it = nkb > S - 1 ? nkb - (S - 1) : 0; it < nkb; ++it) mbar_arrive(bar_full + 8 * (it % S));
 
     }
     // epilogue: row = output channel co, columns = packed K columns of this n-tile
@@ -1166,10 +1210,12 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
     for (int c0 = 0; c0 < 128; c0 += 16) {
       float v[16];
       tmem_ld16(t_row + c0, v);
-      if (co < p.Cout) {
-        float* o = p.dwp + (size_t)co * p.K_pad + kcol0 + c0;
-        for (int e = 0; e < 16; ++e)
-          if (kcol0 + c0 + e < p.K_pad) atomicAdd(o + e, v[e]);
+      if (co < p.Cout && kcol0 + c0 < p.K_pad) {     // K_pad % 64 == 0: a 16-column group is inside or outside as a whole
+        float4* o = reinterpret_cast<float4*>(p.dwp + ((size_t)blockIdx.y * p.Cout + co) * p.K_pad + kcol0 + c0);   // this split's private slice
+        o[0] = make_float4(v[0], v[1], v[2], v[3]);
+        o[1] = make_float4(v[4], v[5], v[6], v[7]);
+        o[2] = make_float4(v[8], v[9], v[10], v[11]);
+        o[3] = make_float4(v[12], v[13], v[14], v[15]);
       }
     }
   } else {
@@ -1178,7 +1224,6 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
       const int s = it % S;
       const uint32_t ph = (uint32_t)((it / S) & 1);
       mbar_wait(bar_full + 8 * s, ph);
-      CIS_CONSUMER_PROXY_FENCE();
       tc_fence_after();
       if (elect_one()) {
         const uint32_t st = tile_base + s * kWStage;
@@ -1302,7 +1347,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_halo_kernel(const __grid_
         if (!tv) continue;
         for (int e = 0; e < 16; ++e) {
           const int co = half * 64 + c0 + e;
-          if (co < p.Cout) atomicAdd(p.dwp + (size_t)co * p.K_pad + kcol, v[e]);   // lanes = consecutive kcol: coalesced
+          if (co < p.Cout) p.dwp[((size_t)blockIdx.y * p.Cout + co) * p.K_pad + kcol] = v[e];   // private slice; lanes = consecutive kcol: coalesced
         }
       }
     }
@@ -1446,6 +1491,14 @@ static bool encode_src_map(CUtensorMap* m, const CisSrc& s, int N, int H, int W,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+#ifdef CIS_TRACE
+extern "C" int cis_trace_set(unsigned long long* buf, int cap) {
+  cudaError_t e = cudaMemcpyToSymbol(cis::g_trace, &buf, sizeof(buf));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(cis::g_trace_cap, &cap, sizeof(cap));
+  return e == cudaSuccess ? CIS_OK : cis_set_cuda_error(e, "cis_trace_set");
+}
+#endif
+
 static int g_persist_mode = -1;   // -1: environment / default (1 = thin layers)
 extern "C" int cis_set_persist_mode(int mode) {
   g_persist_mode = mode;
@@ -1465,9 +1518,14 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   int BS = (226 * 1024 - fixed) / (BN * 128);     // as deep a weight ring as fits ...
   if (BS > kHaloMaxBStages) BS = kHaloMaxBStages;
   if (BS > steps) BS = steps;                     // ... but never deeper than the number of pipeline steps
-  // prefer several co-resident CTAs per SM (their load / MMA / epilogue phases overlap) over a very deep ring
+  // prefer several co-resident CTAs per SM (their load / MMA / epilogue phases overlap) over a very deep ring -- unless the whole
+  // grid fits one CTA per SM anyway (low-resolution layers): then the ring depth is what hides the L2 latency of the weight stream
+  static const int deep_env = getenv("CIS_DEEP_RING") ? atoi(getenv("CIS_DEEP_RING")) : 0;
+  const int dd0 = d->dil;
+  const long ncta_all = (long)(((d->OW + dd0 - 1) / dd0 + 7) / 8) * (((d->OH + dd0 - 1) / dd0 + 16 * d->MT - 1) / (16 * d->MT)) * dd0 * dd0 * d->N *
+                        d->n_tiles * (d->splits > 1 ? d->splits : 1);
   const int budgets[5] = {36 * 1024, 44 * 1024, 56 * 1024, 74 * 1024, 112 * 1024};
-  for (int b = 0; b < 5; ++b) {
+  for (int b = 0; b < 5 && !(deep_env && ncta_all <= deep_env); ++b) {
     const int fit = (budgets[b] - fixed) / (BN * 128);
     if (fit >= 3 || (fit >= steps && fit >= 1)) { if (BS > fit) BS = fit; break; }
   }
@@ -1664,6 +1722,13 @@ extern "C" int cis_conv_wgrad(const CisWgrad* d, cis_stream_t stream) {
   if (!d || d->ntaps < 1 || d->ntaps > CIS_MAX_TAPS || d->nsrc < 1 || d->nsrc > CIS_MAX_SRC || d->K_pad % 64 != 0 || d->Cout < 1 ||
       d->Cout > 128 || d->splits < 1 || !d->g || !d->dwp)
     return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_wgrad: bad descriptor");
+  {
+    // every split must own at least one reduction block: its private slice of dwp is only defined if the CTA runs
+    const long M = (long)d->N * d->OH * d->OW;
+    const long nkb_total = d->tma ? (long)d->N * ((d->OW + 7) / 8) * ((d->OH + 7) / 8) : (M + 63) / 64;
+    const long per = (nkb_total + d->splits - 1) / d->splits;
+    if ((long)(d->splits - 1) * per >= nkb_total) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_wgrad: a split would own no reduction block");
+  }
   if (d->tma == 2) return launch_wgrad_halo(d, (cudaStream_t)stream);
   static bool attr_set = false;
   if (!attr_set) {

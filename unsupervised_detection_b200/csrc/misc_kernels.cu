@@ -68,15 +68,34 @@ __global__ void pack_weights_tiled_kernel(const float* __restrict__ w, const int
   }
   out[i] = __float2bfloat16(v);
 }
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const int* __restrict__ kmap, int K_pad, int cout,
-                                    float* __restrict__ dw) {
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const int* __restrict__ kmap, int K_pad, int cout, int nsplit,
+                                    float* __restrict__ dw, const float* __restrict__ colpart, int nblocks, int nch, float* __restrict__ db) {
   pdl_launch_dependents();
   pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)cout * K_pad) return;
-  const int n = (int)(i / K_pad), k = (int)(i % K_pad);
-  const int km = kmap[k];
-  if (km >= 0) dw[(size_t)km + n] = dwp[i];
+  const size_t nw = (size_t)cout * K_pad;
+  if (i < nw) {
+    const int n = (int)(i / K_pad), k = (int)(i % K_pad);
+    const int km = kmap[k];
+    if (km < 0) return;
+    // fixed-order sum of the private split-K slices; 4 independent loads in flight per thread
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float* q = dwp + i;
+    int s = 0;
+    for (; s + 4 <= nsplit; s += 4) {
+      a0 += __ldcg(q + (size_t)s * nw);
+      a1 += __ldcg(q + (size_t)(s + 1) * nw);
+      a2 += __ldcg(q + (size_t)(s + 2) * nw);
+      a3 += __ldcg(q + (size_t)(s + 3) * nw);
+    }
+    for (; s < nsplit; ++s) a0 += __ldcg(q + (size_t)s * nw);
+    dw[(size_t)km + n] = (a0 + a1) + (a2 + a3);
+  } else if (colpart != nullptr && i - nw < (size_t)nch) {
+    const int c = (int)(i - nw);
+    float a = 0.f;
+    for (int b = 0; b < nblocks; ++b) a += __ldcg(colpart + (size_t)b * nch + c);
+    db[c] = a;
+  }
 }
 #define BN_RSQRT 0.99950037468777323f /* 1/sqrt(1 + 1e-3): tf.layers.batch_normalization defaults, convolution_utils.py:50 */
 __global__ void bn_fold_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
@@ -159,8 +178,8 @@ __global__ void add_slice_kernel(bf16* dst, int dp, int dc, const bf16* __restri
   }
   *d = pack8(a);
 }
-// db[c] += sum_pix g[pix][c].  blockDim = 256 = P pixel lanes x chunks (chunks <= 32).
-__global__ void colsum_kernel(const bf16* __restrict__ g, int gp, int gc, size_t npix, int nch, int chunks, float* __restrict__ db) {
+// part[blockIdx.x][c] = sum over this block's pixels of g[pix][c].  blockDim = 256 = P pixel lanes x chunks (chunks <= 32).
+__global__ void colsum_kernel(const bf16* __restrict__ g, int gp, int gc, size_t npix, int nch, int chunks, float* __restrict__ part) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float sm[];  // [P][chunks*8]
@@ -180,7 +199,7 @@ __global__ void colsum_kernel(const bf16* __restrict__ g, int gp, int gc, size_t
   for (int c = threadIdx.x; c < nch; c += blockDim.x) {
     float s = 0.f;
     for (int q = 0; q < P; ++q) s += sm[q * chunks * 8 + c];
-    atomicAdd(db + c, s);
+    part[(size_t)blockIdx.x * nch + c] = s;
   }
 }
 
@@ -825,8 +844,11 @@ int cis_pack_weights_tiled(const float* w, const int32_t* kmap, int32_t cin8, in
   CIS_LAUNCH(pack_weights_tiled_kernel, nblk(total), 256, 0, ST, w, kmap, cin8, ntaps, n_tiles, BN, cout, sn, nmap, (mbf)out);
   return cis_check_launch("pack_weights_tiled");
 }
-int cis_unpack_wgrad(const float* dwp, const int32_t* kmap, int32_t K_pad, int32_t cout, float* dw, cis_stream_t stream) {
-  CIS_LAUNCH(unpack_wgrad_kernel, nblk((size_t)cout * K_pad), 256, 0, ST, dwp, kmap, K_pad, cout, dw);
+int cis_unpack_wgrad(const float* dwp, const int32_t* kmap, int32_t K_pad, int32_t cout, int32_t nsplit, float* dw, const float* colpart,
+                     int32_t nblocks, int32_t nch, float* db, cis_stream_t stream) {
+  if (nsplit < 1 || (colpart && (nblocks < 1 || !db))) return cis_set_error(CIS_ERR_BAD_ARG, "cis_unpack_wgrad: bad split / column-sum arguments");
+  CIS_LAUNCH(unpack_wgrad_kernel, nblk((size_t)cout * K_pad + (colpart ? nch : 0)), 256, 0, ST, dwp, kmap, K_pad, cout, nsplit, dw, colpart, nblocks,
+             nch, db);
   return cis_check_launch("unpack_wgrad");
 }
 int cis_bn_fold(const float* w, const float* bias, const float* gamma, const float* beta, int64_t nw, int32_t cout, float* w_eff, float* b_eff,
@@ -850,14 +872,12 @@ int cis_add_slice(void* dst, int32_t dp, int32_t dc, const void* src, int32_t sp
   CIS_LAUNCH(add_slice_kernel, nblk((size_t)npix * chunks), 256, 0, ST, (mbf)dst, dp, dc, (cbf)src, sp, sc, (size_t)npix, chunks, reps, accumulate);
   return cis_check_launch("add_slice");
 }
-int cis_colsum(const void* g, int32_t gp, int32_t gc, int64_t npix, int32_t nch, float* db, cis_stream_t stream) {
+int cis_colsum(const void* g, int32_t gp, int32_t gc, int64_t npix, int32_t nch, float* part, int32_t nblocks, cis_stream_t stream) {
   const int chunks = (nch + 7) / 8;
   if (chunks > 32) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_colsum: more than 256 channels");
+  if (nblocks < 1 || nblocks > 592) return cis_set_error(CIS_ERR_BAD_ARG, "cis_colsum: nblocks must be in [1, 592]");
   const int P = 256 / chunks;
-  unsigned blocks = (unsigned)((npix + P * 16 - 1) / (P * 16));
-  if (blocks > 592) blocks = 592;
-  if (blocks < 1) blocks = 1;
-  CIS_LAUNCH(colsum_kernel, blocks, 256, P * chunks * 8 * sizeof(float), ST, (cbf)g, gp, gc, (size_t)npix, nch, chunks, db);
+  CIS_LAUNCH(colsum_kernel, (unsigned)nblocks, 256, P * chunks * 8 * sizeof(float), ST, (cbf)g, gp, gc, (size_t)npix, nch, chunks, part);
   return cis_check_launch("colsum");
 }
 int cis_resize_bilinear_bf16(const void* src, int32_t sp, int32_t sc, int32_t N, int32_t H, int32_t W, void* dst, int32_t dp, int32_t dc, int32_t OH,

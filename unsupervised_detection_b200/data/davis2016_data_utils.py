@@ -7,6 +7,7 @@ the head of a sequence / backward from its tail), same preprocessing (x/255-0.5,
 flips applied to both frames, random / central crop resized back).  JPEG decoding and augmentation stay on the CPU.
 """
 import collections
+import copy
 import os
 import queue
 import random
@@ -119,7 +120,11 @@ class _Iter(object):
     decoded ahead."""
 
     def __init__(self, reader, pairs, train, shuffle, num_threads, prefetch=0):
-        self.reader, self.pairs, self.train, self.shuffle = reader, list(pairs), train, shuffle
+        # Snapshot of the reader as it is NOW (file lists, temporal shift, crops): a later image_inputs()/test_inputs() call on the
+        # same reader rebinds those attributes for ITS iterator and must not change what this one decodes -- the reference gets the
+        # same isolation from tf.gather(self.filenames) being captured as a graph constant when each dataset map is traced.
+        self.reader, self.view = reader, copy.copy(reader)
+        self.pairs, self.train, self.shuffle = list(pairs), train, shuffle
         self.pool = ThreadPoolExecutor(max_workers=max(1, num_threads))
         self.rng = random.Random(reader.rng.getrandbits(64))     # private stream: iterators of one reader do not interleave draws
         self.pos = 0
@@ -146,7 +151,7 @@ class _Iter(object):
         return self
 
     def _name_of(self, pair):
-        return pair[0] if isinstance(pair[0], str) else self.reader.filenames[int(pair[0])]
+        return pair[0] if isinstance(pair[0], str) else self.view.filenames[int(pair[0])]
 
     def _next_index(self):
         if self.pos >= len(self.order):          # dataset.repeat(None) (+ reshuffle_each_iteration)
@@ -160,7 +165,7 @@ class _Iter(object):
     def _submit(self, n):
         """Draw the next n samples (indices + augmentation seeds, in stream order) and hand them to the thread pool."""
         idx = [self._next_index() for _ in range(n)]
-        fn = self.reader._train_sample if self.train else self.reader._test_sample
+        fn = self.view._train_sample if self.train else self.view._test_sample
         seeds = [self.rng.getrandbits(32) for _ in idx]
         return [self.pool.submit(fn, self.pairs[i], sd) for i, sd in zip(idx, seeds)]
 

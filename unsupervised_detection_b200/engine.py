@@ -221,6 +221,7 @@ WGRAD_TMA = True
 MATERIALIZE_MISALIGNED_CONCAT = True
 
 
+WGRAD_CTAS_PER_SM = int(os.environ.get('CIS_WGRAD_CTAS_PER_SM', '4'))   # split-K target: CTAs per SM of one weight-gradient launch
 WGRAD_HALO = os.environ.get('CIS_WGRAD_HALO', '0') == '1'   # experimental halo-resident swapped wgrad kernel (CisWgrad.tma = 2), off
 
 
@@ -503,18 +504,15 @@ class ConvLayer(object):
                     plan.add('cis_pack_weights', self.w_src_ptr(), pk['kmap'].data_ptr(), pk['K_pad'], pk['rows'], len(self.in_chanmap),
                              self.cout, pk['nmap'].data_ptr(), pk['w'].data_ptr())
 
-    def plan_zero_grads(self, bp):
-        if hasattr(self, 'dwp'):
-            bp.zero(self.dwp)
-            if self.bn:
-                bp.zero(self.db_eff)
-
-    def plan_finalize(self, bp):
-        """packed fp32 weight gradient -> HWIO slot of the flat gradient buffer (+ BN chain rule for the generator)."""
-        if not hasattr(self, 'dwp'):
+    def plan_finalize(self, bp, mode):
+        """Fixed-order sum of the private split-K slices of the packed fp32 weight gradient -> HWIO slot of the flat gradient
+        buffer, same for the per-block bias-gradient partials (+ BN chain rule for the generator).  No atomics, nothing to zero."""
+        if not hasattr(self, 'dwp') or mode not in getattr(self, 'wg_splits', {}):
             return
         s = self.store
-        bp.add('cis_unpack_wgrad', self.dwp.data_ptr(), self.wg_kmap.data_ptr(), self.wg_K_pad, self.cout, s.ptr(self.wkey, 'grad'))
+        bp.add('cis_unpack_wgrad', self.dwp.data_ptr(), self.wg_kmap.data_ptr(), self.wg_K_pad, self.cout, self.wg_splits[mode],
+               s.ptr(self.wkey, 'grad'), self.colpart.data_ptr(), self.col_blocks[mode], self.cout,
+               (self.db_eff.data_ptr() if self.bn else s.ptr(self.bkey, 'grad')))
         if self.bn:
             bp.add('cis_bn_chain', s.ptr(self.wkey), s.ptr(self.bkey), s.ptr(self.name + '/gamma'), s.ptr(self.wkey, 'grad'),
                    self.db_eff.data_ptr(), self.k * self.k * self.cin * self.cout, self.cout, s.ptr(self.bkey, 'grad'),
@@ -707,24 +705,35 @@ class Builder(object):
                     layer.wg_kmap = torch.from_numpy(km).to(self.device)
                 else:
                     layer.wg_K_pad, layer.wg_kmap = layer.K_pad, layer.fwd_kmap
-                layer.dwp = torch.zeros(layer.cout, layer.wg_K_pad, dtype=torch.float32, device=self.device)
+                layer.dwp, layer.wg_splits, layer.col_blocks = None, {}, {}
             w = CisWgrad()
             w.N, w.H, w.W, w.OH, w.OW, w.sh, w.sw = nb, H, W, out.H, out.W, layer.stride, layer.stride
             _fill_taps(w, taps)
             _fill_srcs(w, srcs)
             w.g, w.g_pitch, w.g_coff, w.g_chunks = G.ptr, G.pitch, G.c_off, G.C8 // 8
-            w.dwp, w.Cout, w.K_pad = layer.dwp.data_ptr(), layer.cout, layer.wg_K_pad
+            w.Cout, w.K_pad = layer.cout, layer.wg_K_pad
             w.tma = 2 if layer.wg_halo else (1 if layer.wg_tma else 0)
             nkb = (nb * (-(-out.H // 8)) * (-(-out.W // 8))) if w.tma else -(-npix // 64)
             ntile = -(-layer.wg_K_pad // 128)
             if w.tma == 2:      # grid.x = 64-channel chunks of the input, grid.z = 64-channel halves of Cout
                 ntile = (-(-len(layer.in_chanmap) // 64)) * (2 if layer.cout > 64 else 1)
-            w.splits = max(1, min(nkb // 8 if nkb >= 8 else 1, max(1, (4 * NUM_SMS) // ntile)))
+            splits = max(1, min(nkb // 8 if nkb >= 8 else 1, max(1, (WGRAD_CTAS_PER_SM * NUM_SMS) // ntile)))
+            splits = -(-nkb // (-(-nkb // splits)))        # every split owns >= 1 reduction block (its slice is written, not accumulated)
+            w.splits = splits
+            layer.wg_splits[mode] = splits
+            if layer.dwp is None or layer.dwp.numel() < splits * layer.cout * layer.wg_K_pad:
+                assert not getattr(layer, 'wgrad_modes', None), 'slice buffer must be sized by the first (largest) mode'
+                layer.dwp = torch.empty(max(layer.wg_splits.values()) * layer.cout * layer.wg_K_pad, dtype=torch.float32, device=self.device)
+            w.dwp = layer.dwp.data_ptr()
             bp.keep.append(w)
             bp.add('cis_conv_wgrad', C.byref(w), flops=2.0 * npix * layer.k * layer.k * layer.cin * layer.cout, lane=1)
             layer.wgrad_modes = getattr(layer, 'wgrad_modes', set()) | {mode}
-            bp.add('cis_colsum', G.ptr, G.pitch, G.c_off, npix, layer.cout,
-                   (layer.db_eff.data_ptr() if layer.bn else layer.store.ptr(layer.bkey, 'grad')), lane=1)
+            chunks = -(-layer.cout // 8)
+            ppb = (256 // chunks) * 16                      # pixels per colsum block (cis_colsum: P lanes x 16 pixels each)
+            layer.col_blocks[mode] = max(1, min(592, -(-npix // ppb)))
+            if getattr(layer, 'colpart', None) is None:
+                layer.colpart = torch.empty(592 * layer.cout, dtype=torch.float32, device=self.device)
+            bp.add('cis_colsum', G.ptr, G.pitch, G.c_off, npix, layer.cout, layer.colpart.data_ptr(), layer.col_blocks[mode], lane=1)
         need = [s for s in srcs if mode in s.dep]
         if not need:
             return

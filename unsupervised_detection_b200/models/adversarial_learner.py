@@ -207,9 +207,13 @@ class AdversarialLearner(object):
         st = getattr(self, '_staged', None)
         if st is not None and st[0] is img1:
             # this batch was prefetched on the copy stream while the previous step was computing: device-to-device hand-over
-            torch.cuda.current_stream().wait_event(st[3])
+            cur = torch.cuda.current_stream()
+            cur.wait_event(st[3])
             g.img1.copy_(st[1], non_blocking=True)
             g.img2.copy_(st[2], non_blocking=True)
+            # the staging slot may be overwritten by a later prefetch only after these two reads have executed
+            self._slot_read[st[4]] = torch.cuda.Event()
+            self._slot_read[st[4]].record(cur)
             self._staged = None
             return
         g.img1.copy_(img1, non_blocking=True)
@@ -222,14 +226,17 @@ class AdversarialLearner(object):
             self._copy_stream = torch.cuda.Stream()
             self._stage_bufs = [(torch.empty_like(g.img1), torch.empty_like(g.img2)) for _ in range(2)]
             self._stage_idx = 0
+            self._slot_read = [None, None]     # per slot: event recorded after the main stream's last read of it (feed)
         self._stage_idx ^= 1
         d1, d2 = self._stage_bufs[self._stage_idx]
+        if self._slot_read[self._stage_idx] is not None:
+            self._copy_stream.wait_event(self._slot_read[self._stage_idx])   # write-after-read: the host can run steps ahead of the GPU
         with torch.cuda.stream(self._copy_stream):
             d1.copy_(batch[0], non_blocking=True)
             d2.copy_(batch[1], non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(self._copy_stream)
-        self._staged = (batch[0], d1, d2, ev)
+        self._staged = (batch[0], d1, d2, ev, self._stage_idx)
 
     def step(self, batch=None, fetch_losses=None, use_graph=True, next_batch=None, summarize=False):
         """One iteration of the training loop body (adversarial_learner.py:380-409): picks train_recover_op or
@@ -250,11 +257,15 @@ class AdversarialLearner(object):
         if next_batch is not None:
             self.prefetch(next_batch)          # overlaps this step's kernels; consumed by the next step() call
         res = {"global_step": self.global_step, "train_op": mode}
-        if fetch_losses if fetch_losses is not None else (step % cfg.summary_freq == 0):
-            L = self.graph.losses()                                            # device -> host read
+        fetch = fetch_losses if fetch_losses is not None else (step % cfg.summary_freq == 0)
+        if fetch or summarize:
+            # device -> host read; under data parallelism every rank holds its share of the global-batch losses (each is already
+            # divided by the GLOBAL batch), so one SUM all-reduce of the four scalars gives every rank the true values -- all ranks
+            # take this branch on the same steps
+            L = self.graph.losses(full=summarize, reduce=self._allreduce())
             res["loss_recover"], res["loss_generator"] = L['recover'], L['generator']
         if summarize:
-            self._write_step_summary(self.global_step, mode, other_grads)      # add_summary(results["summary"], gs), :403
+            self._write_step_summary(self.global_step, mode, other_grads, L)   # add_summary(results["summary"], gs), :403
         return res
 
     # ------------------------------------------------------------------------------------------------ summaries
@@ -286,7 +297,9 @@ class AdversarialLearner(object):
         torch.cuda.synchronize()
         return self._net_gradients(other)
 
-    def _write_step_summary(self, gs, mode, other_grads):
+    def _write_step_summary(self, gs, mode, other_grads, losses=None):
+        """`losses`: the (already all-reduced) dict of CISGraph.losses(full=True); its four first-sample diagnostics
+        (reconstruction_loss, ..., adversarial_learner.py:201-204) are those of rank 0's first sample."""
         w = getattr(self, 'summary_writer', None)
         if w is None:
             return
@@ -294,13 +307,13 @@ class AdversarialLearner(object):
         from .utils.general_utils import disambiguate_forw_back
         g = self.graph
         B = g.B
-        for k, v in g.losses(full=True).items():                               # :262-263
+        for k, v in (losses if losses is not None else g.losses(full=True)).items():   # :262-263
             w.add_scalar(k, v)
         flow = g.flow.cpu().numpy()
         mask = g.mask.cpu().numpy()
         pred = g.pred.cpu().numpy()
         rec = pred[:B] * mask + flow * (1.0 - mask)                            # self.pred_flow, :251
-        rec_c = pred[B:2 * B] * (1.0 - mask) + flow * mask                     # self.pred_flow_compl, :252
+        rec_c = pred[:B] * (1.0 - mask) + flow * mask                          # self.pred_flow_compl, :252 (the PRIMARY prediction, as the reference)
         w.add_image("input_image", g.image[:1].cpu().numpy())                  # :265-268
         w.add_image("next_image", g.img2[:1].cpu().numpy())
         flow_img = flow_to_image_pm(flow)

@@ -120,13 +120,12 @@ class CISGraph(object):
                 body = bld.build_backward(mode, [self.rec.flow1])
                 store = self.rec_store if mode == 'R' else self.gen_store
                 layers = self.rec.all_layers() if mode == 'R' else self.gen.all_layers()
+                # nothing to zero: every real entry of the flat gradient buffer is overwritten by cis_unpack_wgrad / cis_bn_chain each
+                # step, and its padding slots are never written (they stay at their initial 0, also through the all-reduce)
                 pre = Plan('zero_' + mode)
-                pre.zero(store.grad)
-                for L in layers:
-                    L.plan_zero_grads(pre)
                 fin = Plan('fin_' + mode)
                 for L in layers:
-                    L.plan_finalize(fin)
+                    L.plan_finalize(fin, mode)
                 full = Plan('bwd_' + mode)
                 for pl in (pre, head, body):
                     full.extend(pl)
@@ -232,10 +231,16 @@ class CISGraph(object):
         self.graphs[mode] = (g1, g2)
         return self.graphs[mode]
 
-    def losses(self, full=False):
+    def losses(self, full=False, reduce=None):
         """The `losses` dict of adversarial_learner.py:196-204 (device -> host read).  full=True adds the four first-sample
-        diagnostics (:201-204) taken from the per-sample Charbonnier sums {rec, rec_c, prior, den, den_c}."""
-        s = self.scalars.tolist()
+        diagnostics (:201-204) taken from the per-sample Charbonnier sums {rec, rec_c, prior, den, den_c}.  `reduce`: the SUM
+        all-reduce of a data-parallel job -- the local scalars are this rank's share of the global-batch losses."""
+        if reduce is not None:
+            t = self.scalars[:4].clone()
+            reduce(t)
+            s = t.tolist()
+        else:
+            s = self.scalars.tolist()
         out = dict(generator=s[0], recover=s[1], red_rate=s[2], red_rate_compl=s[3])
         if full:
             r = self.sums[0].tolist()

@@ -152,7 +152,7 @@ def test_step_schedule_and_global_step():
         def train_step(self, mode, allreduce=None, use_graph=False):
             self.modes.append(mode)
 
-        def losses(self):
+        def losses(self, full=False, reduce=None):
             return dict(generator=0.0, recover=0.0)
     L = AdversarialLearner()
     L.config = Config(summary_freq=4)

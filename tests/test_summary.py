@@ -127,7 +127,7 @@ class _Graph:
         self.rec_store = _Store(['FlownetS/aconv1/weights', 'FlownetS/aconv1/biases'], 1)
         self.gen_store = _Store(['MaskNet/conv1/kernel', 'MaskNet/conv1/gamma', 'MaskNet/conv13_upsample/beta'], 2)
 
-    def losses(self, full=False):
+    def losses(self, full=False, reduce=None):
         assert full
         return dict(generator=1.0, recover=2.0, red_rate=0.5, red_rate_compl=0.5, reconstruction_loss=3.0,
                     reconstruction_compl_loss=4.0, denominator_red_rate=80.0, denominator_red_rate_compl=81.0)

@@ -9,6 +9,9 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box via gpurun)')
+    # the torch-CPU oracle oversubscribes badly on many-core hosts (128 threads: tens of seconds per step instead of ~1 s)
+    import torch
+    torch.set_num_threads(max(1, min(os.cpu_count() or 1, 16)))
 
 
 def pytest_collection_modifyitems(config, items):

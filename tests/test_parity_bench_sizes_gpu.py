@@ -22,7 +22,7 @@ import torch.nn.functional as F
 from oracle import params as OP, losses as OL, pwcnet as OW, nets as ON
 from unsupervised_detection_b200.step_graph import CISGraph
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(1200)]     # the CPU oracle at 256x448x4 + PWC-Net 384x640 takes ~1 min
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REPORT = {}
 

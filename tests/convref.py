@@ -85,12 +85,11 @@ def run_conv_case(N, H, W, cins, cout, k, stride=1, dil=1, act=ACT_NONE, alpha=0
     bp = B.build_backward('R', [out])
     pre = E.Plan('pre')
     layer.plan_pack(pre, dgrad=True)
-    layer.plan_zero_grads(pre)
     store.grad.zero_()
     pre.run()
     bp.run()
     fin = E.Plan('fin')
-    layer.plan_finalize(fin)
+    layer.plan_finalize(fin, 'R')
     fin.run()
     torch.cuda.synchronize()
     grads = torch.autograd.grad(y, [xcat, wd, bd] + ([gam, bet] if bn else []), gy)

@@ -47,11 +47,11 @@ def test_recover_net_matches_oracle(params):
 
 def test_predict_from_img_pairs_matches_oracle(params):
     g = torch.Generator().manual_seed(2)
-    a = torch.rand(1, 64, 64, 3, generator=g) - 0.5
+    a = torch.rand(1, 128, 128, 3, generator=g) - 0.5      # level 6 must be at least 2x2 (dense_image_warp, core_warp.py:188)
     b = torch.roll(a, shifts=(1, 2), dims=(1, 2))
     got = ModelPWCNet.predict_from_img_pairs(a.cuda(), b.cuda(), params=params).cpu()
     ref = OW.predict_from_img_pairs(a, b, params)
-    assert got.shape == ref.shape == (1, 64, 64, 2)
+    assert got.shape == ref.shape == (1, 128, 128, 2)
     assert float((got - ref).abs().mean()) <= 0.02 * float(ref.abs().mean()) + 0.05
 
 

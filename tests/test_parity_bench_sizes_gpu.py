@@ -8,7 +8,8 @@
 
 Stated tolerances (bf16 tensor-core operands and bf16 activations in HBM, fp32 accumulation; the oracle is fp32 end to end):
   masks: <= 1e-3 mean-abs and identical threshold-0.1 segmentation outside a +-2e-3 band (north_star);
-  recovered flows: <= 5e-3 mean-abs; loss scalars: <= 2e-3 relative (recover) / 2e-3 absolute (generator, red_rate*);
+  recovered flows: <= 5e-3 mean-abs; loss scalars: <= 2e-3 relative (recover, Charbonnier sums) / 2e-3 absolute per reduction-rate
+  term 1 - rec/den (so 4e-3 for the generator loss, the sum of two);
   PWC-Net: features <= 4e-3 mean-abs, flow pyramid <= 5e-3 * max(1, mean|flow|), final flow <= 1e-2 * max(1, mean|flow|);
   gradients: see GRAD_TOL below (relative L2 per variable, norm-weighted).
 Every measured figure is also written to gpurun_out/parity_r02.json so BASELINE.md's parity column can be filled from a run."""
@@ -27,8 +28,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REPORT = {}
 
 # relative-L2 bound of the whole gradient vector of a scope and the norm-weighted share of variables allowed above VAR_TOL
-GRAD_TOL = {'R': 0.05, 'G': 0.12}
-VAR_TOL = {'R': 0.10, 'G': 0.25}
+GRAD_TOL = {'R': 0.02, 'G': 0.12}     # measured r02 at 256x448x4: 0.0046 / 0.086 (cosine 1.000 / 0.9992)
+VAR_TOL = {'R': 0.05, 'G': 0.25}      # measured worst variable: 0.014 / 0.133
 
 
 def _dump():
@@ -121,7 +122,7 @@ def test_config2_pwcnet_384x640(cfg2):
     for l in range(6, 1, -1):
         assert rep['flow_l%d' % l] <= 5e-3 * max(1.0, rep['flow_l%d_mag' % l]), (l, rep)
     assert rep['final_flow'] <= 1e-2 * max(1.0, rep['final_flow_mag']), rep
-    assert rep['resized_image_max_abs'] <= 1e-6
+    assert rep['resized_image_max_abs'] <= 2e-5      # fp32 legacy-bilinear 384x640 -> 256x448 (non-integer x scale): a few ulps of the lerp weight
 
 
 def test_config2_masks_256x448(cfg2):
@@ -146,8 +147,8 @@ def test_config2_recovered_flows_and_all_loss_scalars(cfg2):
         assert rep[k + '_mean_abs'] <= 5e-3, rep
     for k in ('recover', 'reconstruction_loss', 'reconstruction_compl_loss', 'denominator_red_rate', 'denominator_red_rate_compl'):
         assert abs(ls[k] - ref[k]) <= 2e-3 * max(1.0, abs(ref[k])), (k, ls[k], ref[k])
-    for k in ('generator', 'red_rate', 'red_rate_compl'):
-        assert abs(ls[k] - ref[k]) <= 2e-3, (k, ls[k], ref[k])
+    for k, tol in (('generator', 4e-3), ('red_rate', 2e-3), ('red_rate_compl', 2e-3)):   # 1 - rec/den: 2e-3 per reduction-rate term
+        assert abs(ls[k] - ref[k]) <= tol, (k, ls[k], ref[k])
 
 
 @pytest.mark.parametrize('mode,key,scope', [('R', 'recover', 'FlownetS/'), ('G', 'generator', 'MaskNet/')])
@@ -204,7 +205,7 @@ def test_defaults_192x384_batch16():
     for j, k in enumerate(('pred', 'pred_c', 'pred_i')):
         assert float((g.pred[j * B:(j + 1) * B].cpu() - L[k]).abs().mean()) <= 5e-3, k
     assert abs(ls['recover'] - float(L['recover'])) <= 2e-3 * max(1.0, abs(float(L['recover'])))
-    assert abs(ls['generator'] - float(L['generator'])) <= 2e-3
+    assert abs(ls['generator'] - float(L['generator'])) <= 4e-3           # two reduction-rate terms, 2e-3 each
 
 
 def test_sixteen_steps_track_the_oracle():

@@ -504,25 +504,26 @@ struct HaloMaps {
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_constant__ CisConv p, const int halo_stage_bytes, const int BS, const int NHS,
-                                                        const __grid_constant__ HaloMaps maps, const int use_tma, const int cl) {
-  // cl = 2 (experimental, launched as 2-CTA clusters along blockIdx.x): the two CTAs work on neighbouring pixel tiles of the same
-  // n-tile, so they consume the same sequence of weight tiles; each fetches HALF of every tile and multicasts it to both, and a
-  // stage is refilled only after BOTH have committed their MMAs on it (bempty counts cl arrivals).  Halves the L2->SM weight
-  // stream that bounds the MT = 1 wide layers.  cl = 1: unchanged behaviour.
+                                                        const __grid_constant__ HaloMaps maps, const int use_tma, const int G) {
+  // One weight pipeline stage = the tiles of G consecutive taps of one 64-channel chunk (contiguous in the pre-tiled operand, ONE
+  // bulk copy): the single MMA-issuing thread then pays the per-stage cost (mbarrier wait, tcgen05 fence, election, commits: several
+  // hundred clocks of dependent single-thread latency, measured with the CIS_TRACE build) once per 4*MT*G MMAs instead of once per
+  // 4*MT -- that cost, not the tensor pipe, bounded every launch of round 1.
   constexpr int kBStage = BN * 128;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * 2 + 2 * kHaloMaxBStages + 1];
   __shared__ uint32_t tmem_slot;
-  __shared__ int s_dh[CIS_MAX_TAPS], s_dw[CIS_MAX_TAPS];
+  __shared__ uint32_t s_aoff[CIS_MAX_TAPS];   // tap origin inside the halo, in descriptor start-field units (16 B)
   __shared__ SrcS s_src[CIS_MAX_SRC];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int MT = p.MT, d = p.dil;
   const int Wh = 8 + p.ex, Hh = 16 * MT + p.ey, HP = Wh * Hh;
+  const uint32_t stage_bytes = (uint32_t)G * kBStage;
   const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t h_base = tile_base;                                // 2 halo stages
-  const uint32_t b_base = tile_base + NHS * halo_stage_bytes;       // BS weight stages
-  int* pixtab = reinterpret_cast<int*>(smem_raw + (b_base + BS * kBStage - smem_u32(smem_raw)));
+  const uint32_t h_base = tile_base;                                // NHS halo stages
+  const uint32_t b_base = tile_base + NHS * halo_stage_bytes;       // BS weight stages of G tap tiles each
+  int* pixtab = reinterpret_cast<int*>(smem_raw + (b_base + BS * stage_bytes - smem_u32(smem_raw)));
   const uint32_t bar_hfull = smem_u32(&bars[0]), bar_hempty = smem_u32(&bars[2]);
   const uint32_t bar_bfull = smem_u32(&bars[4]), bar_bempty = smem_u32(&bars[4 + kHaloMaxBStages]);
   const uint32_t bar_accum = smem_u32(&bars[4 + 2 * kHaloMaxBStages]);
@@ -550,10 +551,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   pdl_launch_dependents();
   const uint32_t ncols = (MT * BN <= 32) ? 32u : (MT * BN <= 64) ? 64u : (MT * BN <= 128) ? 128u : (MT * BN <= 256) ? 256u : 512u;
 
-  if (tid < p.ntaps) {
-    s_dh[tid] = p.dh[tid];
-    s_dw[tid] = p.dw[tid];
-  }
+  if (tid < p.ntaps) s_aoff[tid] = (uint32_t)((p.dh[tid] * Wh + p.dw[tid]) * 8);   // * 128 B / 16
   if (tid < p.nsrc) {
     s_src[tid].ptr = reinterpret_cast<const __nv_bfloat16*>(p.src[tid].ptr);
     s_src[tid].pitch = p.src[tid].pitch;
@@ -561,7 +559,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     s_src[tid].chunks = p.src[tid].chunks;
     s_src[tid].n_mod = p.src[tid].n_mod;
   }
-  for (int q = tid; q < HP; q += kThreads) {
+  for (int q = tid; q < (use_tma ? 0 : HP); q += kThreads) {
     const int hy = q / Wh, hx = q - hy * Wh;
     const int gy = ty * 16 * MT + hy + p.hoy, gx = tx * 8 + hx + p.hox;
     const int y = pa + d * gy, x = pb + d * gx;
@@ -575,7 +573,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
       }
       for (int s = 0; s < BS; ++s) {
         mbar_init(bar_bfull + 8 * s, 1);   // one expect_tx arrival; the bulk copy completes the transaction bytes
-        mbar_init(bar_bempty + 8 * s, cl); // one commit per CTA that reads the stage
+        mbar_init(bar_bempty + 8 * s, 1);  // one commit by the MMA thread
       }
       mbar_init(bar_accum, 1);
       fence_mbar_init();
@@ -587,7 +585,6 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   if (tid < BN) s_bias[tid] = p.bias ? p.bias[ny * BN + tid] : 0.f;
   tc_fence_before();
   __syncthreads();
-  if (cl > 1) cluster_sync_all();   // the peer's barriers must be initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   if (tid == 0) CIS_TRACE_AT(0);
@@ -664,19 +661,20 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
       }
     }
     if (tid == 64) {
-      // weights: pre-swizzled [n-tile][chunk][tap] tiles of BN x 128 B (cis_pack_weights_tiled) -> ONE bulk copy per pipeline step
+      // weights: pre-swizzled [n-tile][chunk][tap] tiles of BN x 128 B (cis_pack_weights_tiled); the tiles of the G taps of a stage
+      // are adjacent in that layout -> ONE bulk copy per pipeline stage
       const uint8_t* wt = reinterpret_cast<const uint8_t*>(p.wpack) + ((size_t)ny * nchunks_all + cc_lo) * p.ntaps * kBStage;
-      int it = 0;
+      int bs = 0;
+      uint32_t bph = 1;           // parity to wait for on the empty barrier: the first pass over the ring finds every stage free
       for (int cc = 0; cc < nchunks; ++cc) {
-        for (int t = 0; t < p.ntaps; ++t, ++it) {
-          const int bs = it % BS;
-          mbar_wait(bar_bempty + 8 * bs, (uint32_t)(((it / BS) & 1) ^ 1));
-          mbar_expect_tx(bar_bfull + 8 * bs, kBStage);
-          if (cl > 1) {
-            const uint32_t hb = kBStage / 2, ho = cluster_ctarank() * hb;
-            bulk_g2s_mc(b_base + bs * kBStage + ho, wt + (size_t)it * kBStage + ho, hb, bar_bfull + 8 * bs, (uint16_t)3);
-          } else {
-            bulk_g2s(b_base + bs * kBStage, wt + (size_t)it * kBStage, kBStage, bar_bfull + 8 * bs);
+        for (int t0 = 0; t0 < p.ntaps; t0 += G) {
+          const uint32_t bytes = (uint32_t)min(G, p.ntaps - t0) * kBStage;
+          mbar_wait(bar_bempty + 8 * bs, bph);
+          mbar_expect_tx(bar_bfull + 8 * bs, bytes);
+          bulk_g2s(b_base + bs * stage_bytes, wt + (size_t)(cc * p.ntaps + t0) * kBStage, bytes, bar_bfull + 8 * bs);
+          if (++bs == BS) {
+            bs = 0;
+            bph ^= 1u;
           }
         }
       }
@@ -728,47 +726,58 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
     const uint32_t ahi = desc_hi((uint32_t)(Wh * 128)), bhi = desc_hi(1024);
     const uint32_t a_mstep = (uint32_t)(16 * Wh * 128) >> 4;   // descriptor start-field step between stacked M tiles
-    int it = 0;
+    int bs = 0, hs = 0, it = 0;
+    uint32_t bph = 0, hph = 0;
     for (int cc = 0; cc < nchunks; ++cc) {
-      const int hs = cc % NHS;
       const int rem = m_chunks - (cc_lo + cc) * 8;
       const int nk16 = rem >= 8 ? 4 : (rem + 1) / 2;
-      mbar_wait(bar_hfull + 8 * hs, (uint32_t)((cc / NHS) & 1));
+      mbar_wait(bar_hfull + 8 * hs, hph);
       if (cc == 0 && lane == 0) CIS_TRACE_AT(1);
-      const uint32_t hsrc = h_base + hs * halo_stage_bytes;
-      for (int t = 0; t < p.ntaps; ++t, ++it) {
-        const int bs = it % BS;
-        mbar_wait(bar_bfull + 8 * bs, (uint32_t)((it / BS) & 1));
+      const uint32_t hlo = desc_lo(h_base + hs * halo_stage_bytes, 16);
+      for (int t0 = 0; t0 < p.ntaps; t0 += G, ++it) {
+        const int gt = min(G, p.ntaps - t0);
+        mbar_wait(bar_bfull + 8 * bs, bph);
         tc_fence_after();
         if (elect_one()) {
           CIS_TRACE_AT(8 + 2 * it);
-          const uint32_t blo = desc_lo(b_base + bs * kBStage, 16);
-          uint32_t alo = desc_lo(hsrc + (uint32_t)((s_dh[t] * Wh + s_dw[t]) * 128), 16);
-          const uint32_t acc0 = (uint32_t)(it != 0);
-          for (int m = 0; m < MT; ++m, alo += a_mstep) {
-            const uint32_t td = tmem + m * BN;
-            if (nk16 == 4) {
-              umma_bf16_lh(td, alo, ahi, blo, bhi, idesc, acc0);
-              umma_bf16_lh(td, alo + 2, ahi, blo + 2, bhi, idesc, 1u);
-              umma_bf16_lh(td, alo + 4, ahi, blo + 4, bhi, idesc, 1u);
-              umma_bf16_lh(td, alo + 6, ahi, blo + 6, bhi, idesc, 1u);
-            } else {
-              for (int k = 0; k < nk16; ++k) umma_bf16_lh(td, alo + 2 * k, ahi, blo + 2 * k, bhi, idesc, k ? 1u : acc0);
+          uint32_t blo = desc_lo(b_base + bs * stage_bytes, 16);
+          for (int tt = 0; tt < gt; ++tt, blo += kBStage >> 4) {
+            uint32_t alo = hlo + s_aoff[t0 + tt];
+            const uint32_t acc0 = (uint32_t)((cc | t0 | tt) != 0);
+            for (int m = 0; m < MT; ++m, alo += a_mstep) {
+              const uint32_t td = tmem + m * BN;
+              if (nk16 == 4) {
+                umma_bf16_lh(td, alo, ahi, blo, bhi, idesc, acc0);
+                umma_bf16_lh(td, alo + 2, ahi, blo + 2, bhi, idesc, 1u);
+                umma_bf16_lh(td, alo + 4, ahi, blo + 4, bhi, idesc, 1u);
+                umma_bf16_lh(td, alo + 6, ahi, blo + 6, bhi, idesc, 1u);
+              } else {
+                for (int k = 0; k < nk16; ++k) umma_bf16_lh(td, alo + 2 * k, ahi, blo + 2 * k, bhi, idesc, k ? 1u : acc0);
+              }
             }
           }
-          if (cl > 1) umma_commit_mc(bar_bempty + 8 * bs, (uint16_t)3); else umma_commit(bar_bempty + 8 * bs);
-          if (t == p.ntaps - 1) umma_commit(bar_hempty + 8 * hs);
-          if (cc == nchunks - 1 && t == p.ntaps - 1) umma_commit(bar_accum);
+          umma_commit(bar_bempty + 8 * bs);
+          if (t0 + G >= p.ntaps) {
+            umma_commit(bar_hempty + 8 * hs);
+            if (cc == nchunks - 1) umma_commit(bar_accum);
+          }
           CIS_TRACE_AT(9 + 2 * it);
         }
         __syncwarp();
+        if (++bs == BS) {
+          bs = 0;
+          bph ^= 1u;
+        }
+      }
+      if (++hs == NHS) {
+        hs = 0;
+        hph ^= 1u;
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (tid == 0) CIS_TRACE_AT(3);
-  if (cl > 1) cluster_sync_all();   // the peer may still be arriving on this CTA's bempty barriers
   if (warp == 4) tmem_dealloc_dyn(tmem, ncols);
 }
 
@@ -1512,34 +1521,37 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   int chunks = 0;
   for (int i = 0; i < d->nsrc; ++i) chunks += d->src[i].chunks;
   const int nchunks = (chunks + 7) / 8;
-  const int steps = ((nchunks + (d->splits > 1 ? d->splits : 1) - 1) / (d->splits > 1 ? d->splits : 1)) * d->ntaps;
-  const int nhs = steps > d->ntaps ? 2 : 1;         // halo stages: double-buffer only when there is a next chunk to prefetch
+  const int nsp = d->splits > 1 ? d->splits : 1;
+  const int cper = (nchunks + nsp - 1) / nsp;                  // 64-channel chunks per CTA
+  const int nhs = cper > 1 ? 2 : 1;                            // halo stages: double-buffer only when there is a next chunk to prefetch
+  const int dd = d->dil;
+  const int Hp0 = (d->OH + dd - 1) / dd, Wp0 = (d->OW + dd - 1) / dd;
+  const int tiles = ((Wp0 + 7) / 8) * ((Hp0 + 16 * d->MT - 1) / (16 * d->MT));
+  const long ncta_all = (long)tiles * dd * dd * d->N * d->n_tiles * nsp;
+  // ---- weight pipeline: G taps per stage (one bulk copy, one wait / commit of the MMA thread), BS stages
+  static const int g_env = getenv("CIS_HALO_G") ? atoi(getenv("CIS_HALO_G")) : 0;            // experiments: force the group size
+  static const int stage_kb = getenv("CIS_HALO_STAGE_KB") ? atoi(getenv("CIS_HALO_STAGE_KB")) : 32;
+  const int kB = BN * 128;
+  int G = g_env > 0 ? g_env : (stage_kb * 1024) / kB;
+  if (G < 1) G = 1;
+  if (G > d->ntaps) G = d->ntaps;
   const int fixed = nhs * halo_stage + HP * 4 + 1024;
-  int BS = (226 * 1024 - fixed) / (BN * 128);     // as deep a weight ring as fits ...
-  if (BS > kHaloMaxBStages) BS = kHaloMaxBStages;
-  if (BS > steps) BS = steps;                     // ... but never deeper than the number of pipeline steps
-  // prefer several co-resident CTAs per SM (their load / MMA / epilogue phases overlap) over a very deep ring -- unless the whole
-  // grid fits one CTA per SM anyway (low-resolution layers): then the ring depth is what hides the L2 latency of the weight stream
-  static const int deep_env = getenv("CIS_DEEP_RING") ? atoi(getenv("CIS_DEEP_RING")) : 0;
-  const int dd0 = d->dil;
-  const long ncta_all = (long)(((d->OW + dd0 - 1) / dd0 + 7) / 8) * (((d->OH + dd0 - 1) / dd0 + 16 * d->MT - 1) / (16 * d->MT)) * dd0 * dd0 * d->N *
-                        d->n_tiles * (d->splits > 1 ? d->splits : 1);
-  const int budgets[5] = {36 * 1024, 44 * 1024, 56 * 1024, 74 * 1024, 112 * 1024};
-  for (int b = 0; b < 5 && !(deep_env && ncta_all <= deep_env); ++b) {
-    const int fit = (budgets[b] - fixed) / (BN * 128);
-    if (fit >= 3 || (fit >= steps && fit >= 1)) { if (BS > fit) BS = fit; break; }
-  }
+  // two co-resident CTAs per SM overlap one CTA's epilogue with the other's main loop -- when the grid has that many CTAs
+  const int limit = (ncta_all > 148 && fixed + 2 * kB <= 113 * 1024) ? 113 * 1024 : 226 * 1024;
+  while (G > 1 && fixed + 2 * G * kB > limit) --G;
+  const int groups = cper * ((d->ntaps + G - 1) / G);          // pipeline stages one CTA walks
+  int BS = (limit - fixed) / (G * kB);
+  if (BS > (ncta_all > 148 ? 4 : kHaloMaxBStages)) BS = ncta_all > 148 ? 4 : kHaloMaxBStages;
+  if (BS > groups) BS = groups;
   if (BS < 1) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_conv_igemm(halo): tile does not fit shared memory");
-  const int smem = fixed + BS * BN * 128;
+  const int smem = fixed + BS * G * kB;
   static int attr_smem = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return cis_set_cuda_error(e, "cudaFuncSetAttribute(conv_halo)");
     attr_smem = smem;
   }
-  const int dd = d->dil;
-  const int Hp0 = (d->OH + dd - 1) / dd, Wp0 = (d->OW + dd - 1) / dd;
-  const int tiles = ((Wp0 + 7) / 8) * ((Hp0 + 16 * d->MT - 1) / (16 * d->MT));
+
   int splits = d->splits > 1 ? d->splits : 1;
   if (splits > 1) {
     const int per = (nchunks + splits - 1) / splits;
@@ -1556,7 +1568,7 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   if (!use_tma) memset(&maps, 0, sizeof(maps));
   // persistent variant: measured (r01) to win on single-chunk thin layers (weights re-streamed per tile are tiny) and to lose on
   // the wide ones at MT=1 (one weight stream per SM instead of 2-3 co-resident CTAs); CIS_PERSIST_MODE: 0 off, 1 thin (default), 2 all
-  const int persist_mode = g_persist_mode >= 0 ? g_persist_mode : (getenv("CIS_PERSIST_MODE") ? atoi(getenv("CIS_PERSIST_MODE")) : 1);
+  const int persist_mode = g_persist_mode >= 0 ? g_persist_mode : (getenv("CIS_PERSIST_MODE") ? atoi(getenv("CIS_PERSIST_MODE")) : 0);
   const bool persist_ok = persist_mode == 2 || ((persist_mode == 1 || persist_mode == 3) && BN <= 32 && nchunks == 1 && d->ntaps <= 9);
   // weight-stationary persistent variant (mode 3 / CIS_PERSIST_WS=1; experimental, off by default): thin layers whose whole
   // weight set (nchunks * ntaps tiles of BN x 128 B) fits next to two halo stages
@@ -1613,15 +1625,7 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
       return cis_check_launch("conv_halo_persist");
     }
   }
-  // experimental 2-CTA clusters sharing the weight stream (CIS_HALO_CLUSTER=2): wide n-tiles, an even number of pixel tiles
-  const char* cl_s = getenv("CIS_HALO_CLUSTER");   // read per launch (cheap) so tests can toggle it through os.environ
-  const int cl_env = cl_s ? atoi(cl_s) : 0;
-  cudaError_t le;
-  if (cl_env == 2 && BN >= 64 && grid.x % 2 == 0 && BS >= 2) {
-    le = launch_pdl_cluster(conv_halo_kernel<BN>, grid, dim3(kThreads), smem, st, 2, *d, halo_stage, BS, nhs, maps, use_tma, 2);
-  } else {
-    le = launch_pdl(conv_halo_kernel<BN>, grid, dim3(kThreads), smem, st, *d, halo_stage, BS, nhs, maps, use_tma, 1);
-  }
+  cudaError_t le = launch_pdl(conv_halo_kernel<BN>, grid, dim3(kThreads), smem, st, *d, halo_stage, BS, nhs, maps, use_tma, G);
   if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_halo)");
   if (splits > 1 && !d->sk_counters) {
     le = launch_splitk_finish<BN>(d, grid, st);

@@ -453,7 +453,10 @@ class AdversarialLearner(object):
             from ..data.crops import central_crops
             img1, img2, gt = central_crops(img1[:1], img2[:1], gt[:1], self.test_crops)
         self.feed(img1, img2)
-        g.forward()
+        if self.aug_test:
+            g.forward_masks(use_graph=True)      # the multi-crop graph of the reference outputs masks only (:525-592)
+        else:
+            g.forward()
         H, W = g.H, g.W
         gtr = torch.nn.functional.interpolate(gt.permute(0, 3, 1, 2), size=(H, W), mode='nearest').permute(0, 2, 3, 1).numpy()
         masks = g.mask.cpu().numpy()

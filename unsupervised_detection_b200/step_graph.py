@@ -67,9 +67,12 @@ class CISGraph(object):
         P.add('cis_pack_f32_to_bf16', self.image.data_ptr(), B * hw, 3, 0.0, self.img8.ptr, 8, 0)
         self.mask = f32(B, H, W, 1)
         bld.lane = 1
+        i0 = len(P.ops)
         self.rec.build_a_encoder(bld, self.img8)        # side stream, overlaps the generator
+        i1 = len(P.ops)
         bld.lane = 0
         self.gen.build(bld, self.gen_in, self.mask)
+        self._mask_ops = (i0, i1, len(P.ops))           # forward ops [0,i0) + [i1,end) produce the masks (no recover net, no losses)
         # mask (x) flow -> recover inputs for the 3 calls (adversarial_learner.py:107-131)
         self.rec_in = Act(3 * B, H, W, 4, device, name='rec_in', dep={'G'})
         self.rec_in.gen_rows = 2 * B
@@ -191,6 +194,35 @@ class CISGraph(object):
     def forward(self):
         self._ensure_packed()
         self.fwd.run()
+
+    def forward_masks(self, use_graph=False):
+        """Mask path only: [PWC-Net -> resize ->] flow normalisation -> generator -> self.mask (what test_generator*.py consume;
+        the reference's multi-crop test graph, adversarial_learner.py:525-592, builds nothing else).  use_graph replays it as one
+        CUDA graph."""
+        self._ensure_packed()
+        if getattr(self, '_mask_plan', None) is None:
+            i0, i1, i2 = self._mask_ops
+            mp = Plan('fwd_masks')
+            mp.ops = self.fwd.ops[:i0] + self.fwd.ops[i1:i2]
+            mp.keep = self.fwd.keep
+            self._mask_plan = mp
+        if not use_graph:
+            self._mask_plan.run()
+            return
+        g = self.graphs.get('masks')
+        if g is None:
+            torch.cuda.synchronize()
+            s = torch.cuda.Stream()
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._mask_plan.run()          # warm-up outside capture (function attributes, lazy allocations)
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._mask_plan.run()
+            self.graphs['masks'] = g
+        g.replay()
 
     def launches_per_step(self, mode):
         return self.fwd.count() + self.bwd[mode].count() + self.adam[mode].count() + self._pack_of(mode).count()

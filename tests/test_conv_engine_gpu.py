@@ -86,9 +86,6 @@ def test_conv_engine_split_k(case):
         assert r['dx_err'] <= tol(r['dx_ref']), r
 
 
-@pytest.mark.skipif(os.environ.get('CIS_TEST_EXPERIMENTAL') != '1',
-                    reason='two-launch split-K was written after the GPU budget of round 1 was spent: compiled but never run; '
-                           'set CIS_TEST_EXPERIMENTAL=1 to validate it before enabling CIS_SPLITK=2')
 @pytest.mark.parametrize('case', MODE_CASES, ids=lambda c: 'k%d_d%d_c%s_o%d' % (c['k'], c.get('dil', 1), '+'.join(map(str, c['cins'])), c['cout']))
 def test_conv_engine_split_k_two_launch(case):
     """Two-launch split-K (slices + parallel finish kernel, engine.SPLITK = 2; off by default): same fixed summation order as the
@@ -114,9 +111,6 @@ WS_CASES = [CASES[2], CASES[11], CASES[16], CASES[17], CASES[18], CASES[0],
             dict(N=3, H=48, W=80, cins=[16, 16, 16, 2], cout=2, k=5, backward=False)]
 
 
-@pytest.mark.skipif(os.environ.get('CIS_TEST_EXPERIMENTAL') != '1',
-                    reason='weight-stationary persistent kernel was written after the GPU budget of round 1 was spent: compiled but '
-                           'never run; set CIS_TEST_EXPERIMENTAL=1 to validate it before enabling CIS_PERSIST_WS=1')
 @pytest.mark.parametrize('case', WS_CASES, ids=lambda c: 'k%d_c%s_o%d_%dx%d' % (c['k'], '+'.join(map(str, c['cins'])), c['cout'], c['H'], c['W']))
 def test_conv_engine_weight_stationary_persistent(case):
     """Persist mode 3: thin layers whose whole weight set fits in shared memory keep it resident across the tiles of a CTA."""
@@ -155,37 +149,9 @@ def test_conv_engine_halo_wgrad(case):
         assert r['dgamma_err'] <= 2 ** -6 * r['dgamma_ref'] + 1e-2, r
 
 
-CL_CASES = [CASES[0], CASES[1], CASES[6], CASES[12], CASES[13], CASES[14],
-            dict(N=4, H=48, W=80, cins=[128, 128, 64], cout=128, k=3, act=ACT_LEAKY, alpha=0.1, backward=False),
-            dict(N=2, H=32, W=64, cins=[256], cout=96, k=3, act=ACT_LEAKY, backward=False)]
-
-
-@pytest.mark.skipif(os.environ.get('CIS_TEST_EXPERIMENTAL') != '1',
-                    reason='2-CTA cluster weight multicast was written after the GPU budget of round 1 was spent: compiled but never run; '
-                           'set CIS_TEST_EXPERIMENTAL=1 (and run it under a short timeout) before enabling CIS_HALO_CLUSTER=2')
-@pytest.mark.parametrize('case', CL_CASES, ids=lambda c: 'k%d_c%s_o%d_%dx%d' % (c['k'], '+'.join(map(str, c['cins'])), c['cout'], c['H'], c['W']))
-def test_conv_engine_cluster_weight_multicast(case):
-    """CIS_HALO_CLUSTER=2: pairs of CTAs share every weight tile through multicast bulk copies; results are bit-identical to the
-    default launch (same MMAs, same order)."""
-    r0 = run_conv_case(**case)
-    os.environ['CIS_HALO_CLUSTER'] = '2'
-    try:
-        r = run_conv_case(**case)
-    finally:
-        del os.environ['CIS_HALO_CLUSTER']
-    tol = lambda ref: 2 ** -7 * ref + 1e-3
-    assert r['fwd_err'] <= tol(r['fwd_ref']), r
-    assert r['fwd_err'] == r0['fwd_err']
-    if 'dx_err' in r:
-        assert r['dx_err'] <= tol(r['dx_ref']), r
-
-
 NARROW_CASES = [CASES[1], CASES[6], CASES[10], CASES[12], CASES[13], CASES[4]]
 
 
-@pytest.mark.skipif(os.environ.get('CIS_TEST_EXPERIMENTAL') != '1',
-                    reason='narrow n-tiles (BN = 32/64 with several n-tiles) are an untested kernel configuration prepared after the GPU '
-                           'budget of round 1 was spent; set CIS_TEST_EXPERIMENTAL=1 before enabling CIS_SMALL_BN')
 @pytest.mark.parametrize('cap', [32, 64])
 @pytest.mark.parametrize('case', NARROW_CASES, ids=lambda c: 'k%d_d%d_c%s_o%d' % (c['k'], c.get('dil', 1), '+'.join(map(str, c['cins'])), c['cout']))
 def test_conv_engine_narrow_n_tiles(case, cap):

@@ -149,8 +149,12 @@ __device__ __forceinline__ void epi_group(const CisConv& p, const uint32_t taddr
 #pragma unroll
     for (int e = 0; e < 16; ++e) v[e] = __uint_as_float(raw[c][e]);
     if (p.bias) {
+      const float4* sb = reinterpret_cast<const float4*>(sbias + (cg - cg0));   // sbias = this group's first column; 16-float aligned: 4 x LDS.128
 #pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] += sbias[cg - cg0 + e + (cg0 & 127)];
+      for (int q = 0; q < 4; ++q) {
+        const float4 b4 = sb[q];
+        v[4 * q] += b4.x; v[4 * q + 1] += b4.y; v[4 * q + 2] += b4.z; v[4 * q + 3] += b4.w;
+      }
     }
     if (is_pre) {
 #pragma unroll
@@ -167,8 +171,10 @@ __device__ __forceinline__ void epi_group(const CisConv& p, const uint32_t taddr
       for (int e = 0; e < 16 && cg + e < p.outf_ch; ++e) v[e] += __ldg(p.addf_pre + dpix * p.addf_pitch + p.addf_coff + cg + e);
     }
     if (p.act == CIS_ACT_ELU) {
+      // exp through MUFU.EX2 (4 instructions per element instead of the ~40 of expm1f): |error| <= ~1e-7 absolute, far below the
+      // bf16 rounding of the stored activation; the epilogue runs on one warp per scheduler, so instruction count IS its time
 #pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.f ? v[e] : expm1f(v[e]);
+      for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.f ? v[e] : __expf(v[e]) - 1.f;
     } else if (p.act == CIS_ACT_LEAKY) {
 #pragma unroll
       for (int e = 0; e < 16; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * p.alpha;
@@ -211,7 +217,7 @@ __device__ __forceinline__ void epi_row(const CisConv& p, const uint32_t t_row, 
                                         const float* __restrict__ sbias) {
   if constexpr (BN >= 32) {
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) epi_group<2>(p, t_row + c0, cbase + c0, dpix, valid, sbias);
+    for (int c0 = 0; c0 < BN; c0 += 32) epi_group<2>(p, t_row + c0, cbase + c0, dpix, valid, sbias + c0);   // sbias: the BN columns of THIS n-tile
   } else {
     epi_group<1>(p, t_row, cbase, dpix, valid, sbias);
   }
@@ -323,7 +329,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
   const int nkb = min(kper, nkb_all - kb_lo);     // host guarantees nkb >= 1 for every split
   const int ny = blockIdx.y;
   __shared__ int s_flag;
-  __shared__ float s_bias[BN];
+  __shared__ __align__(16) float s_bias[BN];
   pdl_launch_dependents();
 
   if (tid < p.ntaps) {
@@ -502,6 +508,23 @@ struct HaloMaps {
   CUtensorMap m[CIS_MAX_SRC];   // one 4-D (C, W, H, N) SWIZZLE_128B map per concat source, box = (64, Wh, Hh, 1)
 };
 
+// MMAs of one weight stage (gt taps of one 64-channel chunk, MT stacked tiles, NK K=16 steps each), issued by ONE thread.
+template <int NK>
+__device__ __forceinline__ void halo_issue_stage(const uint32_t tmem, const uint32_t hlo, uint32_t blo, const uint32_t* s_aoff, const int gt,
+                                                 const int MT, const int BN, const uint32_t ahi, const uint32_t bhi, const uint32_t a_mstep,
+                                                 const uint32_t idesc, const bool first) {
+  const uint32_t bstep = (uint32_t)(BN * 128) >> 4;
+  for (int tt = 0; tt < gt; ++tt, blo += bstep) {
+    uint32_t alo = hlo + s_aoff[tt];
+    const uint32_t acc0 = (uint32_t)(!(first && tt == 0));
+    for (int m = 0; m < MT; ++m, alo += a_mstep) {
+      const uint32_t td = tmem + m * BN;
+#pragma unroll
+      for (int k = 0; k < NK; ++k) umma_bf16_lh(td, alo + 2 * k, ahi, blo + 2 * k, bhi, idesc, k ? 1u : acc0);
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_constant__ CisConv p, const int halo_stage_bytes, const int BS, const int NHS,
                                                         const __grid_constant__ HaloMaps maps, const int use_tma, const int G) {
@@ -547,7 +570,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   const int nchunks = min(cper, nchunks_all - cc_lo);   // chunks handled by this CTA (host guarantees >= 1)
   const int cin8 = m_chunks * 8;
   __shared__ int s_flag;
-  __shared__ float s_bias[BN];
+  __shared__ __align__(16) float s_bias[BN];
   pdl_launch_dependents();
   const uint32_t ncols = (MT * BN <= 32) ? 32u : (MT * BN <= 64) ? 64u : (MT * BN <= 128) ? 128u : (MT * BN <= 256) ? 256u : 512u;
 
@@ -581,6 +604,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     __syncwarp();
     tmem_alloc_dyn(smem_u32(&tmem_slot), ncols);
   }
+  if (use_tma && tid < p.nsrc) tma_prefetch_desc(&maps.m[tid]);   // descriptors live in the kernel parameters: fetch them before the grid dependency resolves
   pdl_wait();
   if (tid < BN) s_bias[tid] = p.bias ? p.bias[ny * BN + tid] : 0.f;
   tc_fence_before();
@@ -740,22 +764,12 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
         tc_fence_after();
         if (elect_one()) {
           CIS_TRACE_AT(8 + 2 * it);
-          uint32_t blo = desc_lo(b_base + bs * stage_bytes, 16);
-          for (int tt = 0; tt < gt; ++tt, blo += kBStage >> 4) {
-            uint32_t alo = hlo + s_aoff[t0 + tt];
-            const uint32_t acc0 = (uint32_t)((cc | t0 | tt) != 0);
-            for (int m = 0; m < MT; ++m, alo += a_mstep) {
-              const uint32_t td = tmem + m * BN;
-              if (nk16 == 4) {
-                umma_bf16_lh(td, alo, ahi, blo, bhi, idesc, acc0);
-                umma_bf16_lh(td, alo + 2, ahi, blo + 2, bhi, idesc, 1u);
-                umma_bf16_lh(td, alo + 4, ahi, blo + 4, bhi, idesc, 1u);
-                umma_bf16_lh(td, alo + 6, ahi, blo + 6, bhi, idesc, 1u);
-              } else {
-                for (int k = 0; k < nk16; ++k) umma_bf16_lh(td, alo + 2 * k, ahi, blo + 2 * k, bhi, idesc, k ? 1u : acc0);
-              }
-            }
-          }
+          const uint32_t blo = desc_lo(b_base + bs * stage_bytes, 16);
+          const bool first = (cc | t0) == 0;
+          if (nk16 == 4) halo_issue_stage<4>(tmem, hlo, blo, s_aoff + t0, gt, MT, BN, ahi, bhi, a_mstep, idesc, first);
+          else if (nk16 == 1) halo_issue_stage<1>(tmem, hlo, blo, s_aoff + t0, gt, MT, BN, ahi, bhi, a_mstep, idesc, first);
+          else if (nk16 == 2) halo_issue_stage<2>(tmem, hlo, blo, s_aoff + t0, gt, MT, BN, ahi, bhi, a_mstep, idesc, first);
+          else halo_issue_stage<3>(tmem, hlo, blo, s_aoff + t0, gt, MT, BN, ahi, bhi, a_mstep, idesc, first);
           umma_commit(bar_bempty + 8 * bs);
           if (t0 + G >= p.ntaps) {
             umma_commit(bar_hempty + 8 * hs);
@@ -839,35 +853,38 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const __grid_constan
   epi_chunk(p, v, ny * BN + c0, dpix);
 }
 // ======================================================================================================= persistent halo conv
-// Same math as conv_halo_kernel (TMA halo path only), restructured as a persistent, fully warp-specialised pipeline so the
-// per-tile latency chain (halo fetch -> MMAs -> TMEM read-back -> stores) of one tile overlaps the next tiles:
-//   warp 0: halo TMA producer | warp 1: weight-tile bulk-copy producer | warp 2: MMA issuer | warp 3: TMEM owner
-//   warps 4-7: epilogue (TMEM lane quarter = warp % 4), two accumulator stages in TMEM (full/empty mbarriers).
+// Same math as conv_halo_kernel (TMA halo path only) for layers with MANY output tiles per SM (high-resolution thin layers), where the
+// per-CTA prologue (barrier init, TMEM allocation, first TMA round trip: ~3k clk) and epilogue (TMEM read-back + stores on one warp
+// per scheduler: 2-17k clk) of the one-tile-per-CTA kernel cost more than its MMA loop (CIS_TRACE build, r02).  Here a CTA is
+// persistent and fully warp-specialised so those phases of neighbouring tiles overlap:
+//   warp 0: halo TMA producer (NHS stages) | warp 1: weight producer | warp 2: MMA issuer | warp 3: TMEM owner
+//   warps 4-7 / 8-11: two epilogue groups (TMEM lane quarter = warp % 4); tile i uses accumulator stage i % AS and group i % AS.
+// Weights: resident (ws = 1: the whole set of nchunks*ntaps tiles is fetched once per CTA and stays in shared memory while the CTA
+// walks its tiles) when it fits, else re-streamed per tile in stages of G taps through a ring of BS stages.
 // Every role walks the same static work list  w = blockIdx.x, blockIdx.x + gridDim.x, ...  of output tiles.
-static constexpr int kPThreads = 256;
+static constexpr int kPThreads = 384;
 
 template <int BN>
 __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __grid_constant__ CisConv p, const int halo_stage_bytes,
-                                                                       const int BS, const int NHS, const int AS,
+                                                                       const int BS, const int NHS, const int AS, const int G,
                                                                        const __grid_constant__ HaloMaps maps, const int ws) {
-  // ws = 1 (weight-stationary, experimental): all nchunks*ntaps weight tiles of the layer are fetched ONCE per CTA into
-  // b_base[0 .. per_tile) (one mbarrier, BS = 1 for the barrier bookkeeping) and stay resident for every tile the CTA walks;
-  // thin many-tap layers (generator conv1 5x5x8, recover flow1) otherwise re-stream 25 mostly-zero 4 KB tiles per output tile.
   constexpr int kBStage = BN * 128;
+  constexpr int kMaxHS = 4;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bars[2 * 3 + 2 * kHaloMaxBStages + 4];
+  __shared__ uint64_t bars[2 * kMaxHS + 2 * kHaloMaxBStages + 4];
   __shared__ uint32_t tmem_slot;
-  __shared__ int s_dh[CIS_MAX_TAPS], s_dw[CIS_MAX_TAPS];
-  __shared__ float s_bias[BN];
+  __shared__ uint32_t s_aoff[CIS_MAX_TAPS];
+  __shared__ __align__(16) float s_bias[BN];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int MT = p.MT;
   const int Wh = 8 + p.ex, Hh = 16 * MT + p.ey, HP = Wh * Hh;
+  const uint32_t stage_bytes = (uint32_t)G * kBStage;
   const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t h_base = tile_base, b_base = tile_base + NHS * halo_stage_bytes;
-  const uint32_t bar_hfull = smem_u32(&bars[0]), bar_hempty = smem_u32(&bars[3]);
-  const uint32_t bar_bfull = smem_u32(&bars[6]), bar_bempty = smem_u32(&bars[6 + kHaloMaxBStages]);
-  const uint32_t bar_tfull = smem_u32(&bars[6 + 2 * kHaloMaxBStages]), bar_tempty = smem_u32(&bars[8 + 2 * kHaloMaxBStages]);
+  const uint32_t bar_hfull = smem_u32(&bars[0]), bar_hempty = smem_u32(&bars[kMaxHS]);
+  const uint32_t bar_bfull = smem_u32(&bars[2 * kMaxHS]), bar_bempty = smem_u32(&bars[2 * kMaxHS + kHaloMaxBStages]);
+  const uint32_t bar_tfull = smem_u32(&bars[2 * kMaxHS + 2 * kHaloMaxBStages]), bar_tempty = smem_u32(&bars[2 * kMaxHS + 2 * kHaloMaxBStages + 2]);
 
   const int tiles_x = (p.OW + 7) / 8, tiles_y = (p.OH + 16 * MT - 1) / (16 * MT);
   const int total = tiles_x * tiles_y * p.N;
@@ -879,10 +896,7 @@ __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __gr
   const uint32_t ncols = want <= 32 ? 32u : want <= 64 ? 64u : want <= 128 ? 128u : want <= 256 ? 256u : 512u;
 
   pdl_launch_dependents();
-  if (tid < p.ntaps) {
-    s_dh[tid] = p.dh[tid];
-    s_dw[tid] = p.dw[tid];
-  }
+  if (tid < p.ntaps) s_aoff[tid] = (uint32_t)((p.dh[tid] * Wh + p.dw[tid]) * 8);
   if (warp == 3) {
     if (lane == 0) {
       for (int s = 0; s < NHS; ++s) {
@@ -895,13 +909,14 @@ __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __gr
       }
       for (int s = 0; s < AS; ++s) {
         mbar_init(bar_tfull + 8 * s, 1);
-        mbar_init(bar_tempty + 8 * s, 4);   // one arrival per epilogue warp
+        mbar_init(bar_tempty + 8 * s, 4);   // one arrival per warp of the epilogue group that drained the stage
       }
       fence_mbar_init();
     }
     __syncwarp();
     tmem_alloc_dyn(smem_u32(&tmem_slot), ncols);
   }
+  if (tid < p.nsrc) tma_prefetch_desc(&maps.m[tid]);
   pdl_wait();
   if (tid < BN) s_bias[tid] = p.bias ? p.bias[tid] : 0.f;
   tc_fence_before();
@@ -912,12 +927,12 @@ __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __gr
   if (warp == 0) {
     // ------------------------------------------------------------------ halo producer
     if (lane == 0) {
-      int hc = 0;
+      int hs = 0;
+      uint32_t hph = 1;
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const int tx = w % tiles_x, r1 = w / tiles_x, ty = r1 % tiles_y, n = r1 / tiles_y;
-        for (int cc = 0; cc < nchunks; ++cc, ++hc) {
-          const int hs = hc % NHS;
-          mbar_wait(bar_hempty + 8 * hs, (uint32_t)(((hc / NHS) & 1) ^ 1));
+        for (int cc = 0; cc < nchunks; ++cc) {
+          mbar_wait(bar_hempty + 8 * hs, hph);
           int c = cc * 8, si = 0;
           while (si < p.nsrc - 1 && c >= p.src[si].chunks) {
             c -= p.src[si].chunks;
@@ -930,6 +945,10 @@ __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __gr
           mbar_expect_tx(bar_hfull + 8 * hs, (uint32_t)(HP * 128));
           tma_load_4d(h_base + hs * halo_stage_bytes, &maps.m[si], bar_hfull + 8 * hs, c * 8, tx * 8 + p.hox, ty * 16 * MT + p.hoy,
                       nmod ? (n % nmod) : n);
+          if (++hs == NHS) {
+            hs = 0;
+            hph ^= 1u;
+          }
         }
       }
     }
@@ -938,19 +957,30 @@ __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __gr
     if (lane == 0) {
       const uint8_t* wt = reinterpret_cast<const uint8_t*>(p.wpack);
       const int per_tile = nchunks * p.ntaps;
-      int bc = 0;
       if (ws) {
         if ((int)blockIdx.x < total) {
           mbar_expect_tx(bar_bfull, (uint32_t)(per_tile * kBStage));
-          for (int it = 0; it < per_tile; ++it) bulk_g2s(b_base + it * kBStage, wt + (size_t)it * kBStage, kBStage, bar_bfull);
+          for (int it = 0; it < per_tile; it += 8) {      // bulk copies of up to 8 tiles (<= 128 KB each)
+            const int nt = min(8, per_tile - it);
+            bulk_g2s(b_base + it * kBStage, wt + (size_t)it * kBStage, (uint32_t)(nt * kBStage), bar_bfull);
+          }
         }
-      } else
-      for (int w = blockIdx.x; w < total; w += gridDim.x) {
-        for (int it = 0; it < per_tile; ++it, ++bc) {
-          const int bs = bc % BS;
-          mbar_wait(bar_bempty + 8 * bs, (uint32_t)(((bc / BS) & 1) ^ 1));
-          mbar_expect_tx(bar_bfull + 8 * bs, kBStage);
-          bulk_g2s(b_base + bs * kBStage, wt + (size_t)it * kBStage, kBStage, bar_bfull + 8 * bs);
+      } else {
+        int bs = 0;
+        uint32_t bph = 1;
+        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+          for (int cc = 0; cc < nchunks; ++cc) {
+            for (int t0 = 0; t0 < p.ntaps; t0 += G) {
+              const uint32_t bytes = (uint32_t)min(G, p.ntaps - t0) * kBStage;
+              mbar_wait(bar_bempty + 8 * bs, bph);
+              mbar_expect_tx(bar_bfull + 8 * bs, bytes);
+              bulk_g2s(b_base + bs * stage_bytes, wt + (size_t)(cc * p.ntaps + t0) * kBStage, bytes, bar_bfull + 8 * bs);
+              if (++bs == BS) {
+                bs = 0;
+                bph ^= 1u;
+              }
+            }
+          }
         }
       }
     }
@@ -959,61 +989,78 @@ __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __gr
     constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
     const uint32_t ahi = desc_hi((uint32_t)(Wh * 128)), bhi = desc_hi(1024);
     const uint32_t a_mstep = (uint32_t)(16 * Wh * 128) >> 4;
-    int hc = 0, bc = 0, wi = 0;
+    int hs = 0, bs = 0, as = 0;
+    uint32_t hph = 0, bph = 0, tph = 1;
     if (ws && (int)blockIdx.x < total) {
       mbar_wait(bar_bfull, 0u);      // the resident weight set; never released
       tc_fence_after();
     }
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++wi) {
-      const int as = wi % AS;
-      mbar_wait(bar_tempty + 8 * as, (uint32_t)(((wi / AS) & 1) ^ 1));
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      mbar_wait(bar_tempty + 8 * as, tph);
       tc_fence_after();
       const uint32_t tacc = tmem + as * acc_cols;
-      for (int cc = 0; cc < nchunks; ++cc, ++hc) {
-        const int hs = hc % NHS;
+      for (int cc = 0; cc < nchunks; ++cc) {
         const int rem = m_chunks - cc * 8;
         const int nk16 = rem >= 8 ? 4 : (rem + 1) / 2;
-        mbar_wait(bar_hfull + 8 * hs, (uint32_t)((hc / NHS) & 1));
-        const uint32_t hsrc = h_base + hs * halo_stage_bytes;
-        for (int t = 0; t < p.ntaps; ++t, ++bc) {
-          const int bs = ws ? (cc * p.ntaps + t) : (bc % BS);
-          if (!ws) mbar_wait(bar_bfull + 8 * bs, (uint32_t)((bc / BS) & 1));
+        mbar_wait(bar_hfull + 8 * hs, hph);
+        const uint32_t hlo = desc_lo(h_base + hs * halo_stage_bytes, 16);
+        const int gstep = ws ? p.ntaps : G;
+        for (int t0 = 0; t0 < p.ntaps; t0 += gstep) {
+          const int gt = min(gstep, p.ntaps - t0);
+          if (!ws) mbar_wait(bar_bfull + 8 * bs, bph);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t blo = desc_lo(b_base + bs * kBStage, 16);
-            uint32_t alo = desc_lo(hsrc + (uint32_t)((s_dh[t] * Wh + s_dw[t]) * 128), 16);
-            const uint32_t acc0 = (uint32_t)((cc | t) != 0);
-            for (int m = 0; m < MT; ++m, alo += a_mstep) {
-              const uint32_t td = tacc + m * BN;
-              for (int k = 0; k < nk16; ++k) umma_bf16_lh(td, alo + 2 * k, ahi, blo + 2 * k, bhi, idesc, k ? 1u : acc0);
-            }
+            const uint32_t blo = desc_lo(ws ? b_base + (uint32_t)(cc * p.ntaps) * kBStage : b_base + bs * stage_bytes, 16);
+            const bool first = (cc | t0) == 0;
+            if (nk16 == 4) halo_issue_stage<4>(tacc, hlo, blo, s_aoff + t0, gt, MT, BN, ahi, bhi, a_mstep, idesc, first);
+            else if (nk16 == 1) halo_issue_stage<1>(tacc, hlo, blo, s_aoff + t0, gt, MT, BN, ahi, bhi, a_mstep, idesc, first);
+            else if (nk16 == 2) halo_issue_stage<2>(tacc, hlo, blo, s_aoff + t0, gt, MT, BN, ahi, bhi, a_mstep, idesc, first);
+            else halo_issue_stage<3>(tacc, hlo, blo, s_aoff + t0, gt, MT, BN, ahi, bhi, a_mstep, idesc, first);
             if (!ws) umma_commit(bar_bempty + 8 * bs);
-            if (t == p.ntaps - 1) umma_commit(bar_hempty + 8 * hs);
-            if (cc == nchunks - 1 && t == p.ntaps - 1) umma_commit(bar_tfull + 8 * as);
+            if (t0 + gstep >= p.ntaps) {
+              umma_commit(bar_hempty + 8 * hs);
+              if (cc == nchunks - 1) umma_commit(bar_tfull + 8 * as);
+            }
           }
           __syncwarp();
+          if (!ws && ++bs == BS) {
+            bs = 0;
+            bph ^= 1u;
+          }
         }
+        if (++hs == NHS) {
+          hs = 0;
+          hph ^= 1u;
+        }
+      }
+      if (++as == AS) {
+        as = 0;
+        tph ^= 1u;
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue (warps 4..7 -> TMEM lanes 32*(warp-4)..)
-    const int q = warp - 4;
+    // ------------------------------------------------------------------ epilogue: group g = (warp - 4) / 4 drains accumulator stage g
+    const int grp = (warp - 4) >> 2, q = warp & 3;
     const int r = q * 32 + lane;
-    int wi = 0;
-    for (int w = blockIdx.x; w < total; w += gridDim.x, ++wi) {
-      const int tx = w % tiles_x, r1 = w / tiles_x, ty = r1 % tiles_y, n = r1 / tiles_y;
-      const int as = wi % AS;
-      mbar_wait(bar_tfull + 8 * as, (uint32_t)((wi / AS) & 1));
-      tc_fence_after();
-      for (int m = 0; m < MT; ++m) {
-        const int oy = ty * 16 * MT + 16 * m + (r >> 3), ox = tx * 8 + (r & 7);
-        const bool valid = oy < p.OH && ox < p.OW;
-        const size_t dpix = valid ? ((size_t)(n * p.DH + oy * p.osh + p.oa) * p.DW + ox * p.osw + p.ob) : 0;
-        epi_row<BN>(p, tmem + ((uint32_t)(q * 32) << 16) + as * acc_cols + m * BN, 0, dpix, valid, s_bias);
+    if (grp < AS) {
+      uint32_t tph = 0;
+      int wi = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++wi) {
+        if (wi % AS != grp) continue;
+        const int tx = w % tiles_x, r1 = w / tiles_x, ty = r1 % tiles_y, n = r1 / tiles_y;
+        mbar_wait(bar_tfull + 8 * grp, tph);
+        tph ^= 1u;
+        tc_fence_after();
+        for (int m = 0; m < MT; ++m) {
+          const int oy = ty * 16 * MT + 16 * m + (r >> 3), ox = tx * 8 + (r & 7);
+          const bool valid = oy < p.OH && ox < p.OW;
+          const size_t dpix = valid ? ((size_t)(n * p.DH + oy * p.osh + p.oa) * p.DW + ox * p.osw + p.ob) : 0;
+          epi_row<BN>(p, tmem + ((uint32_t)(q * 32) << 16) + grp * acc_cols + m * BN, 0, dpix, valid, s_bias);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_tempty + 8 * grp);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * as);
     }
   }
   tc_fence_before();
@@ -1530,7 +1577,7 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   const long ncta_all = (long)tiles * dd * dd * d->N * d->n_tiles * nsp;
   // ---- weight pipeline: G taps per stage (one bulk copy, one wait / commit of the MMA thread), BS stages
   static const int g_env = getenv("CIS_HALO_G") ? atoi(getenv("CIS_HALO_G")) : 0;            // experiments: force the group size
-  static const int stage_kb = getenv("CIS_HALO_STAGE_KB") ? atoi(getenv("CIS_HALO_STAGE_KB")) : 32;
+  static const int stage_kb = getenv("CIS_HALO_STAGE_KB") ? atoi(getenv("CIS_HALO_STAGE_KB")) : 48;
   const int kB = BN * 128;
   int G = g_env > 0 ? g_env : (stage_kb * 1024) / kB;
   if (G < 1) G = 1;
@@ -1566,47 +1613,32 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   for (int i = 0; use_tma && i < d->nsrc; ++i)
     if (((uintptr_t)d->src[i].ptr + (size_t)d->src[i].c_off * 2) % 16 || !encode_src_map(&maps.m[i], d->src[i], d->N, d->H, d->W, Wh, Hh)) use_tma = 0;
   if (!use_tma) memset(&maps, 0, sizeof(maps));
-  // persistent variant: measured (r01) to win on single-chunk thin layers (weights re-streamed per tile are tiny) and to lose on
-  // the wide ones at MT=1 (one weight stream per SM instead of 2-3 co-resident CTAs); CIS_PERSIST_MODE: 0 off, 1 thin (default), 2 all
-  const int persist_mode = g_persist_mode >= 0 ? g_persist_mode : (getenv("CIS_PERSIST_MODE") ? atoi(getenv("CIS_PERSIST_MODE")) : 0);
-  const bool persist_ok = persist_mode == 2 || ((persist_mode == 1 || persist_mode == 3) && BN <= 32 && nchunks == 1 && d->ntaps <= 9);
-  // weight-stationary persistent variant (mode 3 / CIS_PERSIST_WS=1; experimental, off by default): thin layers whose whole
-  // weight set (nchunks * ntaps tiles of BN x 128 B) fits next to two halo stages
-  static const int ws_env = getenv("CIS_PERSIST_WS") ? atoi(getenv("CIS_PERSIST_WS")) : 0;
-  static int attr_p = 0;   // largest dynamic-smem limit set so far on conv_halo_persist_kernel<BN> (shared by both variants)
-  const int per_tile = nchunks * d->ntaps;
-  const int ws_smem = 2 * halo_stage + 1024 + per_tile * BN * 128;
-  if ((persist_mode == 3 || (ws_env && g_persist_mode < 0)) && use_tma && d->n_tiles == 1 && splits == 1 && BN <= 32 && per_tile >= 2 &&
-      ws_smem <= 200 * 1024) {
+  // persistent variant (conv_halo_persist_kernel): layers with many tiles per SM.  CIS_PERSIST_MODE / cis_set_persist_mode:
+  //   0 off | 1 (default) layers whose whole weight set stays resident in shared memory and that have >= 2 tiles per SM |
+  //   2 every eligible layer (tests) | 3 every layer whose weight set fits, whatever the tile count (tests)
+  const int persist_mode = g_persist_mode >= 0 ? g_persist_mode : (getenv("CIS_PERSIST_MODE") ? atoi(getenv("CIS_PERSIST_MODE")) : 1);
+  static const int p_min_tiles = getenv("CIS_PERSIST_MIN_TILES") ? atoi(getenv("CIS_PERSIST_MIN_TILES")) : 296;
+  static const int p_ws_kb = getenv("CIS_PERSIST_WS_KB") ? atoi(getenv("CIS_PERSIST_WS_KB")) : 112;
+  if (persist_mode > 0 && use_tma && d->n_tiles == 1 && splits == 1) {
+    const int total = tiles * d->N;
+    const int per_tile = nchunks * d->ntaps;
     const int AS = (2 * d->MT * BN <= 512) ? 2 : 1;
-    if (ws_smem > attr_p) {
-      cudaError_t e = cudaFuncSetAttribute(conv_halo_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem);
-      if (e != cudaSuccess) return cis_set_cuda_error(e, "cudaFuncSetAttribute(conv_halo_persist ws)");
-      attr_p = ws_smem;
+    const int ws_bytes = per_tile * kB;
+    int p_nhs = nchunks >= 3 ? 4 : 3;
+    while (p_nhs > 2 && p_nhs * halo_stage + 1024 + (ws_bytes <= p_ws_kb * 1024 ? ws_bytes : 2 * G * kB) > 226 * 1024) --p_nhs;
+    const bool ws_fits = ws_bytes <= p_ws_kb * 1024 && p_nhs * halo_stage + 1024 + ws_bytes <= 226 * 1024;
+    const bool take = persist_mode == 2 || (persist_mode == 3 && ws_fits) || (persist_mode == 1 && ws_fits && total >= p_min_tiles);
+    int p_bs = 0, p_smem = 0;
+    if (ws_fits) {
+      p_bs = 1;
+      p_smem = p_nhs * halo_stage + 1024 + ws_bytes;
+    } else {
+      p_bs = (226 * 1024 - p_nhs * halo_stage - 1024) / (G * kB);
+      if (p_bs > 4) p_bs = 4;
+      p_smem = p_nhs * halo_stage + 1024 + p_bs * G * kB;
     }
-    const int want = AS * d->MT * BN;
-    const int tcols = want <= 32 ? 32 : want <= 64 ? 64 : want <= 128 ? 128 : want <= 256 ? 256 : 512;
-    int cps = (227 * 1024) / (ws_smem + 1024);
-    if (cps > 512 / tcols) cps = 512 / tcols;
-    if (cps > 4) cps = 4;
-    if (cps < 1) cps = 1;
-    int g = tiles * d->N;
-    if (g > 148 * cps) g = 148 * cps;
-    cudaError_t le = launch_pdl(conv_halo_persist_kernel<BN>, dim3(g), dim3(kPThreads), ws_smem, st, *d, halo_stage, 1, 2, AS, maps, 1);
-    if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_halo_persist ws)");
-    return cis_check_launch("conv_halo_persist ws");
-  }
-  if (persist_ok && use_tma && d->n_tiles == 1 && splits == 1) {
-    // persistent, warp-specialised variant: two halo stages, two accumulator stages when TMEM allows
-    const int AS = (2 * d->MT * BN <= 512) ? 2 : 1;
-    const int p_nhs = 2;
-    const int p_fixed = p_nhs * halo_stage + 1024;
-    int p_bs = (200 * 1024 - p_fixed) / (BN * 128);
-    if (p_bs > kHaloMaxBStages) p_bs = kHaloMaxBStages;
-    const int steps_all = nchunks * d->ntaps;
-    if (p_bs > steps_all && steps_all >= 2) p_bs = steps_all;
-    if (p_bs >= 2) {
-      const int p_smem = p_fixed + p_bs * BN * 128;
+    if (take && p_bs >= (ws_fits ? 1 : 2)) {
+      static int attr_p = 0;   // largest dynamic-smem limit set so far on conv_halo_persist_kernel<BN>
       if (p_smem > attr_p) {
         cudaError_t e = cudaFuncSetAttribute(conv_halo_persist_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, p_smem);
         if (e != cudaSuccess) return cis_set_cuda_error(e, "cudaFuncSetAttribute(conv_halo_persist)");
@@ -1614,13 +1646,14 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
       }
       const int want = AS * d->MT * BN;
       const int tcols = want <= 32 ? 32 : want <= 64 ? 64 : want <= 128 ? 128 : want <= 256 ? 256 : 512;
-      int cps = (227 * 1024) / (p_smem + 1024);
+      int cps = (227 * 1024) / (p_smem + 1024);          // co-resident persistent CTAs per SM: shared memory, TMEM columns, threads
       if (cps > 512 / tcols) cps = 512 / tcols;
-      if (cps > 4) cps = 4;
+      if (cps > 2048 / kPThreads) cps = 2048 / kPThreads;
+      if (cps > 2) cps = 2;
       if (cps < 1) cps = 1;
-      int g = tiles * d->N;
-      if (g > 148 * cps) g = 148 * cps;
-      cudaError_t le = launch_pdl(conv_halo_persist_kernel<BN>, dim3(g), dim3(kPThreads), p_smem, st, *d, halo_stage, p_bs, p_nhs, AS, maps, 0);
+      int g = total < 148 * cps ? total : 148 * cps;
+      cudaError_t le = launch_pdl(conv_halo_persist_kernel<BN>, dim3(g), dim3(kPThreads), p_smem, st, *d, halo_stage, p_bs, p_nhs, AS, G, maps,
+                                  ws_fits ? 1 : 0);
       if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_halo_persist)");
       return cis_check_launch("conv_halo_persist");
     }

@@ -252,14 +252,18 @@ def _pow2_cols(c):
 # split-K of launches that cover only a few SMs.  0 = off (default; the single-launch mode measured slower in r01),
 # 1 = single launch, last-arriving CTA reduces (deterministic ticket), 2 = two launches: partial slices + a parallel finish kernel
 # (written after r01's GPU budget was spent: compiled, covered by tests/test_conv_engine_gpu.py, not yet timed -- DESIGN.md section 6 E2)
-SPLITK = int(os.environ.get('CIS_SPLITK', '0'))
-SPLITK_MAX = int(os.environ.get('CIS_SPLITK_MAX', '4'))
+SPLITK = int(os.environ.get('CIS_SPLITK', '2'))
+SPLITK_MAX = int(os.environ.get('CIS_SPLITK_MAX', '16'))
 SPLITK_NCTA = int(os.environ.get('CIS_SPLITK_NCTA', '64'))          # only launches with at most this many CTAs are split
-SPLITK_MIN_UNITS = int(os.environ.get('CIS_SPLITK_MIN_UNITS', '0'))  # ... and at least this many serial pipeline steps per CTA
+SPLITK_MIN_UNITS = int(os.environ.get('CIS_SPLITK_MIN_UNITS', '18'))  # ... and at least this many serial pipeline steps per CTA
 # experiment switch (default off = current behaviour): stride-1 layers whose padded input width is <= this many channels and that
 # have >= 16 taps (generator conv1 5x5x8, recover flow1 5x5) use the K-dense gather kernel (ceil(taps*cin8/64) pipeline steps)
 # instead of the halo kernel (one step and one mostly-zero BN x 128 B weight tile per tap); see DESIGN.md section 6, E1
 HALO_SKIP_THIN = int(os.environ.get('CIS_HALO_SKIP_THIN', '0'))
+# smallest useful fraction of a launch's 16x8 output tiles for the halo kernel to take a stride-1 layer (below it: the K-dense gather
+# kernel).  Low-resolution maps (6x10, 8x14, 4x7) only fill 20-45 % of their tiles, but the gather kernel's cp.async producers cost
+# ~1450 clk per 64-wide K block against ~400 clk per 3-tap stage of the halo kernel (CIS_TRACE build, r02)
+HALO_MIN_UTIL = float(os.environ.get('CIS_HALO_MIN_UTIL', '0.2'))
 
 
 def setup_splitk(d, device, keep):
@@ -328,7 +332,7 @@ def setup_halo(d, taps, dil, n_tiles):
             continue
         tiles_y = -(-Hp0 // (16 * MT))
         util = (Hp0 * Wp0) / float(tiles_y * 16 * MT * tiles_x * 8)
-        if util < 0.5:
+        if util < (HALO_MIN_UTIL if dil == 1 else 0.5):      # dilated phases: no TMA halo path, d*d times the CTAs -> keep the old rule
             continue
         ncta = d.N * dil * dil * tiles_x * tiles_y * n_tiles
         cps = max(1, min((225 * 1024) // smem, 512 // _pow2_cols(MT * d.BN), 6))
@@ -340,7 +344,7 @@ def setup_halo(d, taps, dil, n_tiles):
         cost = -(-ncta // (NUM_SMS * cps)) * cps * t_cta / min(cps, max(1.0, ncta / float(NUM_SMS)))
         if best is None or cost < best[0] - 1e-9:
             best = (cost, MT, util)
-    if best is None or best[2] < 0.5:
+    if best is None:
         return False
     d.halo, d.dil, d.MT, d.hoy, d.hox, d.ey, d.ex = 1, dil, best[1], hoy, hox, ey, ex
     _fill_taps(d, rel)

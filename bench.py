@@ -224,8 +224,10 @@ def run_ours(args):
 
     def dev_step(_):
         cnt[0] += 1
-        g.train_step('R' if (cnt[0] % (cfg.iters_rec + cfg.iters_gen)) < cfg.iters_rec else 'G', allreduce=ar, use_graph=True)
+        g.train_step('R' if (cnt[0] % (cfg.iters_rec + cfg.iters_gen)) < cfg.iters_rec else 'G', allreduce=ar, use_graph=True, pipeline=PIPE)
     ar = L._allreduce()
+    from unsupervised_detection_b200.models import adversarial_learner as AL
+    PIPE = AL.PIPELINE          # cross-step software pipeline of the frozen flow network (CIS_PIPELINE=0 turns it off)
     for i in range(Wm):
         dev_step(i)
     smp = ClockSampler(L.local_rank)
@@ -246,8 +248,8 @@ def run_ours(args):
             by_kind = {}
             for mode in ('R', 'G'):
                 for _ in range(3):
-                    g.train_step(mode, allreduce=None, use_graph=True)
-                by_kind['recover' if mode == 'R' else 'generator'] = timed(lambda i, m=mode: g.train_step(m, allreduce=None, use_graph=True), 8) / 8
+                    g.train_step(mode, allreduce=None, use_graph=True, pipeline=PIPE)
+                by_kind['recover' if mode == 'R' else 'generator'] = timed(lambda i, m=mode: g.train_step(m, allreduce=None, use_graph=True, pipeline=PIPE), 8) / 8
         except Exception:
             by_kind = None
     gb = BPG * world
@@ -277,7 +279,8 @@ def run_ours(args):
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
             'config': {'workload': WORKLOAD_TRAIN,
                        'global_batch': gb, 'parallelism': 'dp%d' % world, 'l2': 'per-step working set (activations) exceeds the 126 MB L2',
-                       'cuda_graph': True, 'ms_per_step_by_kind': by_kind},
+                       'cuda_graph': True, 'ms_per_step_by_kind': by_kind,
+                       'flow_net_pipelined': bool(PIPE)},
             'e2e': {'value': e2e, 'unit': 'frame-pairs/s', 'h2d_bytes_per_step': 2 * BPG * 384 * 640 * 3 * 4, 'd2h_bytes_per_step': 32,
                     'ms_per_step': ms_e2e / K},
             'gpu_launches': launches,

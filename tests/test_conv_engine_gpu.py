@@ -131,9 +131,6 @@ def test_conv_engine_weight_stationary_persistent(case):
 WGH_CASES = [CASES[0], CASES[1], CASES[2], CASES[4], CASES[6], CASES[7], CASES[11], CASES[12], CASES[14], CASES[16], CASES[17], CASES[18]]
 
 
-@pytest.mark.skipif(os.environ.get('CIS_TEST_EXPERIMENTAL') != '1',
-                    reason='halo-resident wgrad kernel was written after the GPU budget of round 1 was spent: compiled but never run; '
-                           'run tools/umma_probe_mn first, then set CIS_TEST_EXPERIMENTAL=1 to validate it before CIS_WGRAD_HALO=1')
 @pytest.mark.parametrize('case', WGH_CASES, ids=lambda c: 'k%d_d%d_c%s_o%d' % (c['k'], c.get('dil', 1), '+'.join(map(str, c['cins'])), c['cout']))
 def test_conv_engine_halo_wgrad(case):
     """CisWgrad.tma = 2 (engine.WGRAD_HALO): swapped, halo-resident weight gradient; same tolerance as the default kernels."""

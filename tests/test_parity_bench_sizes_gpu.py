@@ -276,3 +276,42 @@ def test_two_identical_steps_give_bit_identical_weights():
     REPORT['determinism_128x192_b2'] = dict(differing_tensors=diff)
     _dump()
     assert not diff, diff[:5]
+
+
+def test_pipelined_flow_network_schedule_is_bit_identical_to_the_sequential_one():
+    """train_step(pipeline=True) runs the frozen PWC-Net for the NEXT batch on a second stream while the current batch trains; only the
+    schedule changes, so a run of alternating steps over a sequence of batches ends with bit-identical parameters and losses."""
+    gen = torch.Generator().manual_seed(21)
+    B, H, W, ph, pw = 2, 64, 96, 128, 192
+    p = OP.make_params(seed=9, jitter=0.1)
+    batches = []
+    for _ in range(6):
+        a = smooth(B, ph, pw, 3, 0.25, gen).clamp(-0.5, 0.5)
+        b = torch.roll(a, shifts=(1, 2), dims=(1, 2)) + 0.01 * torch.randn(B, ph, pw, 3, generator=gen)
+        batches.append((a.cuda(), b.cuda()))
+    modes = 'GGRGG'
+    out = []
+    for pipelined in (False, True):
+        g = CISGraph(H, W, B, with_pwc=True, pwc_hw=(ph, pw))
+        g.load_params(p)
+        losses = []
+        if pipelined:
+            g.img1.copy_(batches[0][0])
+            g.img2.copy_(batches[0][1])
+            g.prime_pipeline()
+        for t, mode in enumerate(modes):
+            nxt = batches[t + 1] if pipelined else batches[t]
+            if pipelined:
+                torch.cuda.current_stream().wait_event(g.pipeline_inputs_free())
+            g.img1.copy_(nxt[0])
+            g.img2.copy_(nxt[1])
+            ready = torch.cuda.Event()
+            ready.record()
+            g.train_step(mode, use_graph=True, pipeline=pipelined, inputs_ready=ready)
+            torch.cuda.synchronize()
+            losses.append(g.losses())
+        g.pipeline_drain()
+        out.append(({k: v.cpu() for k, v in g.export_params().items()}, losses))
+    assert out[0][1] == out[1][1], (out[0][1], out[1][1])
+    diff = [k for k in out[0][0] if not torch.equal(out[0][0][k], out[1][0][k])]
+    assert not diff, diff[:5]

@@ -36,10 +36,13 @@ def _check_conv(d):
         assert 2 * ((hp * 128 + 1023) // 1024 * 1024) + hp * 4 + 1024 + d.BN * 128 <= 227 * 1024      # at least one weight stage fits
         hp0, wp0 = -(-d.OH // d.dil), -(-d.OW // d.dil)
         util = hp0 * wp0 / float((-(-hp0 // (16 * d.MT))) * 16 * d.MT * (-(-wp0 // 8)) * 8)
-        assert util >= 0.5
+        assert util >= (0.2 if d.dil == 1 else 0.5)               # engine.HALO_MIN_UTIL; dilated phases keep the old rule
         for t in range(d.ntaps):
             assert 0 <= d.dh[t] <= d.ey and 0 <= d.dw[t] <= d.ex                                   # taps are halo-relative
-    assert d.splits in (0, 1)                                                                      # split-K is off by default
+    if d.splits > 1:                                  # two-launch split-K (default): private slices, no ticket counters, every split owns work
+        assert d.sk_scratch and not d.sk_counters and 2 <= d.splits <= 16
+        units = -(-chunks // 8) if d.halo else d.K_pad // 64
+        assert (d.splits - 1) * (-(-units // d.splits)) < units
 
 
 def test_every_conv_descriptor_is_launchable(graph):
@@ -54,7 +57,7 @@ def test_every_conv_descriptor_is_launchable(graph):
             if name != 'cis_conv_wgrad':
                 continue
             w = a[0]._obj
-            assert w.Cout <= 128 and w.K_pad % 64 == 0 and w.splits >= 1 and w.g and w.dwp and w.tma in (0, 1)
+            assert w.Cout <= 128 and w.K_pad % 64 == 0 and w.splits >= 1 and w.g and w.dwp and w.tma in (0, 1, 2)
             assert lane == 1                                                                       # weight gradients run on the side lane
             if w.tma:
                 assert w.sh == 1 and all(w.src[i].chunks % 8 == 0 for i in range(w.nsrc - 1))
@@ -74,9 +77,11 @@ def test_plan_bookkeeping(graph):
 
 
 def test_experiment_switches_change_only_what_they_claim(monkeypatch):
-    """Two-launch split-K and the thin-layer switch are planner decisions: preview them without a GPU."""
+    """Two-launch split-K (on by default) and the thin-layer switch are planner decisions: preview them without a GPU."""
+    monkeypatch.setattr(engine, 'SPLITK', 0)
     base = CISGraph(64, 96, 1, device='cpu', global_batch=1)
     nbase = base.fwd.count()
+    assert not [d for d in _convs(base.fwd) if d.splits > 1]
     monkeypatch.setattr(engine, 'SPLITK', 2)
     monkeypatch.setattr(engine, 'SPLITK_MAX', 16)
     monkeypatch.setattr(engine, 'SPLITK_NCTA', 8)

@@ -29,11 +29,13 @@ SIDE_STREAM = True
 _SIDE = {}
 
 
-def _side_stream(device):
-    key = str(device)
-    if key not in _SIDE:
-        _SIDE[key] = torch.cuda.Stream(device=device)
-    return _SIDE[key]
+def _side_stream(device, key=0):
+    """Side lane of a plan replay.  `key` gives concurrently replayed plans (the pipelined PWC-Net branch) their own lane so the two
+    branches do not serialise on one helper stream."""
+    k = (str(device), key)
+    if k not in _SIDE:
+        _SIDE[k] = torch.cuda.Stream(device=device)
+    return _SIDE[k]
 
 
 class Plan(object):
@@ -58,7 +60,7 @@ class Plan(object):
         """Main lane waits for everything issued on the side lane so far."""
         self.ops.append((None, None, 'join', 0.0, 0))
 
-    def run(self, stream=None):
+    def run(self, stream=None, lane_key=0):
         """Lane 0 = the current stream; lane 1 = a side stream forked/joined with events (weight-gradient GEMMs run there,
         concurrently with the data-gradient chain).  Works eagerly and under CUDA-graph capture."""
         if stream is not None or not SIDE_STREAM or not any(op[4] for op in self.ops):
@@ -73,7 +75,7 @@ class Plan(object):
                         _lib.check(rc, name)
             return
         main = torch.cuda.current_stream()
-        side = _side_stream(main.device)
+        side = _side_stream(main.device, lane_key)
         st0, st1 = main.cuda_stream, side.cuda_stream
         main_ahead, side_used = True, False
         for fn, args, name, _, lane in self.ops:
@@ -222,7 +224,7 @@ MATERIALIZE_MISALIGNED_CONCAT = True
 
 
 WGRAD_CTAS_PER_SM = int(os.environ.get('CIS_WGRAD_CTAS_PER_SM', '4'))   # split-K target: CTAs per SM of one weight-gradient launch
-WGRAD_HALO = os.environ.get('CIS_WGRAD_HALO', '0') == '1'   # experimental halo-resident swapped wgrad kernel (CisWgrad.tma = 2), off
+WGRAD_HALO = os.environ.get('CIS_WGRAD_HALO', '1') == '1'   # halo-resident swapped wgrad kernel (CisWgrad.tma = 2) where it fits
 
 
 def wgrad_halo_fits(taps, cout, stride):
@@ -694,7 +696,8 @@ class Builder(object):
                 # TMA operand path (8x8 pixel tiles) for stride-1 layers whose concat sources are 64-channel aligned
                 layer.wg_tma = bool(WGRAD_TMA and layer.stride == 1 and len(layer.in_chanmap) >= 32 and
                                     all(s_.C8 % 64 == 0 for s_ in srcs[:-1]))   # thin inputs: per-tap 64-channel padding would waste the loads
-                layer.wg_halo = bool(WGRAD_HALO and wgrad_halo_fits(taps, layer.cout, layer.stride) and
+                # (thin inputs are excluded like for the TMA path: every tap is padded to a 64-channel column group there)
+                layer.wg_halo = bool(WGRAD_HALO and len(layer.in_chanmap) >= 32 and wgrad_halo_fits(taps, layer.cout, layer.stride) and
                                      all(s_.C8 % 64 == 0 for s_ in srcs[:-1]))
                 if layer.wg_tma or layer.wg_halo:
                     cin8 = len(layer.in_chanmap)

@@ -21,6 +21,10 @@ from .. import checkpoint as ckpt_io
 from .utils.general_utils import compute_all_IoU
 
 
+# CIS_PIPELINE=0 disables the cross-step software pipeline of the frozen flow network (see CISGraph.train_step)
+PIPELINE = os.environ.get('CIS_PIPELINE', '1') != '0'
+
+
 def _dist():
     import torch.distributed as dist
     return dist if (dist.is_available() and dist.is_initialized()) else None
@@ -204,6 +208,7 @@ class AdversarialLearner(object):
     def feed(self, img1, img2):
         """Host -> device copy of one batch of frame pairs [B,384,640,3] fp32 (pinned host tensors copy asynchronously)."""
         g = self.graph
+        g.pipeline_drain()          # a pipelined flow-network branch may still be reading img1 / img2
         st = getattr(self, '_staged', None)
         if st is not None and st[0] is img1:
             # this batch was prefetched on the copy stream while the previous step was computing: device-to-device hand-over
@@ -250,12 +255,33 @@ class AdversarialLearner(object):
         mode = 'R' if (step % sum_iters) < cfg.iters_rec else 'G'              # :386-389
         if batch is None:
             batch = self.reader.batch(self.local_batch)
-        self.feed(batch[0], batch[1])
         summarize = summarize and step % cfg.summary_freq == 0                 # :391-394 (same decision on every rank)
-        other_grads = self._summary_prepass(mode) if summarize else None
-        self.graph.train_step(mode, allreduce=self._allreduce(), use_graph=use_graph)
-        if next_batch is not None:
-            self.prefetch(next_batch)          # overlaps this step's kernels; consumed by the next step() call
+        g = self.graph
+        if use_graph and next_batch is not None and not summarize and PIPELINE:
+            # Software pipeline over steps: PWC-Net (frozen, parameter-independent) runs for `next_batch` on a second stream while
+            # this step trains on `batch`, whose flow the previous call already left in the stage buffers.
+            if getattr(self, '_pipe_for', None) is not batch[0] or not getattr(g, '_stage_valid', False):
+                self.feed(batch[0], batch[1])
+                g.prime_pipeline()
+            if getattr(self, '_copy_stream', None) is None:
+                self._copy_stream = torch.cuda.Stream()
+            cs = self._copy_stream
+            cs.wait_event(g.pipeline_inputs_free())          # the flow network of `batch` has finished reading img1 / img2
+            with torch.cuda.stream(cs):
+                g.img1.copy_(next_batch[0], non_blocking=True)
+                g.img2.copy_(next_batch[1], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(cs)
+            g.train_step(mode, allreduce=self._allreduce(), use_graph=True, pipeline=True, inputs_ready=ready)
+            self._pipe_for, self._staged = next_batch[0], None
+            other_grads = None
+        else:
+            self._pipe_for = None
+            self.feed(batch[0], batch[1])
+            other_grads = self._summary_prepass(mode) if summarize else None
+            g.train_step(mode, allreduce=self._allreduce(), use_graph=use_graph)
+            if next_batch is not None:
+                self.prefetch(next_batch)          # overlaps this step's kernels; consumed by the next step() call
         res = {"global_step": self.global_step, "train_op": mode}
         fetch = fetch_losses if fetch_losses is not None else (step % cfg.summary_freq == 0)
         if fetch or summarize:

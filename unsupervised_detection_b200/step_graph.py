@@ -53,10 +53,17 @@ class CISGraph(object):
             self.pwc.build(bld, i1, i2, self.flow_full)
         self.image = f32(B, H, W, 3)
         self.flow = f32(B, H, W, 2)
+        self._pwc_ops = 0
         if with_pwc:
-            # adversarial_learner.py:87-97: legacy bilinear to (H,W); flow / flow_normalizer
-            P.add('cis_resize_bilinear_f32', self.img1.data_ptr(), B, ph, pw, 3, self.image.data_ptr(), H, W, 1.0)
-            P.add('cis_resize_bilinear_f32', self.flow_full.data_ptr(), B, ph, pw, 2, self.flow.data_ptr(), H, W, 1.0 / flow_normalizer)
+            # adversarial_learner.py:87-97: legacy bilinear to (H,W); flow / flow_normalizer.  The frozen flow network writes its
+            # results to STAGE buffers; the two small device copies below hand them to the trainable part.  That split is what lets
+            # train_step(pipeline=True) run PWC-Net for the NEXT batch on a second stream while this batch trains (the flow network
+            # has no dependency on the parameters being trained).
+            self.image_st, self.flow_st = f32(B, H, W, 3), f32(B, H, W, 2)
+            P.add('cis_resize_bilinear_f32', self.img1.data_ptr(), B, ph, pw, 3, self.image_st.data_ptr(), H, W, 1.0)
+            P.add('cis_resize_bilinear_f32', self.flow_full.data_ptr(), B, ph, pw, 2, self.flow_st.data_ptr(), H, W, 1.0 / flow_normalizer)
+            self._pwc_ops = len(P.ops)                  # fwd.ops[:_pwc_ops] = everything that depends only on the frame pair
+            P.add_py(self._take_stage, 'take_stage')
         self.stats = torch.zeros(B, 4, dtype=torch.float64, device=device)
         self.gen_in = Act(B, H, W, 5, device, name='gen_in')
         self.img8 = Act(B, H, W, 3, device, name='img8')
@@ -193,6 +200,8 @@ class CISGraph(object):
 
     def forward(self):
         self._ensure_packed()
+        self.pipeline_drain()
+        self._stage_valid = False
         self.fwd.run()
 
     def forward_masks(self, use_graph=False):
@@ -200,6 +209,8 @@ class CISGraph(object):
         the reference's multi-crop test graph, adversarial_learner.py:525-592, builds nothing else).  use_graph replays it as one
         CUDA graph."""
         self._ensure_packed()
+        self.pipeline_drain()
+        self._stage_valid = False
         if getattr(self, '_mask_plan', None) is None:
             i0, i1, i2 = self._mask_ops
             mp = Plan('fwd_masks')
@@ -224,12 +235,28 @@ class CISGraph(object):
             self.graphs['masks'] = g
         g.replay()
 
+    def _take_stage(self):
+        self.image.copy_(self.image_st, non_blocking=True)
+        self.flow.copy_(self.flow_st, non_blocking=True)
+
     def launches_per_step(self, mode):
         return self.fwd.count() + self.bwd[mode].count() + self.adam[mode].count() + self._pack_of(mode).count()
 
-    def train_step(self, mode, allreduce=None, use_graph=False):
-        """One alternating step body (adversarial_learner.py:380-397): mode 'R' = train_recover_op, 'G' = train_generator_op."""
+    def train_step(self, mode, allreduce=None, use_graph=False, pipeline=False, inputs_ready=None):
+        """One alternating step body (adversarial_learner.py:380-397): mode 'R' = train_recover_op, 'G' = train_generator_op.
+
+        pipeline=True (CUDA graphs only): software pipeline over steps.  The step trains on the (image, flow) pair that the PREVIOUS
+        call's side branch left in the stage buffers and, concurrently on a second stream, runs the frozen PWC-Net on the frame
+        pair currently in self.img1 / self.img2 -- the NEXT batch -- for the next call.  `inputs_ready`: an event after which
+        img1 / img2 hold that next batch (the host-to-device copy).  The first pipelined call primes the stage from img1 / img2.
+        Results are identical to the sequential order; only the schedule changes."""
         self._ensure_packed()
+        if use_graph and pipeline and self.with_pwc:
+            return self._train_step_pipelined(mode, allreduce, inputs_ready)
+        if inputs_ready is not None:
+            torch.cuda.current_stream().wait_event(inputs_ready)
+        self.pipeline_drain()
+        self._stage_valid = False
         if use_graph:
             g = self.graphs.get(mode)
             if g is None:
@@ -247,21 +274,95 @@ class CISGraph(object):
         self._pack_of(mode).run()      # only the updated network's bf16 operands are re-packed
 
     def _capture(self, mode):
-        torch.cuda.synchronize()
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            # warm-up outside capture (sets function attributes, lazy allocations); does not touch the parameters
-            self.fwd.run(); self.bwd[mode].run(); self._pack_of(mode).run()
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
-        g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1):
-            self.fwd.run(); self.bwd[mode].run()
-        with torch.cuda.graph(g2):
-            self.adam[mode].run(); self._pack_of(mode).run()
+        g1 = self._capture_plans('seq_fwd_bwd_' + mode, [self.fwd, self.bwd[mode]])
+        g2 = self._capture_plans('seq_adam_' + mode, [self.adam[mode], self._pack_of(mode)], warm=False)
         self.graphs[mode] = (g1, g2)
         return self.graphs[mode]
+
+    def _sub_plan(self, lo, hi, name):
+        sp = Plan(name)
+        sp.ops = self.fwd.ops[lo:hi]
+        sp.keep = self.fwd.keep
+        return sp
+
+    def _capture_plans(self, key, plans, lane_key=0, warm=True):
+        """One CUDA graph of `plans`.  warm: run them once outside capture first (sets function attributes, lazy allocations) -- never
+        for plans that change state (the optimiser step)."""
+        g = self.graphs.get(key)
+        if g is None:
+            torch.cuda.synchronize()
+            if warm:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    for pl in plans:
+                        pl.run(lane_key=lane_key)
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for pl in plans:
+                    pl.run(lane_key=lane_key)
+            self.graphs[key] = g
+        return g
+
+    def _pipe_state(self):
+        if getattr(self, '_pipe', None) is None:
+            k = self._pwc_ops
+            self._pipe = dict(stream=torch.cuda.Stream(), done=None, free=None, pwc=self._sub_plan(0, k, 'fwd_pwc'),
+                              rest=self._sub_plan(k + 1, len(self.fwd.ops), 'fwd_rest'))
+        return self._pipe
+
+    def prime_pipeline(self):
+        """Run the frozen flow network (on the current stream) for the frame pair now in img1 / img2 so that the next
+        train_step(pipeline=True) trains on it.  Needed before the first pipelined step and whenever the stream of batches restarts."""
+        self._ensure_packed()
+        pp = self._pipe_state()
+        self.pipeline_drain()
+        self._capture_plans('pipe_pwc', [pp['pwc']], lane_key=1).replay()
+        pp['done'] = None
+        pp['free'] = torch.cuda.Event()
+        pp['free'].record(torch.cuda.current_stream())
+        self._stage_valid = True
+
+    def pipeline_inputs_free(self):
+        """Event after which img1 / img2 may be overwritten with the next frame pair (the flow network last reading them is done)."""
+        pp = self._pipe_state()
+        return pp['done'] if pp['done'] is not None else pp['free']
+
+    def _train_step_pipelined(self, mode, allreduce, inputs_ready):
+        pp = self._pipe_state()
+        main, side = torch.cuda.current_stream(), pp['stream']
+        g_pwc = self._capture_plans('pipe_pwc', [pp['pwc']], lane_key=1)
+        g_rest = self._capture_plans('pipe_rest_' + mode, [pp['rest'], self.bwd[mode]])
+        g_adam = self._capture_plans('pipe_adam_' + mode, [self.adam[mode], self._pack_of(mode)], warm=False)
+        if not getattr(self, '_stage_valid', False):
+            # prime: the stage must hold the flow of the batch this call trains on (= what img1 / img2 hold right now)
+            if inputs_ready is not None:
+                main.wait_event(inputs_ready)
+            self.prime_pipeline()
+        if pp['done'] is not None:
+            main.wait_event(pp['done'])              # the previous call's side branch filled the stage
+        self._take_stage()
+        taken = torch.cuda.Event()
+        taken.record(main)
+        side.wait_event(taken)                       # stage and level buffers are free again
+        if inputs_ready is not None:
+            side.wait_event(inputs_ready)
+        with torch.cuda.stream(side):
+            g_pwc.replay()                           # PWC-Net on the NEXT batch, concurrent with everything below
+            pp['done'] = torch.cuda.Event()
+            pp['done'].record(side)
+        g_rest.replay()
+        if allreduce is not None:
+            allreduce((self.rec_store if mode == 'R' else self.gen_store).grad)
+        g_adam.replay()
+
+    def pipeline_drain(self):
+        """Join the side branch (call before reading PWC-Net outputs or re-feeding img1 / img2 outside train_step)."""
+        pp = getattr(self, '_pipe', None)
+        if pp is not None and pp['done'] is not None:
+            torch.cuda.current_stream().wait_event(pp['done'])
 
     def losses(self, full=False, reduce=None):
         """The `losses` dict of adversarial_learner.py:196-204 (device -> host read).  full=True adds the four first-sample

@@ -75,13 +75,13 @@ typedef struct {
   int32_t MT;        /* 1..4 stacked M tiles (MT*BN <= 512 TMEM columns) */
   int32_t hoy, hox;  /* halo origin relative to the tile origin (phase units, <= 0) */
   int32_t ey, ex;    /* halo extent beyond the tile (max tap offset) */
-  /* split-K for launches that would otherwise occupy a handful of SMs: grid.z = splits CTAs share one output tile; each writes
-   * its partial fp32 tile to a private slice of sk_scratch, the last CTA to arrive (ticket in sk_counters) sums the slices in a
-   * fixed order (deterministic), applies the epilogue and resets the ticket. */
+  /* Split-K for launches that cover only a few SMs (low-resolution layers): grid.z = splits CTAs share one output tile, each reduces a
+   * range of the K loop (64-wide K blocks for the gather kernel, 64-channel chunks for the halo kernel) and stores its partial fp32
+   * tile to a private slice of sk_scratch; a second kernel launched by the same call sums the slices in a fixed order
+   * (deterministic) and runs the fused epilogue spread over many CTAs. */
   int32_t splits;        /* 0/1 = off */
   float* sk_scratch;     /* >= tiles * splits * 128 * BN floats (tiles = grid.x * grid.y * MT); need not be initialised */
-  int32_t* sk_counters;  /* zero-initialised, >= grid.x * grid.y ints; NULL = two-launch mode: the conv kernel only writes the slices and
-                          * a second (parallel) kernel launched by the same call sums them in the same fixed order + runs the epilogue */
+  int32_t* sk_counters;  /* must be NULL (the single-launch ticket mode of round 1 was removed; the field keeps the struct layout) */
 } CisConv;
 
 /* Weight gradient of the same convolution: dWp[co][(t,c)] = sum_rows g[row][co] * A[row][(t,c)]  (fp32).  The reduction over rows

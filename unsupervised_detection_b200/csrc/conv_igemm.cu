@@ -40,7 +40,9 @@ static constexpr int kBM = 128;       // GEMM rows per CTA
 static constexpr int kBK = 64;        // bf16 K elements per stage (128-byte swizzled rows)
 static constexpr int kAStage = kBM * 128;
 static constexpr int kProducerThreads = 128;
-static constexpr int kThreads = 160;  // 4 producer/epilogue warps + 1 MMA warp
+static constexpr int kThreads = 160;  // halo / wgrad kernels: 4 producer/epilogue warps + 1 MMA warp
+static constexpr int kGProducers = 256;   // gather kernel: 8 producer/epilogue warps (its cp.async address arithmetic is the bottleneck)
+static constexpr int kGThreads = 288;     // + 1 MMA warp
 
 struct SrcS {
   const __nv_bfloat16* ptr;
@@ -211,31 +213,29 @@ __device__ __forceinline__ void epi_group(const CisConv& p, const uint32_t taddr
     }
   }
 }
-// all BN columns of one row, in groups of at most 64 columns (register budget)
+// columns [c_lo, c_hi) of one row (multiples of 16), in groups of 32 columns (register budget); sbias: the BN columns of THIS n-tile
+template <int BN>
+__device__ __forceinline__ void epi_cols(const CisConv& p, const uint32_t t_row, const int cbase, const size_t dpix, const bool valid,
+                                         const float* __restrict__ sbias, const int c_lo, const int c_hi) {
+  int c0 = c_lo;
+#pragma unroll 1
+  for (; c0 + 32 <= c_hi; c0 += 32) epi_group<2>(p, t_row + c0, cbase + c0, dpix, valid, sbias + c0);
+  if (c0 < c_hi) epi_group<1>(p, t_row + c0, cbase + c0, dpix, valid, sbias + c0);
+}
+// all BN columns of one row
 template <int BN>
 __device__ __forceinline__ void epi_row(const CisConv& p, const uint32_t t_row, const int cbase, const size_t dpix, const bool valid,
                                         const float* __restrict__ sbias) {
-  if constexpr (BN >= 32) {
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) epi_group<2>(p, t_row + c0, cbase + c0, dpix, valid, sbias + c0);   // sbias: the BN columns of THIS n-tile
-  } else {
-    epi_group<1>(p, t_row, cbase, dpix, valid, sbias);
-  }
+  epi_cols<BN>(p, t_row, cbase, dpix, valid, sbias, 0, BN);
 }
 
-// ---- split-K fix-up (single launch): every CTA of a tile adds its partial accumulator to a zero-initialised fp32 scratch tile,
-// takes a ticket, and the last one reads the full sums back (re-zeroing scratch and ticket for the next launch).
-__device__ __forceinline__ void named_bar_sync_128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-__device__ __forceinline__ float ld_cg(const float* p) {
-  float v;
-  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-  return v;
-}
+// ---- split-K (two launches): every CTA of a tile stores its partial accumulator to a private fp32 slice; splitk_finish_kernel sums the
+// slices in a fixed order and runs the fused epilogue.
 template <int BN>
-__device__ __forceinline__ void splitk_store_partial(float* slice, uint32_t t_row, int row) {
+__device__ __forceinline__ void splitk_store_partial(float* slice, uint32_t t_row, int row, int c_lo = 0, int c_hi = BN) {
   // slice = this split's private [128][BN] fp32 tile: plain 16-byte stores, no atomics, fixed summation order later
 #pragma unroll 1
-  for (int c0 = 0; c0 < BN; c0 += 16) {
+  for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
     float v[16];
     tmem_ld16(t_row + c0, v);
     float4* o = reinterpret_cast<float4*>(slice + (size_t)row * BN + c0);
@@ -277,17 +277,6 @@ __device__ __forceinline__ void splitk_reduce16(const float* tile0, int nsplit, 
     }
   }
 }
-// returns true for the last-arriving CTA of the tile (uniform over the 128 epilogue threads)
-__device__ __forceinline__ bool splitk_ticket(int* counter, int splits, int tid, int* s_flag) {
-  __threadfence();
-  named_bar_sync_128();
-  if (tid == 0) *s_flag = (atomicAdd(counter, 1) == splits - 1) ? 1 : 0;
-  named_bar_sync_128();
-  const bool last = *s_flag != 0;
-  if (last) __threadfence();
-  return last;
-}
-
 template <int BN>
 struct FwdCfg {
   static constexpr int kStages = (BN == 128) ? 3 : 4;
@@ -297,9 +286,10 @@ struct FwdCfg {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_constant__ CisConv p) {
+__global__ void __launch_bounds__(kGThreads) conv_igemm_kernel(const __grid_constant__ CisConv p) {
   using Cfg = FwdCfg<BN>;
   constexpr int S = Cfg::kStages;
+  constexpr int kMmaWarp = kGProducers / 32;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * S + 1];
   __shared__ uint32_t tmem_slot;
@@ -328,7 +318,6 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
   const int kb_lo = blockIdx.z * kper;
   const int nkb = min(kper, nkb_all - kb_lo);     // host guarantees nkb >= 1 for every split
   const int ny = blockIdx.y;
-  __shared__ int s_flag;
   __shared__ __align__(16) float s_bias[BN];
   pdl_launch_dependents();
 
@@ -343,10 +332,10 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
     s_src[tid].chunks = p.src[tid].chunks;
     s_src[tid].n_mod = p.src[tid].n_mod;
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(bar_full + 8 * s, kProducerThreads);
+        mbar_init(bar_full + 8 * s, kGProducers);
         mbar_init(bar_empty + 8 * s, 1);
       }
       mbar_init(bar_accum, 1);
@@ -363,15 +352,15 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
   const uint32_t tmem = tmem_slot;
   if (tid == 0) CIS_TRACE_AT(0);
 
-  if (warp < 4) {
-    // ------------------------------------------------------------------ producers
+  if (warp < kMmaWarp) {
+    // ------------------------------------------------------------------ producers: thread = (16-byte K chunk j, rows rl + 32 i)
     const int j = tid & 7;          // 16-byte chunk within the 128-byte K row
-    const int rl = tid >> 3;        // 0..15
+    const int rl = tid >> 3;        // 0..31
     const uint32_t sw_off = (uint32_t)((j ^ (rl & 7)) << 4);
-    int hb[8], wb[8], nb[8];
+    int hb[4], wb[4], nb[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int g = blockIdx.x * kBM + rl + 16 * i;
+    for (int i = 0; i < 4; ++i) {
+      const int g = blockIdx.x * kBM + rl + 32 * i;
       if (g < M) {
         const int ow = g % p.OW;
         const int t = g / p.OW;
@@ -411,17 +400,21 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
       const int dh = s_dh[t], dw = s_dw[t];
       const uint32_t a_dst = a_base + s * kAStage + rl * 128 + sw_off;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const int h = hb[i] + dh, w = wb[i] + dw;
         const bool ok = kvalid && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
         const int n = nmod ? (nb[i] % nmod) : nb[i];
         const size_t off = ok ? ((size_t)((n * p.H + h) * p.W + w) * pitch + coff) : 0;
-        cp_async16(a_dst + i * 16 * 128, sp + off, ok ? 16u : 0u);
+        cp_async16(a_dst + i * 32 * 128, sp + off, ok ? 16u : 0u);
       }
-      // ---- B: packed weights, rows rl + 16 i
+      // ---- B: packed weights, rows rl + 32 i
       const uint32_t b_dst = b_base + s * Cfg::kBStage + rl * 128 + sw_off;
+      if constexpr (BN >= 32) {
 #pragma unroll
-      for (int i = 0; i < BN / 16; ++i) cp_async16(b_dst + i * 16 * 128, wrow + (size_t)i * 16 * p.K_pad + (kb_lo + kb) * kBK, 16u);
+        for (int i = 0; i < BN / 32; ++i) cp_async16(b_dst + i * 32 * 128, wrow + (size_t)i * 32 * p.K_pad + (kb_lo + kb) * kBK, 16u);
+      } else {
+        if (rl < BN) cp_async16(b_dst, wrow + (kb_lo + kb) * kBK, 16u);
+      }
       cp_async_commit();
       if (kb >= S - 1) {             // publish block kb-(S-1): this thread's copies of it have landed
         cp_async_wait<S - 1>();
@@ -433,11 +426,12 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
     fence_proxy_async();
     for (int kb = nkb > S - 1 ? nkb - (S - 1) : 0; kb < nkb; ++kb) mbar_arrive(bar_full + 8 * (kb % S));
 
-    // ------------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------------ epilogue: warps w and w + 4 share a TMEM lane quarter and split the columns
     mbar_wait(bar_accum, 0);
     tc_fence_after();
     if (tid == 0) CIS_TRACE_AT(2);
-    const int row = warp * 32 + lane;
+    const int qtr = warp & 3, half = warp >> 2;
+    const int row = qtr * 32 + lane;
     const int g = blockIdx.x * kBM + row;
     const bool valid = g < M;
     size_t dpix = 0;
@@ -448,27 +442,20 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
       const int n = t / p.OH;
       dpix = (size_t)(n * p.DH + oh * p.osh + p.oa) * p.DW + ow * p.osw + p.ob;
     }
-    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t t_row = tmem + ((uint32_t)(qtr * 32) << 16);
     const int cbase = ny * BN;
+    constexpr int kHalf = BN >= 32 ? BN / 2 : BN;                 // BN = 16: the first warp group does it all
+    const int c_lo = half * kHalf, c_hi = (BN >= 32 || half == 0) ? c_lo + kHalf : c_lo;
     if (nsplit > 1) {
+      // two-launch split-K: this split's private fp32 slice; splitk_finish_kernel reduces the slices and runs the fused epilogue
       const int tile_id = blockIdx.x * gridDim.y + ny;
       float* tile0 = p.sk_scratch + (size_t)tile_id * nsplit * kBM * BN;
-      splitk_store_partial<BN>(tile0 + (size_t)blockIdx.z * kBM * BN, t_row, row);
-      // sk_counters == NULL: two-launch mode, splitk_finish_kernel reduces the slices and runs the epilogue
-      if (p.sk_counters != nullptr && splitk_ticket(p.sk_counters + tile_id, nsplit, tid, &s_flag)) {
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-          float v[16];
-          splitk_reduce16<BN>(tile0, nsplit, row, c0, v);
-          if (valid) epi_chunk(p, v, cbase + c0, dpix);
-        }
-        if (tid == 0) p.sk_counters[tile_id] = 0;
-      }
+      splitk_store_partial<BN>(tile0 + (size_t)blockIdx.z * kBM * BN, t_row, row, c_lo, c_hi);
     } else {
-      epi_row<BN>(p, t_row, cbase, dpix, valid, s_bias);
+      epi_cols<BN>(p, t_row, cbase, dpix, valid, s_bias, c_lo, c_hi);
     }
   } else {
-    // ------------------------------------------------------------------ MMA issuer (warp 4)
+    // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = make_idesc_bf16(kBM, BN, 0, 0);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % S;
@@ -491,7 +478,7 @@ __global__ void __launch_bounds__(kThreads) conv_igemm_kernel(const __grid_const
   tc_fence_before();
   __syncthreads();
   if (tid == 0) CIS_TRACE_AT(3);
-  if (warp == 4) tmem_dealloc<Cfg::kTmemCols>(tmem);
+  if (warp == kMmaWarp) tmem_dealloc<Cfg::kTmemCols>(tmem);
 }
 
 
@@ -569,7 +556,6 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   const int cc_lo = blockIdx.z * cper;
   const int nchunks = min(cper, nchunks_all - cc_lo);   // chunks handled by this CTA (host guarantees >= 1)
   const int cin8 = m_chunks * 8;
-  __shared__ int s_flag;
   __shared__ __align__(16) float s_bias[BN];
   pdl_launch_dependents();
   const uint32_t ncols = (MT * BN <= 32) ? 32u : (MT * BN <= 64) ? 64u : (MT * BN <= 128) ? 128u : (MT * BN <= 256) ? 256u : 512u;
@@ -712,38 +698,19 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     const int r = warp * 32 + lane;
     const int cbase = ny * BN;
     const int tile_id = blockIdx.x * gridDim.y + ny;
-    bool last = true;
     if (nsplit > 1) {
+      // two-launch split-K: this split's private fp32 slices; splitk_finish_kernel reduces them and runs the fused epilogue
       for (int m = 0; m < MT; ++m)
         splitk_store_partial<BN>(p.sk_scratch + (((size_t)tile_id * MT + m) * nsplit + blockIdx.z) * kBM * BN,
                                  tmem + ((uint32_t)(warp * 32) << 16) + m * BN, r);
-      last = p.sk_counters != nullptr ? splitk_ticket(p.sk_counters + tile_id, nsplit, tid, &s_flag) : false;   // NULL: two-launch mode
-    }
-    if (last) {
+    } else {
       for (int m = 0; m < MT; ++m) {
         const int gy = ty * 16 * MT + 16 * m + (r >> 3), gx = tx * 8 + (r & 7);
         const int oy = pa + d * gy, ox = pb + d * gx;
         const bool valid = oy < p.OH && ox < p.OW;
         const size_t dpix = valid ? ((size_t)(n * p.DH + oy * p.osh + p.oa) * p.DW + ox * p.osw + p.ob) : 0;
-        const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16) + m * BN;
-        const float* tile0 = nsplit > 1 ? p.sk_scratch + ((size_t)tile_id * MT + m) * nsplit * kBM * BN : nullptr;
-        if (nsplit <= 1) {
-          epi_row<BN>(p, t_row, cbase, dpix, valid, s_bias);
-          continue;
-        }
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-          float v[16];
-          if (nsplit > 1) {
-            splitk_reduce16<BN>(tile0, nsplit, r, c0, v);
-          } else {
-            tmem_ld16(t_row + c0, v);
-          }
-          if (!valid) continue;
-          epi_chunk(p, v, cbase + c0, dpix);
-        }
+        epi_row<BN>(p, tmem + ((uint32_t)(warp * 32) << 16) + m * BN, cbase, dpix, valid, s_bias);
       }
-      if (nsplit > 1 && tid == 0) p.sk_counters[tile_id] = 0;
     }
   } else {
     // ------------------------------------------------------------------ MMA issuer
@@ -797,10 +764,10 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
 
 
 // ======================================================================================================= split-K finish
-// Second launch of the two-launch split-K mode (CisConv.sk_counters == NULL).  The single-launch mode lets the last-arriving CTA of
-// a tile read all nsplit x 64 KB slices by itself -- one SM pulling up to 1 MB through L2 -- which costs more than the split saves
-// on the low-resolution layers it is meant for.  Here the reduction + fused epilogue of a tile is spread over 128 * BN/16 threads
-// of several CTAs: thread = (accumulator row, 16-column group), column group fastest so slice reads and NHWC stores coalesce.
+// Second launch of split-K.  (Round 1 let the last-arriving CTA of a tile read all nsplit x 64 KB slices by itself -- one SM pulling up
+// to 1 MB through L2 -- which cost more than the split saved on the low-resolution layers it is meant for.)  Here the reduction + fused
+// epilogue of a tile is spread over 128 * BN/16 threads of several CTAs: thread = (accumulator row, 16-column group), column group
+// fastest so slice reads and NHWC stores coalesce.
 template <int BN>
 __global__ void __launch_bounds__(256) splitk_finish_kernel(const __grid_constant__ CisConv p) {
   constexpr int G = BN / 16;                               // 16-column groups per row
@@ -1463,27 +1430,6 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
-// Same as launch_pdl plus a thread-block-cluster dimension along x.
-template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster_x, Args... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cluster_x;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
-}
-
 template <int BN>
 static cudaError_t launch_splitk_finish(const CisConv* d, dim3 main_grid, cudaStream_t st) {
   constexpr int G = BN / 16;
@@ -1506,12 +1452,12 @@ static int launch_fwd(const CisConv* d, cudaStream_t st) {
   int splits = d->splits > 1 ? d->splits : 1;
   if (splits > 1) {
     const int nkb = d->K_pad / kBK, per = (nkb + splits - 1) / splits;
-    if (!d->sk_scratch || (splits - 1) * per >= nkb) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm: bad split-K setup");
+    if (!d->sk_scratch || d->sk_counters || (splits - 1) * per >= nkb) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm: bad split-K setup");
   }
   dim3 grid((M + kBM - 1) / kBM, d->n_tiles, splits);
-  cudaError_t le = launch_pdl(conv_igemm_kernel<BN>, grid, dim3(kThreads), Cfg::kSmem, st, *d);
+  cudaError_t le = launch_pdl(conv_igemm_kernel<BN>, grid, dim3(kGThreads), Cfg::kSmem, st, *d);
   if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_igemm)");
-  if (splits > 1 && !d->sk_counters) {
+  if (splits > 1) {
     le = launch_splitk_finish<BN>(d, grid, st);
     if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(splitk_finish)");
   }
@@ -1602,7 +1548,7 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   int splits = d->splits > 1 ? d->splits : 1;
   if (splits > 1) {
     const int per = (nchunks + splits - 1) / splits;
-    if (!d->sk_scratch || (splits - 1) * per >= nchunks) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm(halo): bad split-K setup");
+    if (!d->sk_scratch || d->sk_counters || (splits - 1) * per >= nchunks) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm(halo): bad split-K setup");
   }
   dim3 grid(tiles * dd * dd * d->N, d->n_tiles, splits);
   // TMA halo path: undilated, every concat source except the last a multiple of 64 channels (a chunk never straddles sources)
@@ -1660,7 +1606,7 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   }
   cudaError_t le = launch_pdl(conv_halo_kernel<BN>, grid, dim3(kThreads), smem, st, *d, halo_stage, BS, nhs, maps, use_tma, G);
   if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_halo)");
-  if (splits > 1 && !d->sk_counters) {
+  if (splits > 1) {
     le = launch_splitk_finish<BN>(d, grid, st);
     if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(splitk_finish)");
   }

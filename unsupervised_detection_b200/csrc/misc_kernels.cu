@@ -78,18 +78,19 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const int* __
     const int n = (int)(i / K_pad), k = (int)(i % K_pad);
     const int km = kmap[k];
     if (km < 0) return;
-    // fixed-order sum of the private split-K slices; 4 independent loads in flight per thread
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    // fixed-order sum of the private split-K slices; 8 independent loads in flight per thread
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const float* q = dwp + i;
     int s = 0;
-    for (; s + 4 <= nsplit; s += 4) {
-      a0 += __ldcg(q + (size_t)s * nw);
-      a1 += __ldcg(q + (size_t)(s + 1) * nw);
-      a2 += __ldcg(q + (size_t)(s + 2) * nw);
-      a3 += __ldcg(q + (size_t)(s + 3) * nw);
+    for (; s + 8 <= nsplit; s += 8) {
+      float t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = __ldcg(q + (size_t)(s + u) * nw);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += t[u];
     }
-    for (; s < nsplit; ++s) a0 += __ldcg(q + (size_t)s * nw);
-    dw[(size_t)km + n] = (a0 + a1) + (a2 + a3);
+    for (; s < nsplit; ++s) a[0] += __ldcg(q + (size_t)s * nw);
+    dw[(size_t)km + n] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   } else if (colpart != nullptr && i - nw < (size_t)nch) {
     const int c = (int)(i - nw);
     float a = 0.f;

@@ -117,7 +117,7 @@ class Plan(object):
             n += 1
             if name == 'cis_conv_igemm':
                 d = args[0]._obj
-                if d.splits > 1 and not d.sk_counters:
+                if d.splits > 1:
                     n += 1
         return n
 
@@ -223,7 +223,7 @@ WGRAD_TMA = True
 MATERIALIZE_MISALIGNED_CONCAT = True
 
 
-WGRAD_CTAS_PER_SM = int(os.environ.get('CIS_WGRAD_CTAS_PER_SM', '4'))   # split-K target: CTAs per SM of one weight-gradient launch
+WGRAD_CTAS_PER_SM = int(os.environ.get('CIS_WGRAD_CTAS_PER_SM', '2'))   # split-K target: CTAs per SM of one weight-gradient launch
 WGRAD_HALO = os.environ.get('CIS_WGRAD_HALO', '1') == '1'   # halo-resident swapped wgrad kernel (CisWgrad.tma = 2) where it fits
 
 
@@ -251,9 +251,8 @@ def _pow2_cols(c):
     return 1024
 
 
-# split-K of launches that cover only a few SMs.  0 = off (default; the single-launch mode measured slower in r01),
-# 1 = single launch, last-arriving CTA reduces (deterministic ticket), 2 = two launches: partial slices + a parallel finish kernel
-# (written after r01's GPU budget was spent: compiled, covered by tests/test_conv_engine_gpu.py, not yet timed -- DESIGN.md section 6 E2)
+# split-K of launches that cover only a few SMs (low-resolution pyramid levels): 0 = off, 2 = on (two launches: private partial slices +
+# a parallel finish kernel with a fixed summation order; measured r02: -0.4 ms per step)
 SPLITK = int(os.environ.get('CIS_SPLITK', '2'))
 SPLITK_MAX = int(os.environ.get('CIS_SPLITK_MAX', '16'))
 SPLITK_NCTA = int(os.environ.get('CIS_SPLITK_NCTA', '64'))          # only launches with at most this many CTAs are split
@@ -292,13 +291,7 @@ def setup_splitk(d, device, keep):
         return
     sc = torch.empty(ncta * mt * splits * 128 * d.BN, dtype=torch.float32, device=device)
     keep.append(sc)
-    d.splits, d.sk_scratch = splits, sc.data_ptr()
-    if int(SPLITK) == 2:
-        d.sk_counters = None                      # NULL selects the two-launch mode in cis_conv_igemm
-    else:
-        ct = torch.zeros(ncta, dtype=torch.int32, device=device)
-        keep.append(ct)
-        d.sk_counters = ct.data_ptr()
+    d.splits, d.sk_scratch, d.sk_counters = splits, sc.data_ptr(), None
 
 
 def setup_halo(d, taps, dil, n_tiles):

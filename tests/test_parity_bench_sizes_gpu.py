@@ -52,11 +52,20 @@ def mask_checks(m, ref, key):
     band = (ref - 0.1).abs() > 2e-3
     flips = int(((m > 0.1) != (ref > 0.1))[band].sum())
     flips_all = int(((m > 0.1) != (ref > 0.1)).sum())
+    # with random-init weights every mask value sits near 0.5, far from the reference's 0.1 threshold, so the same check is repeated at
+    # the MEDIAN of the oracle mask: half of the pixels are on either side and thousands lie close to the threshold
+    med = float(ref.median())
+    band_m = (ref - med).abs() > 2e-3
+    flips_m = int(((m > med) != (ref > med))[band_m].sum())
     REPORT[key] = dict(mask_mean_abs=mad, mask_max_abs=float((m - ref).abs().max()), threshold_flips_outside_band=flips,
-                       threshold_flips_total=flips_all, pixels=int(ref.numel()), frac_mask_above_thr=float((ref > 0.1).float().mean()))
+                       threshold_flips_total=flips_all, pixels=int(ref.numel()), frac_mask_above_thr=float((ref > 0.1).float().mean()),
+                       median_threshold=med, median_threshold_flips_outside_band=flips_m,
+                       median_threshold_pixels_inside_band=int((~band_m).sum()),
+                       median_threshold_flips_total=int(((m > med) != (ref > med)).sum()))
     _dump()
     assert mad <= 1e-3, mad
     assert flips == 0, flips
+    assert flips_m == 0, flips_m
 
 
 def test_config1_generator_forward_128x224():

@@ -16,6 +16,25 @@ g = L.graph
 for m in ('G', 'R'):
     g.train_step(m)
 torch.cuda.synchronize()
+if os.environ.get('CIS_OPS_JSON'):
+    # conv ops in issue order (what ncu will see, kernel by kernel) with their algorithmic FLOPs: lets tools/ncu_table.py join the launch
+    # list with the layer descriptions
+    import json
+    rows = []
+    for m in os.environ.get('CIS_MODES', 'GR'):
+        for pname, plan in (('fwd', g.fwd), ('bwd' + m, g.bwd[m])):
+            for fn, a, name, fl, lane in plan.ops:
+                if name == 'cis_conv_igemm':
+                    d = a[0]._obj
+                    info = '%s BN%d nt%d MT%d N%d %dx%d taps%d ch%d dil%d sp%d' % ('halo' if d.halo else 'gen', d.BN, d.n_tiles, d.MT, d.N, d.OH, d.OW,
+                                                                               d.ntaps, sum(d.src[k].chunks for k in range(d.nsrc)) * 8, d.dil, d.splits)
+                elif name == 'cis_conv_wgrad':
+                    d = a[0]._obj
+                    info = 'wgrad tma%d N%d %dx%d taps%d cout%d K%d sp%d' % (d.tma, d.N, d.OH, d.OW, d.ntaps, d.Cout, d.K_pad, d.splits)
+                else:
+                    continue
+                rows.append(dict(step=m, plan=pname, op=name, flops=fl, info=info))
+    json.dump(rows, open(os.environ['CIS_OPS_JSON'], 'w'))
 torch.cuda.profiler.start()
 for m in os.environ.get('CIS_MODES', 'GR'):
     g.train_step(m)

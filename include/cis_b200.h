@@ -82,6 +82,12 @@ typedef struct {
   int32_t splits;        /* 0/1 = off */
   float* sk_scratch;     /* >= tiles * splits * 128 * BN floats (tiles = grid.x * grid.y * MT); need not be initialised */
   int32_t* sk_counters;  /* must be NULL (the single-launch ticket mode of round 1 was removed; the field keeps the struct layout) */
+  /* Stride-2 forward convolution on the halo kernel (halo = 1, sh = sw = 1 in this descriptor, H x W = the INPUT size): the input is
+   * read as nph = 4 space-to-depth phases in(2y + py, 2x + px), phase index py*2 + px; taps are listed phase by phase in PHASE
+   * coordinates (dh/dw relative to the halo origin of the phase images) and taps [ph_tap[i], ph_tap[i+1]) belong to phase i.
+   * nph = 0/1: ordinary stride-1 gather. */
+  int32_t nph;
+  int32_t ph_tap[5];
 } CisConv;
 
 /* Weight gradient of the same convolution: dWp[co][(t,c)] = sum_rows g[row][co] * A[row][(t,c)]  (fp32).  The reduction over rows
@@ -160,6 +166,15 @@ int cis_colsum(const void* g, int32_t g_pitch, int32_t g_coff, int64_t npix, int
 /* tf.image.resize_images / resize_bilinear legacy (convolution_utils.py:88, nets.py:108) on a bf16 slice */
 int cis_resize_bilinear_bf16(const void* src, int32_t s_pitch, int32_t s_coff, int32_t N, int32_t H, int32_t W, void* dst,
                              int32_t d_pitch, int32_t d_coff, int32_t OH, int32_t OW, int32_t chunks, cis_stream_t stream);
+/* fused resize + concat of the recover decoder (convolution_utils.py:87-90 feeding nets.py:80-105): up to 4 sources of one resolution
+ * (channel slices, batch-broadcast when n_mod > 0) -> legacy-bilinear to OH x OW -> side by side into one destination slice.
+ * H x W == OH x OW makes it a plain concat copy. */
+int cis_resize_concat_bf16(const CisSrc* srcs, int32_t nsrc, int32_t N, int32_t H, int32_t W, void* dst, int32_t d_pitch, int32_t d_coff,
+                           int32_t OH, int32_t OW, cis_stream_t stream);
+/* its transpose: for every source i with want[i]: grads[i] (=|+= when accumulate[i]) sum over broadcast replicas of R^T ddst[slice i];
+ * grads[i].chunks must equal the forward source's (it positions the slice inside ddst), N = batch rows of ddst processed. */
+int cis_resize_concat_bf16_bwd(const void* ddst, int32_t d_pitch, int32_t d_coff, int32_t N, int32_t OH, int32_t OW, const CisSrc* grads,
+                               const int32_t* want, const int32_t* accumulate, int32_t nsrc, int32_t H, int32_t W, cis_stream_t stream);
 /* its transpose: dsrc (=|+=) R^T ddst */
 int cis_resize_bilinear_bf16_bwd(const void* ddst, int32_t d_pitch, int32_t d_coff, int32_t N, int32_t OH, int32_t OW, void* dsrc,
                                  int32_t s_pitch, int32_t s_coff, int32_t H, int32_t W, int32_t chunks, int32_t accumulate,

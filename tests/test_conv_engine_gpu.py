@@ -142,3 +142,23 @@ def test_conv_engine_narrow_n_tiles(case, cap):
     if 'dx_err' in r:
         assert r['dx_err'] <= tol(r['dx_ref']), r
         assert r['dw_err'] <= 2 ** -7 * r['dw_ref'] + 1e-3, r
+
+
+S2_CASES = [c for c in CASES if c.get('stride', 1) == 2]
+
+
+@pytest.mark.parametrize('case', S2_CASES, ids=lambda c: 'k%d_c%s_o%d' % (c['k'], '+'.join(map(str, c['cins'])), c['cout']))
+def test_conv_engine_stride2_on_the_halo_kernel(case):
+    """engine.S2_HALO (off by default): stride-2 forward convs as four space-to-depth phase halos (CisConv.nph = 4, TMA phase maps)."""
+    from unsupervised_detection_b200 import engine
+    assert S2_CASES
+    engine.S2_HALO = True
+    try:
+        r = run_conv_case(**case)
+    finally:
+        engine.S2_HALO = False
+    tol = lambda ref: 2 ** -7 * ref + 1e-3
+    assert r['fwd_err'] <= tol(r['fwd_ref']), r
+    if 'dx_err' in r:
+        assert r['dx_err'] <= tol(r['dx_ref']), r
+        assert r['dw_err'] <= 2 ** -7 * r['dw_ref'] + 1e-3, r

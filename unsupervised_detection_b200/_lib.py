@@ -33,7 +33,8 @@ class CisConv(C.Structure):
                 ('mode', C.c_int32),
                 ('halo', C.c_int32), ('dil', C.c_int32), ('MT', C.c_int32), ('hoy', C.c_int32), ('hox', C.c_int32),
                 ('ey', C.c_int32), ('ex', C.c_int32),
-                ('splits', C.c_int32), ('sk_scratch', C.c_void_p), ('sk_counters', C.c_void_p)]
+                ('splits', C.c_int32), ('sk_scratch', C.c_void_p), ('sk_counters', C.c_void_p),
+                ('nph', C.c_int32), ('ph_tap', C.c_int32 * 5)]
 
 
 class CisWgrad(C.Structure):
@@ -60,6 +61,8 @@ _PROTOS = {
     'cis_add_slice': [_p, _i32, _i32, _p, _i32, _i32, _i64, _i32, _i32, _i32],
     'cis_colsum': [_p, _i32, _i32, _i64, _i32, _p, _i32],
     'cis_resize_bilinear_bf16': [_p, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _i32, _i32, _i32],
+    'cis_resize_concat_bf16': [C.POINTER(CisSrc), _i32, _i32, _i32, _i32, _p, _i32, _i32, _i32, _i32],
+    'cis_resize_concat_bf16_bwd': [_p, _i32, _i32, _i32, _i32, _i32, C.POINTER(CisSrc), C.POINTER(C.c_int32), C.POINTER(C.c_int32), _i32, _i32, _i32],
     'cis_resize_bilinear_bf16_bwd': [_p, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32, _i32, _i32, _i32, _i32],
     'cis_resize_bilinear_f32': [_p, _i32, _i32, _i32, _i32, _p, _i32, _i32, _f32],
     'cis_upsample_nn2x': [_p, _i32, _i32, _i32, _i32, _p],

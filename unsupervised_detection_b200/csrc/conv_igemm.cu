@@ -416,15 +416,15 @@ __global__ void __launch_bounds__(kGThreads) conv_igemm_kernel(const __grid_cons
         if (rl < BN) cp_async16(b_dst, wrow + (kb_lo + kb) * kBK, 16u);
       }
       cp_async_commit();
-      if (kb >= S - 1) {             // publish block kb-(S-1): this thread's copies of it have landed
-        cp_async_wait<S - 1>();
+      if (kb >= 1) {                 // publish block kb-1 (its copies have landed) while block kb is in flight: the first MMA starts
+        cp_async_wait<1>();          // after two blocks are issued -- most launches of this kernel have < 10 K blocks
         fence_proxy_async();
-        mbar_arrive(bar_full + 8 * ((kb - (S - 1)) % S));
+        mbar_arrive(bar_full + 8 * ((kb - 1) % S));
       }
     }
     cp_async_wait<0>();
     fence_proxy_async();
-    for (int kb = nkb > S - 1 ? nkb - (S - 1) : 0; kb < nkb; ++kb) mbar_arrive(bar_full + 8 * (kb % S));
+    mbar_arrive(bar_full + 8 * ((nkb - 1) % S));
 
     // ------------------------------------------------------------------ epilogue: warps w and w + 4 share a TMEM lane quarter and split the columns
     mbar_wait(bar_accum, 0);
@@ -492,7 +492,8 @@ __global__ void __launch_bounds__(kGThreads) conv_igemm_kernel(const __grid_cons
 // (tap, chunk) are reused by the MT tiles.
 static constexpr int kHaloMaxBStages = 8;
 struct HaloMaps {
-  CUtensorMap m[CIS_MAX_SRC];   // one 4-D (C, W, H, N) SWIZZLE_128B map per concat source, box = (64, Wh, Hh, 1)
+  // one 4-D (C, W, H, N) SWIZZLE_128B map per (concat source, stride-2 phase): index si * nph + phase; box = (64, Wh, Hh, 1)
+  CUtensorMap m[CIS_MAX_SRC * 4];
 };
 
 // MMAs of one weight stage (gt taps of one 64-channel chunk, MT stacked tiles, NK K=16 steps each), issued by ONE thread.
@@ -528,6 +529,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int MT = p.MT, d = p.dil;
+  const int nph = p.nph > 1 ? p.nph : 1;       // stride-2 forward conv: 4 space-to-depth phases, each with its own halo and tap range
   const int Wh = 8 + p.ex, Hh = 16 * MT + p.ey, HP = Wh * Hh;
   const uint32_t stage_bytes = (uint32_t)G * kBStage;
   const uint32_t tile_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -605,10 +607,14 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     // stream the per-(tap, chunk) weight tiles (BS stages).
     if (use_tma) {
       if (tid == 0) {
-        // halo through the TMA engine: one 4-D tiled load per 64-channel chunk, out-of-image pixels / channels are zero-filled
-        for (int cc = 0; cc < nchunks; ++cc) {
-          const int hs = cc % NHS;
-          mbar_wait(bar_hempty + 8 * hs, (uint32_t)(((cc / NHS) & 1) ^ 1));
+        // halo through the TMA engine: one 4-D tiled load per 64-channel chunk (x phase), out-of-image pixels / channels are zero-filled
+        int hcount = 0;
+        for (int vc = 0; vc < nchunks * nph; ++vc) {
+          const int cc = vc / nph, ph = vc - cc * nph;
+          if (nph > 1 && p.ph_tap[ph + 1] == p.ph_tap[ph]) continue;      // phase without taps (kernel size 1)
+          const int hs = hcount % NHS;
+          mbar_wait(bar_hempty + 8 * hs, (uint32_t)(((hcount / NHS) & 1) ^ 1));
+          ++hcount;
           int c = (cc_lo + cc) * 8, si = 0;
           while (si < p.nsrc - 1 && c >= s_src[si].chunks) {
             c -= s_src[si].chunks;
@@ -616,7 +622,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
           }
           const int nmod = s_src[si].n_mod;
           mbar_expect_tx(bar_hfull + 8 * hs, (uint32_t)(HP * 128));
-          tma_load_4d(h_base + hs * halo_stage_bytes, &maps.m[si], bar_hfull + 8 * hs, c * 8, tx * 8 + p.hox, ty * 16 * MT + p.hoy,
+          tma_load_4d(h_base + hs * halo_stage_bytes, &maps.m[si * nph + ph], bar_hfull + 8 * hs, c * 8, tx * 8 + p.hox, ty * 16 * MT + p.hoy,
                       nmod ? (n % nmod) : n);
         }
       }
@@ -676,9 +682,11 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
       const uint8_t* wt = reinterpret_cast<const uint8_t*>(p.wpack) + ((size_t)ny * nchunks_all + cc_lo) * p.ntaps * kBStage;
       int bs = 0;
       uint32_t bph = 1;           // parity to wait for on the empty barrier: the first pass over the ring finds every stage free
-      for (int cc = 0; cc < nchunks; ++cc) {
-        for (int t0 = 0; t0 < p.ntaps; t0 += G) {
-          const uint32_t bytes = (uint32_t)min(G, p.ntaps - t0) * kBStage;
+      for (int vc = 0; vc < nchunks * nph; ++vc) {
+        const int cc = vc / nph, ph = vc - cc * nph;
+        const int tlo = nph > 1 ? p.ph_tap[ph] : 0, thi = nph > 1 ? p.ph_tap[ph + 1] : p.ntaps;
+        for (int t0 = tlo; t0 < thi; t0 += G) {
+          const uint32_t bytes = (uint32_t)min(G, thi - t0) * kBStage;
           mbar_wait(bar_bempty + 8 * bs, bph);
           mbar_expect_tx(bar_bfull + 8 * bs, bytes);
           bulk_g2s(b_base + bs * stage_bytes, wt + (size_t)(cc * p.ntaps + t0) * kBStage, bytes, bar_bfull + 8 * bs);
@@ -719,32 +727,39 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     const uint32_t a_mstep = (uint32_t)(16 * Wh * 128) >> 4;   // descriptor start-field step between stacked M tiles
     int bs = 0, hs = 0, it = 0;
     uint32_t bph = 0, hph = 0;
-    for (int cc = 0; cc < nchunks; ++cc) {
+    int vlast = nchunks * nph - 1;                       // last virtual chunk that has taps
+    while (nph > 1 && vlast > 0 && p.ph_tap[vlast % nph + 1] == p.ph_tap[vlast % nph]) --vlast;
+    bool any = false;
+    for (int vc = 0; vc < nchunks * nph; ++vc) {
+      const int cc = vc / nph, ph = vc - cc * nph;
+      const int tlo = nph > 1 ? p.ph_tap[ph] : 0, thi = nph > 1 ? p.ph_tap[ph + 1] : p.ntaps;
+      if (thi == tlo) continue;
       const int rem = m_chunks - (cc_lo + cc) * 8;
       const int nk16 = rem >= 8 ? 4 : (rem + 1) / 2;
       mbar_wait(bar_hfull + 8 * hs, hph);
-      if (cc == 0 && lane == 0) CIS_TRACE_AT(1);
+      if (vc == 0 && lane == 0) CIS_TRACE_AT(1);
       const uint32_t hlo = desc_lo(h_base + hs * halo_stage_bytes, 16);
-      for (int t0 = 0; t0 < p.ntaps; t0 += G, ++it) {
-        const int gt = min(G, p.ntaps - t0);
+      for (int t0 = tlo; t0 < thi; t0 += G, ++it) {
+        const int gt = min(G, thi - t0);
         mbar_wait(bar_bfull + 8 * bs, bph);
         tc_fence_after();
         if (elect_one()) {
           CIS_TRACE_AT(8 + 2 * it);
           const uint32_t blo = desc_lo(b_base + bs * stage_bytes, 16);
-          const bool first = (cc | t0) == 0;
+          const bool first = !any;
           if (nk16 == 4) halo_issue_stage<4>(tmem, hlo, blo, s_aoff + t0, gt, MT, BN, ahi, bhi, a_mstep, idesc, first);
           else if (nk16 == 1) halo_issue_stage<1>(tmem, hlo, blo, s_aoff + t0, gt, MT, BN, ahi, bhi, a_mstep, idesc, first);
           else if (nk16 == 2) halo_issue_stage<2>(tmem, hlo, blo, s_aoff + t0, gt, MT, BN, ahi, bhi, a_mstep, idesc, first);
           else halo_issue_stage<3>(tmem, hlo, blo, s_aoff + t0, gt, MT, BN, ahi, bhi, a_mstep, idesc, first);
           umma_commit(bar_bempty + 8 * bs);
-          if (t0 + G >= p.ntaps) {
+          if (t0 + G >= thi) {
             umma_commit(bar_hempty + 8 * hs);
-            if (cc == nchunks - 1) umma_commit(bar_accum);
+            if (vc == vlast) umma_commit(bar_accum);
           }
           CIS_TRACE_AT(9 + 2 * it);
         }
         __syncwarp();
+        any = true;
         if (++bs == BS) {
           bs = 0;
           bph ^= 1u;
@@ -1479,16 +1494,19 @@ static EncodeTiledFn get_encode_tiled() {
   }
   return fn;
 }
-// (C, W, H, N) bf16 map of one concat source slice; box (64, bw, bh, 1), 128B swizzle, zero OOB fill.
-static bool encode_src_map(CUtensorMap* m, const CisSrc& s, int N, int H, int W, int bw, int bh) {
+// (C, W, H, N) bf16 map of one concat source slice; box (64, bw, bh, 1), 128B swizzle, zero OOB fill.  step = 2 selects the
+// space-to-depth phase (py, px) of the image: pixel (y, x) of the map is input pixel (2y + py, 2x + px).
+static bool encode_src_map(CUtensorMap* m, const CisSrc& s, int N, int H, int W, int bw, int bh, int step = 1, int py = 0, int px = 0) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
   const int nb = s.n_mod > 0 ? s.n_mod : N;
-  cuuint64_t dims[4] = {(cuuint64_t)s.chunks * 8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)nb};
-  cuuint64_t strides[3] = {(cuuint64_t)s.pitch * 2, (cuuint64_t)W * s.pitch * 2, (cuuint64_t)H * W * s.pitch * 2};
+  const int Hq = (H - py + step - 1) / step, Wq = (W - px + step - 1) / step;
+  if (Hq < 1 || Wq < 1) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)s.chunks * 8, (cuuint64_t)Wq, (cuuint64_t)Hq, (cuuint64_t)nb};
+  cuuint64_t strides[3] = {(cuuint64_t)step * s.pitch * 2, (cuuint64_t)step * W * s.pitch * 2, (cuuint64_t)H * W * s.pitch * 2};
   cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  void* base = (void*)((const char*)s.ptr + (size_t)s.c_off * 2);
+  void* base = (void*)((const char*)s.ptr + ((size_t)(py * W + px) * s.pitch + (size_t)s.c_off) * 2);
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -1553,19 +1571,24 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   dim3 grid(tiles * dd * dd * d->N, d->n_tiles, splits);
   // TMA halo path: undilated, every concat source except the last a multiple of 64 channels (a chunk never straddles sources)
   HaloMaps maps;
+  const int nph = d->nph > 1 ? d->nph : 1;
   int use_tma = (d->dil == 1 && Wh <= 256 && Hh <= 256) ? 1 : 0;
   for (int i = 0; use_tma && i < d->nsrc - 1; ++i)
     if (d->src[i].chunks % 8) use_tma = 0;
-  for (int i = 0; use_tma && i < d->nsrc; ++i)
-    if (((uintptr_t)d->src[i].ptr + (size_t)d->src[i].c_off * 2) % 16 || !encode_src_map(&maps.m[i], d->src[i], d->N, d->H, d->W, Wh, Hh)) use_tma = 0;
+  for (int i = 0; use_tma && i < d->nsrc; ++i) {
+    if (((uintptr_t)d->src[i].ptr + (size_t)d->src[i].c_off * 2) % 16) use_tma = 0;
+    for (int ph = 0; use_tma && ph < nph; ++ph)
+      if (!encode_src_map(&maps.m[i * nph + ph], d->src[i], d->N, d->H, d->W, Wh, Hh, nph > 1 ? 2 : 1, ph >> 1, ph & 1)) use_tma = 0;
+  }
   if (!use_tma) memset(&maps, 0, sizeof(maps));
+  if (nph > 1 && !use_tma) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_conv_igemm(halo): stride-2 phases need the TMA halo path");
   // persistent variant (conv_halo_persist_kernel): layers with many tiles per SM.  CIS_PERSIST_MODE / cis_set_persist_mode:
   //   0 off | 1 (default) layers whose whole weight set stays resident in shared memory and that have >= 2 tiles per SM |
   //   2 every eligible layer (tests) | 3 every layer whose weight set fits, whatever the tile count (tests)
   const int persist_mode = g_persist_mode >= 0 ? g_persist_mode : (getenv("CIS_PERSIST_MODE") ? atoi(getenv("CIS_PERSIST_MODE")) : 1);
   static const int p_min_tiles = getenv("CIS_PERSIST_MIN_TILES") ? atoi(getenv("CIS_PERSIST_MIN_TILES")) : 296;
   static const int p_ws_kb = getenv("CIS_PERSIST_WS_KB") ? atoi(getenv("CIS_PERSIST_WS_KB")) : 112;
-  if (persist_mode > 0 && use_tma && d->n_tiles == 1 && splits == 1) {
+  if (persist_mode > 0 && use_tma && d->n_tiles == 1 && splits == 1 && nph == 1) {
     const int total = tiles * d->N;
     const int per_tile = nchunks * d->ntaps;
     const int AS = (2 * d->MT * BN <= 512) ? 2 : 1;
@@ -1629,7 +1652,7 @@ extern "C" int cis_conv_igemm(const CisConv* d, cis_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   if (d->halo) {
     if (d->MT < 1 || d->MT > 4 || d->MT * d->BN > 512 || d->dil < 1 || d->sh != 1 || d->sw != 1 || d->ey < 0 || d->ex < 0 ||
-        (d->dil > 1 && (d->OH != d->H || d->OW != d->W)))
+        (d->dil > 1 && (d->OH != d->H || d->OW != d->W)) || (d->nph > 1 && (d->nph != 4 || d->dil != 1 || d->ph_tap[0] != 0 || d->ph_tap[4] != d->ntaps)))
       return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm(halo): bad tile parameters");
     switch (d->BN) {
       case 16: return launch_halo<16>(d, st);

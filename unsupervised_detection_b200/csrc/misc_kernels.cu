@@ -286,6 +286,105 @@ __global__ void resize_bilinear_bf16_bwd_kernel(const bf16* __restrict__ dd, int
   }
   *o = pack8(a);
 }
+// ---- fused resize + concat (recover decoder, convolution_utils.py:87-90 + nets.py:80-105): up to 4 sources of one resolution, each
+// a channel slice of its own tensor (batch-broadcast when n_mod > 0), are legacy-bilinear resized to OH x OW and written side by side
+// into ONE destination slice -- one launch instead of a resize per source plus a copy per source (and per broadcast replica).
+struct RcArgs {
+  CisSrc s[CIS_MAX_SRC];
+  int nsrc;
+};
+__global__ void resize_concat_bf16_kernel(const RcArgs a, int N, int H, int W, bf16* __restrict__ dst, int dp, int dc, int OH, int OW,
+                                          int total_chunks) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * OH * OW * total_chunks) return;
+  int ck = (int)(i % total_chunks);
+  const size_t pix = i / total_chunks;
+  const int off = ck * 8;
+  int si = 0;
+  while (si < a.nsrc - 1 && ck >= a.s[si].chunks) {
+    ck -= a.s[si].chunks;
+    ++si;
+  }
+  CisSrc sd = a.s[0];
+  if (si == 1) sd = a.s[1];
+  if (si == 2) sd = a.s[2];
+  if (si == 3) sd = a.s[3];
+  const int ox = (int)(pix % OW);
+  const int oy = (int)((pix / OW) % OH);
+  const int n = (int)(pix / ((size_t)OW * OH));
+  const int ns = sd.n_mod ? n % sd.n_mod : n;
+  const Lerp ly = legacy_lerp(oy, H, (float)H / (float)OH), lx = legacy_lerp(ox, W, (float)W / (float)OW);
+  float tl[8], tr[8], bl[8], br[8], o[8];
+  const bf16* b = reinterpret_cast<const bf16*>(sd.ptr) + (size_t)ns * H * W * sd.pitch + sd.c_off + ck * 8;
+  unpack8(*reinterpret_cast<const uint4*>(b + ((size_t)ly.lo * W + lx.lo) * sd.pitch), tl);
+  unpack8(*reinterpret_cast<const uint4*>(b + ((size_t)ly.lo * W + lx.hi) * sd.pitch), tr);
+  unpack8(*reinterpret_cast<const uint4*>(b + ((size_t)ly.hi * W + lx.lo) * sd.pitch), bl);
+  unpack8(*reinterpret_cast<const uint4*>(b + ((size_t)ly.hi * W + lx.hi) * sd.pitch), br);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float t = tl[e] + (tr[e] - tl[e]) * lx.f;
+    const float bo = bl[e] + (br[e] - bl[e]) * lx.f;
+    o[e] = t + (bo - t) * ly.f;
+  }
+  *reinterpret_cast<uint4*>(dst + pix * dp + dc + off) = pack8(o);
+}
+// its transpose: for every source with want != 0, dsrc (=|+=) sum over broadcast replicas of R^T ddst[.., slice of that source]
+struct RcGrad {
+  void* ptr;
+  int pitch, c_off, chunks, n_mod, want, accumulate;
+};
+struct RcGradArgs {
+  RcGrad s[CIS_MAX_SRC];
+  int nsrc;
+};
+__global__ void resize_concat_bf16_bwd_kernel(const bf16* __restrict__ dd, int dp, int dc, int N, int OH, int OW, const RcGradArgs a, int H,
+                                              int W, int total_chunks) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)N * H * W * total_chunks) return;
+  int ck = (int)(i % total_chunks);
+  const size_t pix = i / total_chunks;
+  const int off = ck * 8;
+  int si = 0;
+  while (si < a.nsrc - 1 && ck >= a.s[si].chunks) {
+    ck -= a.s[si].chunks;
+    ++si;
+  }
+  RcGrad sd = a.s[0];
+  if (si == 1) sd = a.s[1];
+  if (si == 2) sd = a.s[2];
+  if (si == 3) sd = a.s[3];
+  const int x = (int)(pix % W);
+  const int y = (int)((pix / W) % H);
+  const int n = (int)(pix / ((size_t)W * H));
+  if (!sd.want || (sd.n_mod && n >= sd.n_mod)) return;
+  const int reps = sd.n_mod ? N / sd.n_mod : 1;
+  const float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
+  int y0, y1, x0, x1;
+  legacy_range(y, OH, sy, y0, y1);
+  legacy_range(x, OW, sx, x0, x1);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t[8];
+  uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(sd.ptr) + ((size_t)(n * H + y) * W + x) * sd.pitch + sd.c_off + ck * 8);
+  if (sd.accumulate) unpack8(*o, acc);
+  for (int r = 0; r < reps; ++r) {
+    const int nd = n + r * sd.n_mod;
+    for (int dy = y0; dy <= y1; ++dy) {
+      const float wy = legacy_w(dy, y, H, sy);
+      if (wy == 0.f) continue;
+      for (int dx = x0; dx <= x1; ++dx) {
+        const float wt = wy * legacy_w(dx, x, W, sx);
+        if (wt == 0.f) continue;
+        unpack8(*reinterpret_cast<const uint4*>(dd + ((size_t)(nd * OH + dy) * OW + dx) * dp + dc + off), t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += wt * t[e];
+      }
+    }
+  }
+  *o = pack8(acc);
+}
 __global__ void resize_bilinear_f32_kernel(const float* __restrict__ src, int N, int H, int W, int C, float* __restrict__ dst, int OH, int OW,
                                            float scale) {
   pdl_launch_dependents();
@@ -891,6 +990,42 @@ int cis_resize_bilinear_bf16_bwd(const void* dd, int32_t dp, int32_t dc, int32_t
   CIS_LAUNCH(resize_bilinear_bf16_bwd_kernel, nblk((size_t)N * H * W * chunks), 256, 0, ST, (cbf)dd, dp, dc, N, OH, OW, (mbf)ds, sp, sc, H, W, chunks,
                                                                                      accumulate);
   return cis_check_launch("resize_bilinear_bf16_bwd");
+}
+int cis_resize_concat_bf16(const CisSrc* srcs, int32_t nsrc, int32_t N, int32_t H, int32_t W, void* dst, int32_t dp, int32_t dc, int32_t OH, int32_t OW,
+                           cis_stream_t stream) {
+  if (!srcs || nsrc < 1 || nsrc > CIS_MAX_SRC) return cis_set_error(CIS_ERR_BAD_ARG, "cis_resize_concat_bf16: 1..4 sources");
+  RcArgs a;
+  a.nsrc = nsrc;
+  int total = 0;
+  for (int i = 0; i < nsrc; ++i) {
+    a.s[i] = srcs[i];
+    if ((srcs[i].pitch | srcs[i].c_off) & 7) return cis_set_error(CIS_ERR_BAD_ARG, "cis_resize_concat_bf16: slices must be 8-channel aligned");
+    total += srcs[i].chunks;
+  }
+  if ((dp | dc) & 7) return cis_set_error(CIS_ERR_BAD_ARG, "cis_resize_concat_bf16: destination must be 8-channel aligned");
+  CIS_LAUNCH(resize_concat_bf16_kernel, nblk((size_t)N * OH * OW * total), 256, 0, ST, a, N, H, W, (mbf)dst, dp, dc, OH, OW, total);
+  return cis_check_launch("resize_concat_bf16");
+}
+int cis_resize_concat_bf16_bwd(const void* ddst, int32_t dp, int32_t dc, int32_t N, int32_t OH, int32_t OW, const CisSrc* grads, const int32_t* want,
+                               const int32_t* accumulate, int32_t nsrc, int32_t H, int32_t W, cis_stream_t stream) {
+  if (!grads || nsrc < 1 || nsrc > CIS_MAX_SRC) return cis_set_error(CIS_ERR_BAD_ARG, "cis_resize_concat_bf16_bwd: 1..4 sources");
+  RcGradArgs a;
+  a.nsrc = nsrc;
+  int total = 0;
+  for (int i = 0; i < nsrc; ++i) {
+    a.s[i].ptr = const_cast<void*>(grads[i].ptr);
+    a.s[i].pitch = grads[i].pitch;
+    a.s[i].c_off = grads[i].c_off;
+    a.s[i].chunks = grads[i].chunks;
+    a.s[i].n_mod = grads[i].n_mod;
+    a.s[i].want = want[i];
+    a.s[i].accumulate = accumulate[i];
+    if (want[i] && (!grads[i].ptr || ((grads[i].pitch | grads[i].c_off) & 7))) return cis_set_error(CIS_ERR_BAD_ARG, "cis_resize_concat_bf16_bwd: bad gradient slice");
+    if (grads[i].n_mod && N % grads[i].n_mod) return cis_set_error(CIS_ERR_BAD_ARG, "cis_resize_concat_bf16_bwd: N must be a multiple of n_mod");
+    total += grads[i].chunks;
+  }
+  CIS_LAUNCH(resize_concat_bf16_bwd_kernel, nblk((size_t)N * H * W * total), 256, 0, ST, (cbf)ddst, dp, dc, N, OH, OW, a, H, W, total);
+  return cis_check_launch("resize_concat_bf16_bwd");
 }
 int cis_resize_bilinear_f32(const float* src, int32_t N, int32_t H, int32_t W, int32_t C, float* dst, int32_t OH, int32_t OW, float scale,
                             cis_stream_t stream) {

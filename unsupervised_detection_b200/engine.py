@@ -346,6 +346,62 @@ def setup_halo(d, taps, dil, n_tiles):
     return True
 
 
+# stride-2 forward convolutions on the halo kernel (4 space-to-depth phase tensor maps, CisConv.nph = 4).  Off by default: measured r02
+# (gpurun_out/r02k) neutral on the >= 32-channel layers and 2-3x slower on the thin 7x7 / 5x5 first layers (every tap pays a
+# 64-channel chunk), +0.25 ms per step in total -- the K-dense gather kernel stays the stride-2 path.
+S2_HALO = os.environ.get('CIS_S2_HALO', '0') == '1'
+
+
+def setup_halo_s2(d, taps, n_tiles):
+    """Stride-2 forward conv as a halo-kernel launch: input pixel (2*oh + u, 2*ow + v) of tap (u, v) is pixel (oh + u // 2, ow + v // 2)
+    of the space-to-depth phase (u % 2, v % 2), so the conv is the sum over the 4 phases of stride-1 convs with the taps of that phase.
+    Returns the tap permutation (phase-major) the pre-tiled weights must follow, or None when the launch stays on the gather kernel."""
+    if not (HALO_ENABLED and S2_HALO) or d.sh != 2 or d.sw != 2:
+        return None
+    if any(d.src[i].chunks % 8 for i in range(d.nsrc - 1)):       # TMA halo path only: a 64-channel chunk never straddles sources
+        return None
+    ph = [((u % 2) * 2 + (v % 2), u // 2, v // 2) for u, v in taps]
+    order = sorted(range(len(taps)), key=lambda i: (ph[i][0], i))
+    hoy, hox = min(a for _, a, _ in ph), min(b for _, _, b in ph)
+    rel = [(ph[i][1] - hoy, ph[i][2] - hox) for i in order]
+    ey, ex = max(a for a, _ in rel), max(b for _, b in rel)
+    m_chunks = sum(d.src[i].chunks for i in range(d.nsrc))
+    nchunks = -(-m_chunks // 8)
+    tiles_x = -(-d.OW // 8)
+    best = None
+    for MT in (1, 2, 3, 4):
+        if MT * d.BN > 512:
+            continue
+        HP = (8 + ex) * (16 * MT + ey)
+        smem = 2 * ru(HP * 128, 1024) + HP * 4 + 2048 + 2 * d.BN * 128
+        if smem > 227 * 1024:
+            continue
+        tiles_y = -(-d.OH // (16 * MT))
+        util = (d.OH * d.OW) / float(tiles_y * 16 * MT * tiles_x * 8)
+        if util < HALO_MIN_UTIL:
+            continue
+        ncta = d.N * tiles_x * tiles_y * n_tiles
+        cps = max(1, min((225 * 1024) // smem, 512 // _pow2_cols(MT * d.BN), 4))
+        t_mma = MT * 2.0 * d.BN * len(taps) * nchunks
+        t_mem = (d.BN * 128 * len(taps) / 40.0 + 4 * HP * 128 / 40.0) * nchunks
+        t_cta = max(t_mma, t_mem) + (4000.0 + 1500.0 * MT) / cps
+        cost = -(-ncta // (NUM_SMS * cps)) * cps * t_cta / min(cps, max(1.0, ncta / float(NUM_SMS)))
+        if best is None or cost < best[0] - 1e-9:
+            best = (cost, MT)
+    if best is None:
+        return None
+    d.halo, d.dil, d.MT, d.hoy, d.hox, d.ey, d.ex = 1, 1, best[1], hoy, hox, ey, ex
+    d.sh = d.sw = 1                     # the phases absorb the stride; H x W stay the input size (tensor maps)
+    _fill_taps(d, rel)
+    d.nph = 4
+    bounds = [0]
+    for q in range(4):
+        bounds.append(bounds[-1] + sum(1 for i in order if ph[i][0] == q))
+    for q in range(5):
+        d.ph_tap[q] = bounds[q]
+    return order
+
+
 class ParamStore(object):
     """One flat fp32 parameter buffer (+ grad, Adam m/v) per variable scope; names follow the TF variable layout
     (adversarial_learner.py:211-214 scopes 'MaskNet' / 'FlownetS'; model_pwcnet.py 'pwcnet')."""
@@ -459,10 +515,16 @@ class ConvLayer(object):
         nchunks = -(-cin8 // 64)
         return torch.zeros(n_tiles * nchunks * ntaps * BN * 64, dtype=torch.bfloat16, device=self.device)
 
-    def fwd_tiles_buf(self):
-        """Pre-swizzled tile-major copy of the forward operand (halo kernel)."""
+    def fwd_tiles_buf(self, tap_order=None):
+        """Pre-swizzled tile-major copy of the forward operand (halo kernel).  tap_order: the phase-major tap permutation of a
+        stride-2 layer (setup_halo_s2); the tiles then follow that order."""
         if getattr(self, 'fwd_tiles', None) is None:
             self.fwd_tiles = self._alloc_tiles(self.k * self.k, len(self.in_chanmap), self.BN, self.n_tiles)
+            self.fwd_tiles_kmap = self.fwd_kmap
+            if tap_order is not None:
+                self.fwd_tiles_kmap, _ = self._kmap(list(tap_order), self.in_chanmap, self.cin * self.cout, self.cout)
+            self.fwd_tap_order = tap_order
+        assert getattr(self, 'fwd_tap_order', None) == tap_order, self.name
         return self.fwd_tiles
 
     def w_src_ptr(self):
@@ -488,7 +550,7 @@ class ConvLayer(object):
                                  None, pk['w'].data_ptr())
             else:
                 if getattr(self, 'fwd_tiles', None) is not None:
-                    plan.add('cis_pack_weights_tiled', self.w_src_ptr(), self.fwd_kmap.data_ptr(), len(self.in_chanmap), self.k * self.k,
+                    plan.add('cis_pack_weights_tiled', self.w_src_ptr(), self.fwd_tiles_kmap.data_ptr(), len(self.in_chanmap), self.k * self.k,
                              self.n_tiles, self.BN, self.cout, 1, None, self.fwd_tiles.data_ptr())
                 if getattr(self, 'fwd_rows_used', True):
                     plan.add('cis_pack_weights', self.w_src_ptr(), self.fwd_kmap.data_ptr(), self.K_pad, self.npad, self.cout, 1,
@@ -653,7 +715,11 @@ class Builder(object):
         if post_add is not None:
             d.add_post, d.add_post_pitch, d.add_post_coff = post_add.ptr, post_add.pitch, post_add.c_off
         d.mode = mode
-        if layer.stride == 1 and setup_halo(d, taps, layer.dil, layer.n_tiles):
+        order = setup_halo_s2(d, taps, layer.n_tiles) if (layer.stride == 2 and layer.dil == 1) else None
+        if order is not None:
+            d.wpack = layer.fwd_tiles_buf(order).data_ptr()
+            layer.fwd_rows_used = getattr(layer, 'fwd_rows_used', False)
+        elif layer.stride == 1 and setup_halo(d, taps, layer.dil, layer.n_tiles):
             d.wpack = layer.fwd_tiles_buf().data_ptr()
             layer.fwd_rows_used = getattr(layer, 'fwd_rows_used', False)
         else:
@@ -778,61 +844,76 @@ class Builder(object):
         if single:
             srcs[0].grad_written[mode] = True
         else:
-            off = 0
-            for s_ in srcs:
-                if mode in s_.dep:
+            # gradient of the virtual concat -> the sources' gradient slices, ONE launch (same-size case of the fused resize-concat
+            # transpose: slices the channels, folds the replicas of batch-broadcast sources, accumulates where a gradient exists)
+            want = [1 if mode in s_.dep else 0 for s_ in srcs]
+            garr, acc = [], []
+            for s_, w_ in zip(srcs, want):
+                if w_:
                     sg = s_.get_grad()
-                    reps = 1
-                    rows = s_.rows(mode)
-                    if s_.n_mod:
-                        reps = nb // s_.n_mod
-                        rows = s_.n_mod
-                    bp.add('cis_add_slice', sg.ptr, sg.pitch, sg.c_off, tgt.ptr, tgt.pitch, off, rows * H * W, s_.C8 // 8, reps,
-                           1 if s_.grad_written.get(mode) else 0)
+                    garr.append(CisSrc(sg.ptr, sg.pitch, sg.c_off, s_.C8 // 8, s_.n_mod))
+                    acc.append(1 if s_.grad_written.get(mode) else 0)
                     s_.grad_written[mode] = True
-                off += s_.C8
+                else:
+                    garr.append(CisSrc(None, 8, 0, s_.C8 // 8, s_.n_mod))
+                    acc.append(0)
+            ga = (CisSrc * len(srcs))(*garr)
+            wa, aa = (C.c_int32 * len(srcs))(*want), (C.c_int32 * len(srcs))(*acc)
+            bp.keep += [ga, wa, aa]
+            bp.add('cis_resize_concat_bf16_bwd', tgt.ptr, tgt.pitch, 0, nb, H, W, ga, wa, aa, len(srcs), H, W)
 
-    # ---- materialised concat (only where the virtual concat is not 64-channel aligned, so the TMA operand paths apply)
-    def concat(self, srcs, name='cat'):
+    # ---- fused resize + concat: ONE launch brings up to 4 same-resolution sources (batch-broadcast ones included) to OH x OW and lays
+    # them side by side in one buffer, ONE launch takes the gradient back (folding the broadcast replicas); replaces a resize launch
+    # per source plus a copy per source and replica (recover decoder: `deconv` inputs, nets.py:80-104; misaligned virtual concats)
+    def resize_concat(self, srcs, OH=None, OW=None, name='cat'):
+        srcs = list(srcs)
+        assert 1 <= len(srcs) <= 4
         N = max(s.N for s in srcs)
         H, W = srcs[0].H, srcs[0].W
+        OH, OW = OH or H, OW or W
+        for s in srcs:
+            assert (s.H, s.W) == (H, W) and (s.n_mod == 0 or N % s.n_mod == 0)
         chanmap, base = [], 0
         for s in srcs:
             chanmap += [(m + base if m >= 0 else -1) for m in s.chanmap]
             base += s.C
         dep = frozenset().union(*[s.dep for s in srcs])
-        cat = Act(N, H, W, base, self.device, chanmap=chanmap, dep=dep, name=name)
+        cat = Act(N, OH, OW, base, self.device, chanmap=chanmap, dep=dep, name=name)
         gr = [s.gen_rows for s in srcs if s.gen_rows]
         if gr:
             cat.gen_rows = gr[0]
-        self.keep += [srcs, cat]
-        off = 0
-        for s in srcs:
-            reps = (N // s.n_mod) if s.n_mod else 1
-            rows = s.n_mod if s.n_mod else s.N
-            for r in range(reps):   # batch-broadcast sources are replicated into every third of the batch
-                self.fwd.add('cis_add_slice', cat.ptr + 2 * r * rows * H * W * cat.pitch, cat.pitch, off, s.ptr, s.pitch, s.c_off,
-                             rows * H * W, s.C8 // 8, 1, 0)
-            off += s.C8
+        arr = (CisSrc * len(srcs))(*[s.src() for s in srcs])
+        self.keep += [srcs, cat, arr]
+        self.fwd.add('cis_resize_concat_bf16', arr, len(srcs), N, H, W, cat.ptr, cat.pitch, cat.c_off, OH, OW, lane=self.lane)
 
         def bwd(bp, mode):
             if mode not in cat.dep or not cat.grad_written.get(mode):
                 return
             g = cat.get_grad()
             nb = cat.rows(mode)
-            o = 0
-            for s_ in srcs:
-                if mode in s_.dep:
+            want = [1 if mode in s_.dep else 0 for s_ in srcs]
+            if not any(want):
+                return
+            garr, acc = [], []
+            for s_, w_ in zip(srcs, want):
+                if w_:
                     sg = s_.get_grad()
-                    reps, rows = 1, s_.rows(mode)
-                    if s_.n_mod:
-                        reps, rows = nb // s_.n_mod, s_.n_mod
-                    bp.add('cis_add_slice', sg.ptr, sg.pitch, sg.c_off, g.ptr, g.pitch, o, rows * H * W, s_.C8 // 8, reps,
-                           1 if s_.grad_written.get(mode) else 0)
+                    garr.append(CisSrc(sg.ptr, sg.pitch, sg.c_off, s_.C8 // 8, s_.n_mod))
+                    acc.append(1 if s_.grad_written.get(mode) else 0)
                     s_.grad_written[mode] = True
-                o += s_.C8
+                else:
+                    garr.append(CisSrc(None, 8, 0, s_.C8 // 8, s_.n_mod))
+                    acc.append(0)
+            ga = (CisSrc * len(srcs))(*garr)
+            wa, aa = (C.c_int32 * len(srcs))(*want), (C.c_int32 * len(srcs))(*acc)
+            bp.keep += [ga, wa, aa]
+            bp.add('cis_resize_concat_bf16_bwd', g.ptr, g.pitch, g.c_off, nb, OH, OW, ga, wa, aa, len(srcs), H, W)
         self.tape.append(bwd)
         return cat
+
+    def concat(self, srcs, name='cat'):
+        """Materialised concat (only where the virtual concat is not 64-channel aligned, so the TMA operand paths apply)."""
+        return self.resize_concat(srcs, name=name)
 
     # ---- transposed conv (PWC-Net up_flow / up_feat), forward only
     def conv_transpose(self, layer, src, out=None, outf=None, plan=None, name=None):

@@ -130,7 +130,8 @@ class RecoverNet(object):
         b = enc('b', flow_in)
         if ncalls > 1:
             a = {k: v.alias(nB) for k, v in a.items()}
-        rs = lambda ts, ref: [B.resize_bilinear(t, ref.H, ref.W) for t in ts]
+        # `deconv` = legacy-bilinear resize of the concat to the next level + conv: the resize of all concat sources is ONE fused launch
+        rs = lambda ts, ref: [B.resize_concat(ts, ref.H, ref.W, name='rs%dx%d' % (ref.H, ref.W))]
         conv6 = [a['6'], b['6']]                                              # nets.py:78
         deconv5 = B.conv(L['deconv5'], rs(conv6, b['51']))
         concat5 = [deconv5, b['51'], a['51']]

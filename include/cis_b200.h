@@ -88,6 +88,9 @@ typedef struct {
    * nph = 0/1: ordinary stride-1 gather. */
   int32_t nph;
   int32_t ph_tap[5];
+  /* 1: the `splits` CTAs of a tile form a thread-block cluster (2..8 CTAs) and reduce their partial accumulators through distributed
+   * shared memory inside the conv kernel (fixed summation order, fused epilogue spread over the cluster): no sk_scratch, no second launch. */
+  int32_t sk_cluster;
 } CisConv;
 
 /* Weight gradient of the same convolution: dWp[co][(t,c)] = sum_rows g[row][co] * A[row][(t,c)]  (fp32).  The reduction over rows

@@ -70,12 +70,14 @@ def _test_masks_dp():
     learner.restore(FLAGS.ckpt_file)
     rank, world, total, b = learner.rank, learner.world, int(learner.test_samples), int(FLAGS.batch_size)
     names = eval_dp.global_names(learner)
+    vt = eval_dp.virtual_total(total, b)      # the single-process loop scores ceil(total/b)*b frames (its last batch wraps around)
+    names = [names[g % total] for g in range(vt)]
     counters = eval_dp.category_counters(names)
     local = []
     for step in range(eval_dp.steps_for(total, b, world)):
         inference = learner.inference(None)
         for j, gidx in enumerate(eval_dp.owned_indices(step, b, rank, world, total)):
-            if gidx >= total or j >= inference['input_image'].shape[0]:
+            if gidx >= vt or j >= inference['input_image'].shape[0]:
                 continue
             gt_mask = inference['gt_masks'][j]
             iou, out_mask = compute_IoU(gt_mask=gt_mask, pred_mask_f=inference['gen_masks'][j])

@@ -162,3 +162,23 @@ def test_conv_engine_stride2_on_the_halo_kernel(case):
     if 'dx_err' in r:
         assert r['dx_err'] <= tol(r['dx_ref']), r
         assert r['dw_err'] <= 2 ** -7 * r['dw_ref'] + 1e-3, r
+
+
+@pytest.mark.parametrize('case', MODE_CASES, ids=lambda c: 'k%d_d%d_c%s_o%d' % (c['k'], c.get('dil', 1), '+'.join(map(str, c['cins'])), c['cout']))
+def test_conv_engine_split_k_cluster(case):
+    """engine.SPLITK_CLUSTER: the splits of a tile form a thread-block cluster (<= 8 CTAs along grid.z) and reduce their partial
+    accumulators through distributed shared memory inside the conv kernel -- same tolerance, bit-reproducible, no finish launch."""
+    from unsupervised_detection_b200 import engine
+    old = (engine.SPLITK, engine.SPLITK_NCTA, engine.SPLITK_MIN_UNITS, engine.SPLITK_CLUSTER)
+    engine.SPLITK, engine.SPLITK_NCTA, engine.SPLITK_MIN_UNITS, engine.SPLITK_CLUSTER = 2, 10 ** 6, 0, True
+    try:
+        r = run_conv_case(**case)
+        r2 = run_conv_case(**case)
+    finally:
+        engine.SPLITK, engine.SPLITK_NCTA, engine.SPLITK_MIN_UNITS, engine.SPLITK_CLUSTER = old
+    tol = lambda ref: 2 ** -7 * ref + 1e-3
+    assert r['fwd_err'] <= tol(r['fwd_ref']), r
+    assert r['fwd_err'] == r2['fwd_err']
+    if 'dx_err' in r:
+        assert r['dx_err'] <= tol(r['dx_ref']), r
+        assert r['dx_err'] == r2['dx_err']

@@ -103,9 +103,10 @@ def test_two_rank_evaluation_equals_single_process(tmp_path, capsys):
     ref_dir = str(tmp_path / 'ref')
     _parse(os.path.join(ref_dir, 'single'), 2)
     r1 = TG._test_masks_dp()
-    # the original single-process loop, with a batch size that divides nothing away (its ceil(n/batch) steps would re-read the first
-    # frames of the endless iterator when the batch does not divide the list -- the reference does the same; the dp loop skips those)
-    _parse(str(tmp_path / 'orig'), 1)
+    # the original single-process loop with the SAME batch size, which does not divide the list: its last batch wraps around and the
+    # head frame is scored twice (the reference does the same); the sharded loop scores the same virtual sequence
+    assert len(NAMES) % 2 == 1
+    _parse(str(tmp_path / 'orig'), 2)
     TG._test_masks()
     out = capsys.readouterr().out
     _parse(os.path.join(ref_dir, 'ens'), 1)
@@ -113,7 +114,8 @@ def test_two_rank_evaluation_equals_single_process(tmp_path, capsys):
     avg = [l for l in out.splitlines() if l.startswith('The Average over the dataset')]
     nums = [[float(t) for t in l.replace('The Average over the dataset: IoU is ', '').split(' and MAE is ')] for l in avg]
     assert len(avg) == 2 and np.allclose(nums[0], nums[1], rtol=0, atol=1e-6)      # dp report (world 1) == original loop (fp32 vs fp64 sums)
-    assert [s[0] for s in r1] == list(range(len(NAMES))) and [s[1] for s in r1].count('catA') == 7
+    assert [s[0] for s in r1] == list(range(len(NAMES) + 1))          # 11 frames + the wrap-around duplicate of frame 0
+    assert r1[-1][1:] == r1[0][1:] and [s[1] for s in r1].count('catA') == 8
     # ---- two gloo ranks
     s = socket.socket()
     s.bind(('127.0.0.1', 0))
@@ -138,7 +140,8 @@ def test_two_rank_evaluation_equals_single_process(tmp_path, capsys):
 
 def test_ownership_helpers():
     assert eval_dp.steps_for(11, 1, 2) == 6 and eval_dp.steps_for(11, 2, 2) == 3 and eval_dp.steps_for(8, 4, 1) == 2
-    assert eval_dp.owned_indices(2, 2, 1, 2, 11) == [10, 11]        # 11 is past the end: the caller skips it
+    assert eval_dp.owned_indices(2, 2, 1, 2, 11) == [10, 11]        # 11 = the wrap-around duplicate of frame 0 (batch 2 scores 12)
+    assert eval_dp.virtual_total(11, 2) == 12 and eval_dp.virtual_total(11, 1) == 11 and eval_dp.virtual_total(8, 4) == 8
     assert eval_dp.category_counters(['d/a/0', 'd/a/1', 'd/b/0', 'd/a/2']) == [1, 2, 1, 3]
     assert eval_dp.merge_scores([(1, 'a', 0.5, 0.1), (0, 'a', 0.2, 0.3)]) == [(0, 'a', 0.2, 0.3), (1, 'a', 0.5, 0.1)]
     lines = []

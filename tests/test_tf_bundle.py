@@ -323,3 +323,117 @@ def test_bundle_roundtrip_random_tensors(tmp_path_factory, specs, seed):
     assert set(r) == set(t)
     for k in t:
         assert r[k].dtype == t[k].dtype and r[k].shape == t[k].shape and np.array_equal(r[k], t[k])
+
+
+# ------------------------------------------------------------------------------------------- foreign bytes: a whole bundle by hand
+def _py_crc32c(data):
+    """Bit-by-bit CRC-32C (Castagnoli, reflected polynomial 0x82F63B78) -- deliberately independent of libcis_b200's table-driven
+    routine and of every encoder in checkpoint/tf_bundle.py."""
+    crc = 0xffffffff
+    for b in bytes(data):
+        crc ^= b
+        for _ in range(8):
+            crc = (crc >> 1) ^ (0x82F63B78 & -(crc & 1))
+    return crc ^ 0xffffffff
+
+
+def _py_mask(c):
+    return ((((c >> 15) | (c << 17)) & 0xffffffff) + 0xa282ead8) & 0xffffffff
+
+
+def _pb_varint(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7f
+        v >>= 7
+        out.append(b | (0x80 if v else 0))
+        if not v:
+            return bytes(out)
+
+
+def _pb_field(num, wt, payload):
+    return _pb_varint((num << 3) | wt) + payload
+
+
+def _entry_proto(dtype, dims, offset, size, crc):
+    # BundleEntryProto: dtype = 1 (varint), shape = 2 (TensorShapeProto: repeated Dim dim = 2 {int64 size = 1}), shard_id = 3,
+    # offset = 4, size = 5, crc32c = 6 (fixed32); proto3 omits zero-valued scalars, as TF's serializer does
+    shape = b''.join(_pb_field(2, 2, _pb_varint(len(d)) + d) for d in (_pb_field(1, 0, _pb_varint(n)) for n in dims))
+    out = _pb_field(1, 0, _pb_varint(dtype)) + _pb_field(2, 2, _pb_varint(len(shape)) + shape)
+    if offset:
+        out += _pb_field(4, 0, _pb_varint(offset))
+    out += _pb_field(5, 0, _pb_varint(size)) + _pb_field(6, 5, struct.pack('<I', crc))
+    return out
+
+
+def _foreign_block(entries):
+    """LevelDB data block with shared-prefix compression and a restart point every 2 entries (TF uses 16; any interval is legal)."""
+    body, restarts, prev = bytearray(), [], b''
+    for i, (k, v) in enumerate(entries):
+        shared = 0
+        if i % 2 == 0:
+            restarts.append(len(body))
+        else:
+            while shared < min(len(prev), len(k)) and prev[shared] == k[shared]:
+                shared += 1
+        body += _pb_varint(shared) + _pb_varint(len(k) - shared) + _pb_varint(len(v)) + k[shared:] + v
+        prev = k
+    for r in restarts:
+        body += struct.pack('<I', r)
+    body += struct.pack('<I', len(restarts))
+    return bytes(body)
+
+
+def _foreign_trailer(body):
+    return body + b'\x00' + struct.pack('<I', _py_mask(_py_crc32c(body + b'\x00')))
+
+
+def test_read_a_bundle_assembled_by_hand_from_the_published_format(tmp_path):
+    """`.index` + `.data-00000-of-00001` built byte by byte here (own varints, protos, block builder with prefix compression, own bitwise
+    CRC-32C) -- nothing from write_bundle / write_table / cis_crc32c -- with the reference's variable naming (`MaskNet//...` double
+    slash, adversarial_learner.py:211-214; `global_step`), two data blocks, non-zero offsets: the reader and the name map must take it."""
+    rng = np.random.RandomState(3)
+    tensors = [('FlownetS//aconv1/biases', rng.randn(16).astype(np.float32)),
+               ('MaskNet//conv1/bias', rng.randn(32).astype(np.float32)),
+               ('MaskNet//conv1/kernel', rng.randn(5, 5, 5, 32).astype(np.float32)),
+               ('global_step', np.asarray(1234, dtype=np.int64))]
+    data, entries = bytearray(), []
+    for name, arr in tensors:                       # keys are already in sorted (byte) order, as a table requires
+        raw = arr.tobytes()
+        dt = 1 if arr.dtype == np.float32 else 9
+        entries.append((name.encode(), _entry_proto(dt, list(arr.shape), len(data), len(raw), _py_mask(_py_crc32c(raw)))))
+        data += raw
+    header = _pb_field(1, 0, _pb_varint(1)) + _pb_field(3, 2, _pb_varint(2) + _pb_field(1, 0, _pb_varint(1)))   # num_shards = 1, version {producer 1}
+    b0 = _foreign_block([(b'', header)] + entries[:2])
+    b1 = _foreign_block(entries[2:])
+    meta = _foreign_block([])
+    off1 = len(b0) + 5
+    offm = off1 + len(b1) + 5
+    offi = offm + len(meta) + 5
+    handle = lambda o, n: _pb_varint(o) + _pb_varint(n)
+    # index block: one entry per data block, key >= last key of the block (the separator TF/LevelDB would shorten; any such key is legal)
+    idx = _foreign_block([(entries[1][0] + b'\x00', handle(0, len(b0))), (b'h', handle(off1, len(b1)))])
+    footer = handle(offm, len(meta)) + handle(offi, len(idx))
+    footer += b'\x00' * (40 - len(footer)) + struct.pack('<Q', 0xdb4775248b80fb57)
+    prefix = str(tmp_path / 'model-1234')
+    with open(prefix + '.index', 'wb') as f:
+        f.write(_foreign_trailer(b0) + _foreign_trailer(b1) + _foreign_trailer(meta) + _foreign_trailer(idx) + footer)
+    with open(prefix + '.data-00000-of-00001', 'wb') as f:
+        f.write(bytes(data))
+    assert tb.is_bundle(prefix)
+    got = tb.read_bundle(prefix)
+    assert sorted(got) == sorted(n for n, _ in tensors)
+    for name, arr in tensors:
+        assert got[name].dtype == arr.dtype and got[name].shape == arr.shape and np.array_equal(got[name], arr), name
+    # the independent CRC agrees with the library routine the reader verifies with
+    assert _py_crc32c(b'123456789') == 0xE3069283 == tb.crc32c(b'123456789')
+    # name map: the internal (single-slash) names of this repo pick the double-slash TF variables
+    from unsupervised_detection_b200.checkpoint import tf_names
+    picked, gs = tf_names.import_params(got, ['MaskNet/conv1/kernel', 'MaskNet/conv1/bias', 'FlownetS/aconv1/biases'])
+    assert gs == 1234 and np.array_equal(picked['MaskNet/conv1/kernel'], tensors[2][1])
+    # a flipped payload byte in the data shard is caught by the per-tensor checksum written by the foreign writer
+    raw = bytearray(open(prefix + '.data-00000-of-00001', 'rb').read())
+    raw[70] ^= 0x10
+    open(prefix + '.data-00000-of-00001', 'wb').write(bytes(raw))
+    with pytest.raises(IOError, match='checksum'):
+        tb.read_bundle(prefix)

@@ -34,7 +34,7 @@ class CisConv(C.Structure):
                 ('halo', C.c_int32), ('dil', C.c_int32), ('MT', C.c_int32), ('hoy', C.c_int32), ('hox', C.c_int32),
                 ('ey', C.c_int32), ('ex', C.c_int32),
                 ('splits', C.c_int32), ('sk_scratch', C.c_void_p), ('sk_counters', C.c_void_p),
-                ('nph', C.c_int32), ('ph_tap', C.c_int32 * 5)]
+                ('nph', C.c_int32), ('ph_tap', C.c_int32 * 5), ('sk_cluster', C.c_int32)]
 
 
 class CisWgrad(C.Structure):

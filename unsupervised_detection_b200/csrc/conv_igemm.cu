@@ -277,6 +277,47 @@ __device__ __forceinline__ void splitk_reduce16(const float* tile0, int nsplit, 
     }
   }
 }
+// Cluster split-K: every CTA of the cluster has written its partial tile to its own shared memory as float4 columns
+// stage[(c4 * 128 + row)] (conflict-free: lanes = consecutive rows).  CTA `rank` of `S` then owns accumulator rows
+// [rank * rpc, (rank + 1) * rpc): it sums the S partials in rank order (deterministic) through DSMEM and runs the fused epilogue.
+template <int BN, typename DPIX>
+__device__ __forceinline__ void cluster_reduce_rows(const CisConv& p, const uint32_t stage, const int S, const int rank, const int tid,
+                                                    const int nthreads, const int cbase, DPIX dpix_of) {
+  const int rpc = (kBM + S - 1) / S;
+  const int r0 = rank * rpc, r1 = min(kBM, r0 + rpc);
+  constexpr int G16 = BN / 16;
+  for (int it = tid; it < (r1 - r0) * G16; it += nthreads) {
+    const int row = r0 + it / G16, c0 = (it % G16) * 16;
+    float v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = 0.f;
+    for (int q = 0; q < S; ++q) {
+      const uint32_t base = dsmem_addr(stage, (uint32_t)q);
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float4 t = dsmem_ld4(base + (uint32_t)(((c0 / 4 + h) * kBM + row) * 16));
+        v[4 * h] += t.x; v[4 * h + 1] += t.y; v[4 * h + 2] += t.z; v[4 * h + 3] += t.w;
+      }
+    }
+    bool valid;
+    const size_t dpix = dpix_of(row, valid);
+    if (valid) epi_chunk(p, v, cbase + c0, dpix);
+  }
+}
+// this warp's 32 accumulator rows x columns [c_lo, c_hi) -> shared-memory stage in the layout above
+__device__ __forceinline__ void tmem_to_stage(const uint32_t t_row, const int row, const uint32_t stage, const int c_lo, const int c_hi) {
+#pragma unroll 1
+  for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
+    float v[16];
+    tmem_ld16(t_row + c0, v);
+#pragma unroll
+    for (int h = 0; h < 4; ++h)
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stage + (uint32_t)(((c0 / 4 + h) * kBM + row) * 16)), "f"(v[4 * h]),
+                   "f"(v[4 * h + 1]), "f"(v[4 * h + 2]), "f"(v[4 * h + 3])
+                   : "memory");
+  }
+}
+
 template <int BN>
 struct FwdCfg {
   static constexpr int kStages = (BN == 128) ? 3 : 4;
@@ -446,7 +487,10 @@ __global__ void __launch_bounds__(kGThreads) conv_igemm_kernel(const __grid_cons
     const int cbase = ny * BN;
     constexpr int kHalf = BN >= 32 ? BN / 2 : BN;                 // BN = 16: the first warp group does it all
     const int c_lo = half * kHalf, c_hi = (BN >= 32 || half == 0) ? c_lo + kHalf : c_lo;
-    if (nsplit > 1) {
+    if (nsplit > 1 && p.sk_cluster) {
+      // cluster split-K: partial tile -> own shared memory (the operand ring is dead: every MMA has completed); reduced below
+      tmem_to_stage(t_row, row, tile_base, c_lo, c_hi);
+    } else if (nsplit > 1) {
       // two-launch split-K: this split's private fp32 slice; splitk_finish_kernel reduces the slices and runs the fused epilogue
       const int tile_id = blockIdx.x * gridDim.y + ny;
       float* tile0 = p.sk_scratch + (size_t)tile_id * nsplit * kBM * BN;
@@ -475,6 +519,23 @@ __global__ void __launch_bounds__(kGThreads) conv_igemm_kernel(const __grid_cons
       __syncwarp();
     }
   }
+  if (nsplit > 1 && p.sk_cluster) {
+    cluster_sync_all();                       // every CTA's partial tile is in its shared memory
+    if (warp < kMmaWarp) {
+      const int cbase = ny * BN;
+      cluster_reduce_rows<BN>(p, tile_base, nsplit, (int)cluster_ctarank(), tid, kGProducers, cbase, [&](int row, bool& valid) -> size_t {
+        const int g = blockIdx.x * kBM + row;
+        valid = g < M;
+        if (!valid) return 0;
+        const int ow = g % p.OW;
+        const int t = g / p.OW;
+        const int oh = t % p.OH;
+        const int n = t / p.OH;
+        return (size_t)(n * p.DH + oh * p.osh + p.oa) * p.DW + ow * p.osw + p.ob;
+      });
+    }
+    cluster_sync_all();                       // peers may still be reading this CTA's shared memory
+  }
   tc_fence_before();
   __syncthreads();
   if (tid == 0) CIS_TRACE_AT(3);
@@ -496,20 +557,32 @@ struct HaloMaps {
   CUtensorMap m[CIS_MAX_SRC * 4];
 };
 
-// MMAs of one weight stage (gt taps of one 64-channel chunk, MT stacked tiles, NK K=16 steps each), issued by ONE thread.
+// MMAs of one weight stage (gt taps of one 64-channel chunk, MT stacked tiles, NK K=16 steps each), issued by ONE thread.  The tap
+// offsets come from a shared-memory table; the next tap's offset is fetched BEFORE the current tap's MMAs are issued so the
+// LDS -> R2UR -> descriptor chain (~100 clk, measured 220 clk per single-MMA tap in r02) overlaps the previous issue.
 template <int NK>
 __device__ __forceinline__ void halo_issue_stage(const uint32_t tmem, const uint32_t hlo, uint32_t blo, const uint32_t* s_aoff, const int gt,
                                                  const int MT, const int BN, const uint32_t ahi, const uint32_t bhi, const uint32_t a_mstep,
                                                  const uint32_t idesc, const bool first) {
   const uint32_t bstep = (uint32_t)(BN * 128) >> 4;
+  uint32_t off0 = s_aoff[0], off1 = gt > 1 ? s_aoff[1] : 0u;
+#pragma unroll 2
   for (int tt = 0; tt < gt; ++tt, blo += bstep) {
-    uint32_t alo = hlo + s_aoff[tt];
+    const uint32_t off2 = tt + 2 < gt ? s_aoff[tt + 2] : 0u;    // two taps ahead
+    uint32_t alo = hlo + off0;
     const uint32_t acc0 = (uint32_t)(!(first && tt == 0));
-    for (int m = 0; m < MT; ++m, alo += a_mstep) {
-      const uint32_t td = tmem + m * BN;
+    if (MT == 1) {
 #pragma unroll
-      for (int k = 0; k < NK; ++k) umma_bf16_lh(td, alo + 2 * k, ahi, blo + 2 * k, bhi, idesc, k ? 1u : acc0);
+      for (int k = 0; k < NK; ++k) umma_bf16_lh(tmem, alo + 2 * k, ahi, blo + 2 * k, bhi, idesc, k ? 1u : acc0);
+    } else {
+      for (int m = 0; m < MT; ++m, alo += a_mstep) {
+        const uint32_t td = tmem + m * BN;
+#pragma unroll
+        for (int k = 0; k < NK; ++k) umma_bf16_lh(td, alo + 2 * k, ahi, blo + 2 * k, bhi, idesc, k ? 1u : acc0);
+      }
     }
+    off0 = off1;
+    off1 = off2;
   }
 }
 
@@ -706,7 +779,11 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     const int r = warp * 32 + lane;
     const int cbase = ny * BN;
     const int tile_id = blockIdx.x * gridDim.y + ny;
-    if (nsplit > 1) {
+    if (nsplit > 1 && p.sk_cluster) {
+      // cluster split-K: the MT partial tiles -> own shared memory (operand buffers are dead: every MMA has completed); reduced below
+      for (int m = 0; m < MT; ++m)
+        tmem_to_stage(tmem + ((uint32_t)(warp * 32) << 16) + m * BN, r, tile_base + (uint32_t)m * (kBM * BN * 4), 0, BN);
+    } else if (nsplit > 1) {
       // two-launch split-K: this split's private fp32 slices; splitk_finish_kernel reduces them and runs the fused epilogue
       for (int m = 0; m < MT; ++m)
         splitk_store_partial<BN>(p.sk_scratch + (((size_t)tile_id * MT + m) * nsplit + blockIdx.z) * kBM * BN,
@@ -771,12 +848,26 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
       }
     }
   }
+  if (nsplit > 1 && p.sk_cluster) {
+    cluster_sync_all();                       // every CTA's partial tiles are in its shared memory
+    if (warp < 4) {
+      const int cbase = ny * BN;
+      for (int m = 0; m < MT; ++m)
+        cluster_reduce_rows<BN>(p, tile_base + (uint32_t)m * (kBM * BN * 4), nsplit, (int)cluster_ctarank(), tid, 128, cbase,
+                                [&](int row, bool& valid) -> size_t {
+                                  const int gy = ty * 16 * MT + 16 * m + (row >> 3), gx = tx * 8 + (row & 7);
+                                  const int oy = pa + d * gy, ox = pb + d * gx;
+                                  valid = oy < p.OH && ox < p.OW;
+                                  return valid ? ((size_t)(n * p.DH + oy * p.osh + p.oa) * p.DW + ox * p.osw + p.ob) : 0;
+                                });
+    }
+    cluster_sync_all();                       // peers may still be reading this CTA's shared memory
+  }
   tc_fence_before();
   __syncthreads();
   if (tid == 0) CIS_TRACE_AT(3);
   if (warp == 4) tmem_dealloc_dyn(tmem, ncols);
 }
-
 
 // ======================================================================================================= split-K finish
 // Second launch of split-K.  (Round 1 let the last-arriving CTA of a tile read all nsplit x 64 KB slices by itself -- one SM pulling up
@@ -905,6 +996,10 @@ __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __gr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (tid == 0) {
+    CIS_TRACE_AT(0);
+    CIS_TRACE_AT(4);      // slot 4 marks a persistent-kernel trace (tools/trace_persist.py)
+  }
 
   if (warp == 0) {
     // ------------------------------------------------------------------ halo producer
@@ -977,14 +1072,18 @@ __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __gr
       mbar_wait(bar_bfull, 0u);      // the resident weight set; never released
       tc_fence_after();
     }
-    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    int wi = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++wi) {
+      if (lane == 0) CIS_TRACE_AT(8 + 5 * wi);
       mbar_wait(bar_tempty + 8 * as, tph);
       tc_fence_after();
+      if (lane == 0) CIS_TRACE_AT(9 + 5 * wi);
       const uint32_t tacc = tmem + as * acc_cols;
       for (int cc = 0; cc < nchunks; ++cc) {
         const int rem = m_chunks - cc * 8;
         const int nk16 = rem >= 8 ? 4 : (rem + 1) / 2;
         mbar_wait(bar_hfull + 8 * hs, hph);
+        if (cc == 0 && lane == 0) CIS_TRACE_AT(10 + 5 * wi);
         const uint32_t hlo = desc_lo(h_base + hs * halo_stage_bytes, 16);
         const int gstep = ws ? p.ntaps : G;
         for (int t0 = 0; t0 < p.ntaps; t0 += gstep) {
@@ -1001,7 +1100,10 @@ __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __gr
             if (!ws) umma_commit(bar_bempty + 8 * bs);
             if (t0 + gstep >= p.ntaps) {
               umma_commit(bar_hempty + 8 * hs);
-              if (cc == nchunks - 1) umma_commit(bar_tfull + 8 * as);
+              if (cc == nchunks - 1) {
+                umma_commit(bar_tfull + 8 * as);
+                CIS_TRACE_AT(11 + 5 * wi);
+              }
             }
           }
           __syncwarp();
@@ -1042,6 +1144,7 @@ __global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __gr
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_tempty + 8 * grp);
+        if (q == 0 && lane == 0) CIS_TRACE_AT(12 + 5 * wi);
       }
     }
   }
@@ -1445,6 +1548,27 @@ static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// launch_pdl + a thread-block cluster along grid.z (the split-K CTAs of one tile)
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl_zcluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cz, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = cz;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <int BN>
 static cudaError_t launch_splitk_finish(const CisConv* d, dim3 main_grid, cudaStream_t st) {
   constexpr int G = BN / 16;
@@ -1467,12 +1591,15 @@ static int launch_fwd(const CisConv* d, cudaStream_t st) {
   int splits = d->splits > 1 ? d->splits : 1;
   if (splits > 1) {
     const int nkb = d->K_pad / kBK, per = (nkb + splits - 1) / splits;
-    if (!d->sk_scratch || d->sk_counters || (splits - 1) * per >= nkb) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm: bad split-K setup");
+    if ((!d->sk_scratch && !d->sk_cluster) || d->sk_counters || (splits - 1) * per >= nkb || (d->sk_cluster && splits > 8))
+      return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm: bad split-K setup");
   }
   dim3 grid((M + kBM - 1) / kBM, d->n_tiles, splits);
-  cudaError_t le = launch_pdl(conv_igemm_kernel<BN>, grid, dim3(kGThreads), Cfg::kSmem, st, *d);
+  cudaError_t le = (splits > 1 && d->sk_cluster)
+                       ? launch_pdl_zcluster(conv_igemm_kernel<BN>, grid, dim3(kGThreads), Cfg::kSmem, st, splits, *d)
+                       : launch_pdl(conv_igemm_kernel<BN>, grid, dim3(kGThreads), Cfg::kSmem, st, *d);
   if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_igemm)");
-  if (splits > 1) {
+  if (splits > 1 && !d->sk_cluster) {
     le = launch_splitk_finish<BN>(d, grid, st);
     if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(splitk_finish)");
   }
@@ -1555,7 +1682,9 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   if (BS > (ncta_all > 148 ? 4 : kHaloMaxBStages)) BS = ncta_all > 148 ? 4 : kHaloMaxBStages;
   if (BS > groups) BS = groups;
   if (BS < 1) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_conv_igemm(halo): tile does not fit shared memory");
-  const int smem = fixed + BS * G * kB;
+  int smem = fixed + BS * G * kB;
+  if (nsp > 1 && d->sk_cluster && smem < d->MT * kBM * BN * 4 + 1024) smem = d->MT * kBM * BN * 4 + 1024;   // fp32 staging tiles of the cluster reduction
+  if (smem > 226 * 1024) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_conv_igemm(halo): cluster split-K staging does not fit shared memory");
   static int attr_smem = 0;
   if (smem > attr_smem) {
     cudaError_t e = cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1566,7 +1695,8 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   int splits = d->splits > 1 ? d->splits : 1;
   if (splits > 1) {
     const int per = (nchunks + splits - 1) / splits;
-    if (!d->sk_scratch || d->sk_counters || (splits - 1) * per >= nchunks) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm(halo): bad split-K setup");
+    if ((!d->sk_scratch && !d->sk_cluster) || d->sk_counters || (splits - 1) * per >= nchunks || (d->sk_cluster && splits > 8))
+      return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm(halo): bad split-K setup");
   }
   dim3 grid(tiles * dd * dd * d->N, d->n_tiles, splits);
   // TMA halo path: undilated, every concat source except the last a multiple of 64 channels (a chunk never straddles sources)
@@ -1627,9 +1757,11 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
       return cis_check_launch("conv_halo_persist");
     }
   }
-  cudaError_t le = launch_pdl(conv_halo_kernel<BN>, grid, dim3(kThreads), smem, st, *d, halo_stage, BS, nhs, maps, use_tma, G);
+  cudaError_t le = (splits > 1 && d->sk_cluster)
+                       ? launch_pdl_zcluster(conv_halo_kernel<BN>, grid, dim3(kThreads), smem, st, splits, *d, halo_stage, BS, nhs, maps, use_tma, G)
+                       : launch_pdl(conv_halo_kernel<BN>, grid, dim3(kThreads), smem, st, *d, halo_stage, BS, nhs, maps, use_tma, G);
   if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_halo)");
-  if (splits > 1) {
+  if (splits > 1 && !d->sk_cluster) {
     le = launch_splitk_finish<BN>(d, grid, st);
     if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(splitk_finish)");
   }

@@ -117,7 +117,7 @@ class Plan(object):
             n += 1
             if name == 'cis_conv_igemm':
                 d = args[0]._obj
-                if d.splits > 1:
+                if d.splits > 1 and not d.sk_cluster:
                     n += 1
         return n
 
@@ -254,6 +254,7 @@ def _pow2_cols(c):
 # split-K of launches that cover only a few SMs (low-resolution pyramid levels): 0 = off, 2 = on (two launches: private partial slices +
 # a parallel finish kernel with a fixed summation order; measured r02: -0.4 ms per step)
 SPLITK = int(os.environ.get('CIS_SPLITK', '2'))
+SPLITK_CLUSTER = os.environ.get('CIS_SPLITK_CLUSTER', '0') == '1'   # reduce through a thread-block cluster (DSMEM) instead of the finish launch
 SPLITK_MAX = int(os.environ.get('CIS_SPLITK_MAX', '16'))
 SPLITK_NCTA = int(os.environ.get('CIS_SPLITK_NCTA', '64'))          # only launches with at most this many CTAs are split
 SPLITK_MIN_UNITS = int(os.environ.get('CIS_SPLITK_MIN_UNITS', '18'))  # ... and at least this many serial pipeline steps per CTA
@@ -282,12 +283,16 @@ def setup_splitk(d, device, keep):
     steps = units * (d.ntaps if d.halo else 1)     # serial pipeline steps of one CTA (halo: one per (chunk, tap); generic: one per 64-wide K block)
     if ncta > SPLITK_NCTA or steps < SPLITK_MIN_UNITS:
         return
-    splits = min(units // min_units, -(-2 * NUM_SMS // ncta), SPLITK_MAX)
+    splits = min(units // min_units, -(-2 * NUM_SMS // ncta), SPLITK_MAX, 8 if SPLITK_CLUSTER else 1 << 30)
     if splits < 2:
         return
     per = -(-units // splits)
     splits = -(-units // per)
     if splits < 2:
+        return
+    if SPLITK_CLUSTER and splits <= 8 and mt * 128 * d.BN * 4 + 1024 <= 226 * 1024:
+        # the splits of a tile form a thread-block cluster and reduce through distributed shared memory: no scratch, no second launch
+        d.splits, d.sk_scratch, d.sk_counters, d.sk_cluster = splits, None, None, 1
         return
     sc = torch.empty(ncta * mt * splits * 128 * d.BN, dtype=torch.float32, device=device)
     keep.append(sc)

@@ -19,8 +19,8 @@ def dist_info():
 
 
 def owned_indices(step, local_n, rank, world, total):
-    """Global list positions of the `local_n` samples rank `rank` reads in step `step` (global batch = local_n * world); positions
-    >= total are wrap-around duplicates of the endless iterator and must be skipped."""
+    """Global list positions of the `local_n` samples rank `rank` reads in step `step` (global batch = local_n * world); position g is
+    frame g % total of the endless iterator; positions >= virtual_total(total, batch) are beyond what the single-process script scores."""
     base = step * local_n * world + rank * local_n
     return [base + j for j in range(local_n)]
 
@@ -28,6 +28,14 @@ def owned_indices(step, local_n, rank, world, total):
 def steps_for(total, local_n, world):
     gb = local_n * world
     return -(-total // gb)
+
+
+def virtual_total(total, batch):
+    """Number of frames the single-process script scores: ceil(total / batch) batches of the endless ordered iterator, i.e. the last
+    batch wraps around and its head frames are scored (and written) a second time -- the reference does exactly that
+    (test_generator.py:62-64 with dataset.repeat()).  The sharded loop scores the same virtual sequence, position g -> frame g % total,
+    so 1-rank and N-rank reports agree with the single-process one for any total % batch."""
+    return -(-total // batch) * batch
 
 
 def category_counters(names):

@@ -91,6 +91,17 @@ typedef struct {
   /* 1: the `splits` CTAs of a tile form a thread-block cluster (2..8 CTAs) and reduce their partial accumulators through distributed
    * shared memory inside the conv kernel (fixed summation order, fused epilogue spread over the cluster): no sk_scratch, no second launch. */
   int32_t sk_cluster;
+  /* Grouped launch (halo kernel, splits <= 1): nsub = 2..4 sub-problems that share sources, epilogue, BN / n_tiles / MT and the halo box
+   * (ey, ex) but have their own tap set, halo origin, packed weights, output extent and output offset -- the four output-parity
+   * launches of a stride-2 data gradient or of conv2d_transpose(k4, s2) as ONE launch (blockIdx.z = sub-problem).  The taps of all
+   * sub-problems are listed back to back in dh / dw (ntaps = their total); nsub = 0/1: ordinary launch. */
+  int32_t nsub;
+  struct {
+    int32_t tap0, ntaps;      /* this sub-problem's taps: dh/dw[tap0 .. tap0 + ntaps) */
+    int32_t hoy, hox;         /* halo origin relative to the output tile */
+    int32_t OH, OW, oa, ob;   /* output extent and offset inside the (DH, DW) destination grid (stride osh / osw) */
+    const void* wpack;        /* pre-tiled weights of this sub-problem */
+  } sub[4];
 } CisConv;
 
 /* Weight gradient of the same convolution: dWp[co][(t,c)] = sum_rows g[row][co] * A[row][(t,c)]  (fp32).  The reduction over rows

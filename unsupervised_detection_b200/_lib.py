@@ -17,6 +17,11 @@ class CisSrc(C.Structure):
     _fields_ = [('ptr', C.c_void_p), ('pitch', C.c_int32), ('c_off', C.c_int32), ('chunks', C.c_int32), ('n_mod', C.c_int32)]
 
 
+class CisSub(C.Structure):
+    _fields_ = [('tap0', C.c_int32), ('ntaps', C.c_int32), ('hoy', C.c_int32), ('hox', C.c_int32), ('OH', C.c_int32), ('OW', C.c_int32),
+                ('oa', C.c_int32), ('ob', C.c_int32), ('wpack', C.c_void_p)]
+
+
 class CisConv(C.Structure):
     _fields_ = [('N', C.c_int32), ('H', C.c_int32), ('W', C.c_int32), ('OH', C.c_int32), ('OW', C.c_int32),
                 ('sh', C.c_int32), ('sw', C.c_int32), ('ntaps', C.c_int32),
@@ -34,7 +39,8 @@ class CisConv(C.Structure):
                 ('halo', C.c_int32), ('dil', C.c_int32), ('MT', C.c_int32), ('hoy', C.c_int32), ('hox', C.c_int32),
                 ('ey', C.c_int32), ('ex', C.c_int32),
                 ('splits', C.c_int32), ('sk_scratch', C.c_void_p), ('sk_counters', C.c_void_p),
-                ('nph', C.c_int32), ('ph_tap', C.c_int32 * 5), ('sk_cluster', C.c_int32)]
+                ('nph', C.c_int32), ('ph_tap', C.c_int32 * 5), ('sk_cluster', C.c_int32),
+                ('nsub', C.c_int32), ('sub', CisSub * 4)]
 
 
 class CisWgrad(C.Structure):

@@ -613,9 +613,17 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   const uint32_t bar_bfull = smem_u32(&bars[4]), bar_bempty = smem_u32(&bars[4 + kHaloMaxBStages]);
   const uint32_t bar_accum = smem_u32(&bars[4 + 2 * kHaloMaxBStages]);
 
+  // ---- grouped launch: blockIdx.z selects one of nsub sub-problems (own taps, halo origin, weights, output extent / offset)
+  const bool grouped = p.nsub > 1;
+  const int tap0 = grouped ? p.sub[blockIdx.z].tap0 : 0, ntaps = grouped ? p.sub[blockIdx.z].ntaps : p.ntaps;
+  const int hoy = grouped ? p.sub[blockIdx.z].hoy : p.hoy, hox = grouped ? p.sub[blockIdx.z].hox : p.hox;
+  const int OHs = grouped ? p.sub[blockIdx.z].OH : p.OH, OWs = grouped ? p.sub[blockIdx.z].OW : p.OW;
+  const int oa = grouped ? p.sub[blockIdx.z].oa : p.oa, ob = grouped ? p.sub[blockIdx.z].ob : p.ob;
+  const void* const wpack = grouped ? p.sub[blockIdx.z].wpack : p.wpack;
   // ---- tile decode: blockIdx.x -> (tx, ty, phase, n)
-  const int Hp0 = (p.OH + d - 1) / d, Wp0 = (p.OW + d - 1) / d;
+  const int Hp0 = (OHs + d - 1) / d, Wp0 = (OWs + d - 1) / d;
   const int tiles_x = (Wp0 + 7) / 8, tiles_y = (Hp0 + 16 * MT - 1) / (16 * MT);
+  if (grouped && (int)blockIdx.x >= tiles_x * tiles_y * p.N) return;   // the grid is sized for the largest sub-problem (uniform per CTA)
   int bid = blockIdx.x;
   const int tx = bid % tiles_x; bid /= tiles_x;
   const int ty = bid % tiles_y; bid /= tiles_y;
@@ -626,16 +634,15 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   int m_chunks = 0;
   for (int i = 0; i < p.nsrc; ++i) m_chunks += p.src[i].chunks;
   const int nchunks_all = (m_chunks + 7) / 8;  // 64-channel chunks
-  const int nsplit = p.splits > 1 ? p.splits : 1;
+  const int nsplit = (!grouped && p.splits > 1) ? p.splits : 1;
   const int cper = (nchunks_all + nsplit - 1) / nsplit;
-  const int cc_lo = blockIdx.z * cper;
+  const int cc_lo = grouped ? 0 : blockIdx.z * cper;
   const int nchunks = min(cper, nchunks_all - cc_lo);   // chunks handled by this CTA (host guarantees >= 1)
-  const int cin8 = m_chunks * 8;
   __shared__ __align__(16) float s_bias[BN];
   pdl_launch_dependents();
   const uint32_t ncols = (MT * BN <= 32) ? 32u : (MT * BN <= 64) ? 64u : (MT * BN <= 128) ? 128u : (MT * BN <= 256) ? 256u : 512u;
 
-  if (tid < p.ntaps) s_aoff[tid] = (uint32_t)((p.dh[tid] * Wh + p.dw[tid]) * 8);   // * 128 B / 16
+  if (tid < ntaps) s_aoff[tid] = (uint32_t)((p.dh[tap0 + tid] * Wh + p.dw[tap0 + tid]) * 8);   // * 128 B / 16
   if (tid < p.nsrc) {
     s_src[tid].ptr = reinterpret_cast<const __nv_bfloat16*>(p.src[tid].ptr);
     s_src[tid].pitch = p.src[tid].pitch;
@@ -645,7 +652,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   }
   for (int q = tid; q < (use_tma ? 0 : HP); q += kThreads) {
     const int hy = q / Wh, hx = q - hy * Wh;
-    const int gy = ty * 16 * MT + hy + p.hoy, gx = tx * 8 + hx + p.hox;
+    const int gy = ty * 16 * MT + hy + hoy, gx = tx * 8 + hx + hox;
     const int y = pa + d * gy, x = pb + d * gx;
     pixtab[q] = (gy >= 0 && gx >= 0 && y < p.H && x < p.W) ? (y * p.W + x) : -1;
   }
@@ -695,7 +702,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
           }
           const int nmod = s_src[si].n_mod;
           mbar_expect_tx(bar_hfull + 8 * hs, (uint32_t)(HP * 128));
-          tma_load_4d(h_base + hs * halo_stage_bytes, &maps.m[si * nph + ph], bar_hfull + 8 * hs, c * 8, tx * 8 + p.hox, ty * 16 * MT + p.hoy,
+          tma_load_4d(h_base + hs * halo_stage_bytes, &maps.m[si * nph + ph], bar_hfull + 8 * hs, c * 8, tx * 8 + hox, ty * 16 * MT + hoy,
                       nmod ? (n % nmod) : n);
         }
       }
@@ -752,17 +759,17 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     if (tid == 64) {
       // weights: pre-swizzled [n-tile][chunk][tap] tiles of BN x 128 B (cis_pack_weights_tiled); the tiles of the G taps of a stage
       // are adjacent in that layout -> ONE bulk copy per pipeline stage
-      const uint8_t* wt = reinterpret_cast<const uint8_t*>(p.wpack) + ((size_t)ny * nchunks_all + cc_lo) * p.ntaps * kBStage;
+      const uint8_t* wt = reinterpret_cast<const uint8_t*>(wpack) + ((size_t)ny * nchunks_all + cc_lo) * ntaps * kBStage;
       int bs = 0;
       uint32_t bph = 1;           // parity to wait for on the empty barrier: the first pass over the ring finds every stage free
       for (int vc = 0; vc < nchunks * nph; ++vc) {
         const int cc = vc / nph, ph = vc - cc * nph;
-        const int tlo = nph > 1 ? p.ph_tap[ph] : 0, thi = nph > 1 ? p.ph_tap[ph + 1] : p.ntaps;
+        const int tlo = nph > 1 ? p.ph_tap[ph] : 0, thi = nph > 1 ? p.ph_tap[ph + 1] : ntaps;
         for (int t0 = tlo; t0 < thi; t0 += G) {
           const uint32_t bytes = (uint32_t)min(G, thi - t0) * kBStage;
           mbar_wait(bar_bempty + 8 * bs, bph);
           mbar_expect_tx(bar_bfull + 8 * bs, bytes);
-          bulk_g2s(b_base + bs * stage_bytes, wt + (size_t)(cc * p.ntaps + t0) * kBStage, bytes, bar_bfull + 8 * bs);
+          bulk_g2s(b_base + bs * stage_bytes, wt + (size_t)(cc * ntaps + t0) * kBStage, bytes, bar_bfull + 8 * bs);
           if (++bs == BS) {
             bs = 0;
             bph ^= 1u;
@@ -792,8 +799,8 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
       for (int m = 0; m < MT; ++m) {
         const int gy = ty * 16 * MT + 16 * m + (r >> 3), gx = tx * 8 + (r & 7);
         const int oy = pa + d * gy, ox = pb + d * gx;
-        const bool valid = oy < p.OH && ox < p.OW;
-        const size_t dpix = valid ? ((size_t)(n * p.DH + oy * p.osh + p.oa) * p.DW + ox * p.osw + p.ob) : 0;
+        const bool valid = oy < OHs && ox < OWs;
+        const size_t dpix = valid ? ((size_t)(n * p.DH + oy * p.osh + oa) * p.DW + ox * p.osw + ob) : 0;
         epi_row<BN>(p, tmem + ((uint32_t)(warp * 32) << 16) + m * BN, cbase, dpix, valid, s_bias);
       }
     }
@@ -809,7 +816,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     bool any = false;
     for (int vc = 0; vc < nchunks * nph; ++vc) {
       const int cc = vc / nph, ph = vc - cc * nph;
-      const int tlo = nph > 1 ? p.ph_tap[ph] : 0, thi = nph > 1 ? p.ph_tap[ph + 1] : p.ntaps;
+      const int tlo = nph > 1 ? p.ph_tap[ph] : 0, thi = nph > 1 ? p.ph_tap[ph + 1] : ntaps;
       if (thi == tlo) continue;
       const int rem = m_chunks - (cc_lo + cc) * 8;
       const int nk16 = rem >= 8 ? 4 : (rem + 1) / 2;
@@ -857,8 +864,8 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
                                 [&](int row, bool& valid) -> size_t {
                                   const int gy = ty * 16 * MT + 16 * m + (row >> 3), gx = tx * 8 + (row & 7);
                                   const int oy = pa + d * gy, ox = pb + d * gx;
-                                  valid = oy < p.OH && ox < p.OW;
-                                  return valid ? ((size_t)(n * p.DH + oy * p.osh + p.oa) * p.DW + ox * p.osw + p.ob) : 0;
+                                  valid = oy < OHs && ox < OWs;
+                                  return valid ? ((size_t)(n * p.DH + oy * p.osh + oa) * p.DW + ox * p.osw + ob) : 0;
                                 });
     }
     cluster_sync_all();                       // peers may still be reading this CTA's shared memory
@@ -1659,25 +1666,41 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   int chunks = 0;
   for (int i = 0; i < d->nsrc; ++i) chunks += d->src[i].chunks;
   const int nchunks = (chunks + 7) / 8;
-  const int nsp = d->splits > 1 ? d->splits : 1;
+  const int nsub = d->nsub > 1 ? d->nsub : 1;                  // grouped launch: grid.z = sub-problem, no split-K
+  const int nsp = (nsub == 1 && d->splits > 1) ? d->splits : 1;
   const int cper = (nchunks + nsp - 1) / nsp;                  // 64-channel chunks per CTA
   const int nhs = cper > 1 ? 2 : 1;                            // halo stages: double-buffer only when there is a next chunk to prefetch
   const int dd = d->dil;
-  const int Hp0 = (d->OH + dd - 1) / dd, Wp0 = (d->OW + dd - 1) / dd;
-  const int tiles = ((Wp0 + 7) / 8) * ((Hp0 + 16 * d->MT - 1) / (16 * d->MT));
-  const long ncta_all = (long)tiles * dd * dd * d->N * d->n_tiles * nsp;
+  int tiles = 0, ntaps_max = d->ntaps;
+  if (nsub > 1) {
+    if (nsub > 4 || dd != 1 || d->splits > 1 || d->nph > 1) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm(halo): bad grouped launch");
+    ntaps_max = 0;
+    int tsum = 0;
+    for (int i = 0; i < nsub; ++i) {
+      const int t = ((d->sub[i].OW + 7) / 8) * ((d->sub[i].OH + 16 * d->MT - 1) / (16 * d->MT));
+      if (t > tiles) tiles = t;
+      if (d->sub[i].ntaps > ntaps_max) ntaps_max = d->sub[i].ntaps;
+      if (d->sub[i].ntaps < 1 || d->sub[i].tap0 != tsum || !d->sub[i].wpack) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm(halo): bad sub-problem");
+      tsum += d->sub[i].ntaps;
+    }
+    if (tsum != d->ntaps) return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm(halo): sub-problem taps must add up to ntaps");
+  } else {
+    const int Hp0 = (d->OH + dd - 1) / dd, Wp0 = (d->OW + dd - 1) / dd;
+    tiles = ((Wp0 + 7) / 8) * ((Hp0 + 16 * d->MT - 1) / (16 * d->MT));
+  }
+  const long ncta_all = (long)tiles * dd * dd * d->N * d->n_tiles * nsp * nsub;
   // ---- weight pipeline: G taps per stage (one bulk copy, one wait / commit of the MMA thread), BS stages
   static const int g_env = getenv("CIS_HALO_G") ? atoi(getenv("CIS_HALO_G")) : 0;            // experiments: force the group size
   static const int stage_kb = getenv("CIS_HALO_STAGE_KB") ? atoi(getenv("CIS_HALO_STAGE_KB")) : 48;
   const int kB = BN * 128;
   int G = g_env > 0 ? g_env : (stage_kb * 1024) / kB;
   if (G < 1) G = 1;
-  if (G > d->ntaps) G = d->ntaps;
+  if (G > ntaps_max) G = ntaps_max;
   const int fixed = nhs * halo_stage + HP * 4 + 1024;
   // two co-resident CTAs per SM overlap one CTA's epilogue with the other's main loop -- when the grid has that many CTAs
   const int limit = (ncta_all > 148 && fixed + 2 * kB <= 113 * 1024) ? 113 * 1024 : 226 * 1024;
   while (G > 1 && fixed + 2 * G * kB > limit) --G;
-  const int groups = cper * ((d->ntaps + G - 1) / G);          // pipeline stages one CTA walks
+  const int groups = cper * ((nsub > 1 ? 1 : (ntaps_max + G - 1) / G));   // pipeline stages one CTA walks (grouped: at least one per chunk)
   int BS = (limit - fixed) / (G * kB);
   if (BS > (ncta_all > 148 ? 4 : kHaloMaxBStages)) BS = ncta_all > 148 ? 4 : kHaloMaxBStages;
   if (BS > groups) BS = groups;
@@ -1698,7 +1721,7 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
     if ((!d->sk_scratch && !d->sk_cluster) || d->sk_counters || (splits - 1) * per >= nchunks || (d->sk_cluster && splits > 8))
       return cis_set_error(CIS_ERR_BAD_ARG, "cis_conv_igemm(halo): bad split-K setup");
   }
-  dim3 grid(tiles * dd * dd * d->N, d->n_tiles, splits);
+  dim3 grid(tiles * dd * dd * d->N, d->n_tiles, nsub > 1 ? nsub : splits);
   // TMA halo path: undilated, every concat source except the last a multiple of 64 channels (a chunk never straddles sources)
   HaloMaps maps;
   const int nph = d->nph > 1 ? d->nph : 1;
@@ -1718,7 +1741,7 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   const int persist_mode = g_persist_mode >= 0 ? g_persist_mode : (getenv("CIS_PERSIST_MODE") ? atoi(getenv("CIS_PERSIST_MODE")) : 1);
   static const int p_min_tiles = getenv("CIS_PERSIST_MIN_TILES") ? atoi(getenv("CIS_PERSIST_MIN_TILES")) : 296;
   static const int p_ws_kb = getenv("CIS_PERSIST_WS_KB") ? atoi(getenv("CIS_PERSIST_WS_KB")) : 112;
-  if (persist_mode > 0 && use_tma && d->n_tiles == 1 && splits == 1 && nph == 1) {
+  if (persist_mode > 0 && use_tma && d->n_tiles == 1 && splits == 1 && nph == 1 && nsub == 1) {
     const int total = tiles * d->N;
     const int per_tile = nchunks * d->ntaps;
     const int AS = (2 * d->MT * BN <= 512) ? 2 : 1;

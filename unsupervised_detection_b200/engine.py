@@ -407,6 +407,39 @@ def setup_halo_s2(d, taps, n_tiles):
     return order
 
 
+GROUP_PARITY = os.environ.get('CIS_GROUP_PARITY', '1') == '1'   # the 4 output-parity launches of a stride-2 dgrad / transposed conv as one
+
+
+def merge_parity_launches(descs):
+    """Four (or fewer) halo-kernel descriptors that differ only in taps / halo origin / weights / output extent and offset -> ONE grouped
+    descriptor (CisConv.nsub), or None when they cannot share a launch."""
+    if not GROUP_PARITY or not (2 <= len(descs) <= 4):
+        return None
+    d0 = descs[0]
+    same = ('N', 'H', 'W', 'BN', 'n_tiles', 'nsrc', 'act', 'DH', 'DW', 'osh', 'osw', 'out', 'out_pitch', 'out_coff', 'out_ch', 'outf', 'outf_pitch',
+            'outf_coff', 'outf_ch', 'add_pre', 'add_pre_pitch', 'add_pre_coff', 'add_post', 'addf_pre', 'mode', 'bias')
+    for d in descs:
+        if not d.halo or d.dil != 1 or d.splits > 1 or d.nph > 1 or any(getattr(d, f) != getattr(d0, f) for f in same):
+            return None
+        if any(bytes(d.src[i]) != bytes(d0.src[i]) for i in range(d0.nsrc)):
+            return None
+    if sum(d.ntaps for d in descs) > _lib.MAX_TAPS:
+        return None
+    g = CisConv.from_buffer_copy(bytes(d0))
+    g.MT, g.ey, g.ex = min(d.MT for d in descs), max(d.ey for d in descs), max(d.ex for d in descs)
+    g.OH, g.OW = max(d.OH for d in descs), max(d.OW for d in descs)
+    t = 0
+    for i, d in enumerate(descs):
+        for k in range(d.ntaps):
+            g.dh[t + k], g.dw[t + k] = d.dh[k], d.dw[k]
+        sb = g.sub[i]
+        sb.tap0, sb.ntaps, sb.hoy, sb.hox, sb.OH, sb.OW, sb.oa, sb.ob, sb.wpack = t, d.ntaps, d.hoy, d.hox, d.OH, d.OW, d.oa, d.ob, d.wpack
+        t += d.ntaps
+    m_chunks = sum(g.src[i].chunks for i in range(g.nsrc))
+    g.ntaps, g.nsub, g.splits, g.K_pad = t, len(descs), 0, ru(t * m_chunks * 8, 64)
+    return g
+
+
 class ParamStore(object):
     """One flat fp32 parameter buffer (+ grad, Adam m/v) per variable scope; names follow the TF variable layout
     (adversarial_learner.py:211-214 scopes 'MaskNet' / 'FlownetS'; model_pwcnet.py 'pwcnet')."""
@@ -819,6 +852,7 @@ class Builder(object):
             if not hasattr(layer, 'dcat'):
                 layer.dcat = Act(max(s.N for s in srcs), H, W, cin8, self.device, chanmap=layer.in_chanmap, name=layer.name + '.dcat')
             tgt, acc = layer.dcat, False
+        emitted = []
         for pk in layer.dgrad_packs:
             s = layer.stride
             oh = -(-(H - pk['a']) // s)
@@ -843,9 +877,16 @@ class Builder(object):
                 pk['rows_used'] = pk.get('rows_used', False)
             else:
                 pk['rows_used'] = True
-            setup_splitk(d, self.device, bp.keep)
-            bp.keep.append(d)
-            bp.add('cis_conv_igemm', C.byref(d), flops=2.0 * nb * oh * ow * len(pk['taps']) * layer.cin * layer.cout)
+            emitted.append((d, 2.0 * nb * oh * ow * len(pk['taps']) * layer.cin * layer.cout))
+        grp = merge_parity_launches([d for d, _ in emitted]) if len(emitted) > 1 else None
+        if grp is not None:
+            bp.keep.append(grp)
+            bp.add('cis_conv_igemm', C.byref(grp), flops=sum(f for _, f in emitted))
+        else:
+            for d, fl in emitted:
+                setup_splitk(d, self.device, bp.keep)
+                bp.keep.append(d)
+                bp.add('cis_conv_igemm', C.byref(d), flops=fl)
         if single:
             srcs[0].grad_written[mode] = True
         else:
@@ -928,6 +969,7 @@ class Builder(object):
         N, H, W = src.N, src.H, src.W
         if out is None:
             out = self.new_act(N, 2 * H, 2 * W, layer.cout, name=name or layer.name, dep=src.dep)
+        emitted = []
         for pk in layer.tr_packs:
             d = CisConv()
             d.N, d.H, d.W, d.OH, d.OW, d.sh, d.sw = N, H, W, H, W, 1, 1
@@ -946,10 +988,17 @@ class Builder(object):
                 pk['rows_used'] = pk.get('rows_used', False)
             else:
                 pk['rows_used'] = True
-            setup_splitk(d, self.device, plan.keep)
-            plan.keep.append(d)
             plan.keep += [src, out, outf, layer]
-            plan.add('cis_conv_igemm', C.byref(d), flops=2.0 * N * H * W * len(pk['taps']) * layer.cin * layer.cout)
+            emitted.append((d, 2.0 * N * H * W * len(pk['taps']) * layer.cin * layer.cout))
+        grp = merge_parity_launches([d for d, _ in emitted])
+        if grp is not None:
+            plan.keep.append(grp)
+            plan.add('cis_conv_igemm', C.byref(grp), flops=sum(f for _, f in emitted), lane=self.lane)
+        else:
+            for d, fl in emitted:
+                setup_splitk(d, self.device, plan.keep)
+                plan.keep.append(d)
+                plan.add('cis_conv_igemm', C.byref(d), flops=fl)
         return out
 
     # ---- resampling ops

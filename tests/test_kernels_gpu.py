@@ -126,3 +126,46 @@ def test_flow_normalise_and_generator_input():
     ref = torch.cat([image, OL.preprocess_flow_batch(flow)], 3)
     assert float((out[..., :5].float().cpu() - ref).abs().max()) <= 2 ** -7 * float(ref.abs().max())
     assert float(out[..., 5:].abs().max()) == 0
+
+
+@pytest.mark.parametrize('size', [(7, 9, 14, 18), (8, 14, 16, 28), (6, 10, 6, 10), (4, 7, 7, 13)])
+def test_fused_resize_concat_and_its_transpose(size):
+    """cis_resize_concat_bf16(_bwd): three sources of one resolution (the middle one batch-broadcast over 3 replicas, as the a-encoder
+    features of the three weight-shared recover_net calls) -> legacy bilinear -> one concatenated slice; the transpose slices the
+    channels, applies R^T, folds the replicas and accumulates where asked.  Checked against the oracle's resize + autograd."""
+    import ctypes as C
+    from unsupervised_detection_b200._lib import CisSrc
+    H, W, OH, OW = size
+    g = torch.Generator().manual_seed(17)
+    N, nm = 6, 2
+    chans = (16, 8, 24)
+    xs = [bf(torch.randn(N if i != 1 else nm, H, W, c, generator=g)) for i, c in enumerate(chans)]
+    xd = [x.cuda().to(torch.bfloat16).contiguous() for x in xs]
+    tot = sum(chans)
+    out = torch.zeros(N, OH, OW, tot + 8, dtype=torch.bfloat16, device='cuda')        # destination slice at channel offset 8
+    arr = (CisSrc * 3)(*[CisSrc(t.data_ptr(), c, 0, c // 8, nm if i == 1 else 0) for i, (t, c) in enumerate(zip(xd, chans))])
+    _lib.call('cis_resize_concat_bf16', arr, 3, N, H, W, out.data_ptr(), tot + 8, 8, OH, OW, ST())
+    torch.cuda.synchronize()
+    xr = [x.clone().requires_grad_(True) for x in xs]
+    parts = [T.resize_bilinear_legacy(xr[0], OH, OW), T.resize_bilinear_legacy(xr[1], OH, OW).repeat(N // nm, 1, 1, 1),
+             T.resize_bilinear_legacy(xr[2], OH, OW)]
+    ref = torch.cat(parts, 3)
+    got = out[..., 8:].float().cpu()
+    assert float(out[..., :8].abs().max()) == 0
+    assert float((got - ref.detach()).abs().max()) <= 2 ** -7 * float(ref.abs().max()) + 1e-3
+    # transpose: source 0 plain, source 1 folds the replicas AND accumulates onto an existing gradient, source 2 not wanted
+    gy = bf(torch.randn(N, OH, OW, tot, generator=g))
+    ref.backward(gy)
+    gd = torch.zeros(N, OH, OW, tot + 8, dtype=torch.bfloat16, device='cuda')
+    gd[..., 8:] = gy.cuda().to(torch.bfloat16)
+    pre = bf(torch.randn(nm, H, W, chans[1], generator=g))
+    grads = [torch.zeros(N, H, W, chans[0], dtype=torch.bfloat16, device='cuda'), pre.cuda().to(torch.bfloat16).contiguous(),
+             torch.full((N, H, W, chans[2]), 7.0, dtype=torch.bfloat16, device='cuda')]
+    ga = (CisSrc * 3)(*[CisSrc(t.data_ptr(), c, 0, c // 8, nm if i == 1 else 0) for i, (t, c) in enumerate(zip(grads, chans))])
+    want, acc = (C.c_int32 * 3)(1, 1, 0), (C.c_int32 * 3)(0, 1, 0)
+    _lib.call('cis_resize_concat_bf16_bwd', gd.data_ptr(), tot + 8, 8, N, OH, OW, ga, want, acc, 3, H, W, ST())
+    torch.cuda.synchronize()
+    tol = lambda r: 2 ** -6 * float(r.abs().max()) + 1e-2
+    assert float((grads[0].float().cpu() - xr[0].grad).abs().max()) <= tol(xr[0].grad)
+    assert float((grads[1].float().cpu() - (xr[1].grad + pre)).abs().max()) <= tol(xr[1].grad + pre)
+    assert float((grads[2].float() - 7.0).abs().max()) == 0                      # untouched

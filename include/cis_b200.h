@@ -165,6 +165,20 @@ int cis_bn_fold(const float* w, const float* bias, const float* gamma, const flo
 int cis_bn_chain(const float* w, const float* bias, const float* gamma, float* dw_eff_to_dw, const float* db_eff, int64_t nw,
                  int32_t cout, float* dbias, float* dgamma, float* dbeta, cis_stream_t stream);
 
+/* Multi-job form of the five parameter-space ops above: ONE launch over a flat grid of 256-thread blocks.  A job holds the arguments of
+ * the single-launch entry point of its kind in order: pointers in p[], the size_t argument (nw) in n, the int arguments in i[0..6]
+ * (bn_chain: p[0..7] = w, bias, gamma, dw_eff, db_eff, dbias, dgamma, dbeta), and in i[7] the index of its first block; job j owns blocks
+ * [i[7] of j, i[7] of j+1) and needs ceil(elements / 256) of them (bn_chain: cout).  The table lives in device memory, sorted by i[7];
+ * total_blocks = the sum.  Jobs of one launch must not depend on each other. */
+enum { CIS_JOB_PACK = 0, CIS_JOB_PACK_TILED = 1, CIS_JOB_UNPACK = 2, CIS_JOB_BN_FOLD = 3, CIS_JOB_BN_CHAIN = 4 };
+typedef struct {
+  int32_t kind;
+  int32_t i[8];
+  int64_t n;
+  const void* p[8];
+} CisParamJob;
+int cis_param_multi(const CisParamJob* jobs_dev, int32_t njobs, int32_t total_blocks, cis_stream_t stream);
+
 /* ---- elementwise / reduction helpers on bf16 NHWC slices ---- */
 /* g *= act'(y - res)   (ELU: u>0 ? 1 : u+1; leaky: u>0 ? 1 : alpha) */
 int cis_dact_mul(void* g, int32_t g_pitch, int32_t g_coff, const void* y, int32_t y_pitch, int32_t y_coff, const void* res,

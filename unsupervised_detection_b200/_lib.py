@@ -17,6 +17,13 @@ class CisSrc(C.Structure):
     _fields_ = [('ptr', C.c_void_p), ('pitch', C.c_int32), ('c_off', C.c_int32), ('chunks', C.c_int32), ('n_mod', C.c_int32)]
 
 
+class CisParamJob(C.Structure):
+    _fields_ = [('kind', C.c_int32), ('i', C.c_int32 * 8), ('n', C.c_int64), ('p', C.c_void_p * 8)]
+
+
+JOB_PACK, JOB_PACK_TILED, JOB_UNPACK, JOB_BN_FOLD, JOB_BN_CHAIN = range(5)
+
+
 class CisSub(C.Structure):
     _fields_ = [('tap0', C.c_int32), ('ntaps', C.c_int32), ('hoy', C.c_int32), ('hox', C.c_int32), ('OH', C.c_int32), ('OW', C.c_int32),
                 ('oa', C.c_int32), ('ob', C.c_int32), ('wpack', C.c_void_p)]
@@ -62,6 +69,7 @@ _PROTOS = {
     'cis_pack_weights_tiled': [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
     'cis_unpack_wgrad': [_p, _p, _i32, _i32, _i32, _p, _p, _i32, _i32, _p],
     'cis_bn_fold': [_p, _p, _p, _p, _i64, _i32, _p, _p],
+    'cis_param_multi': [_p, _i32, _i32],
     'cis_bn_chain': [_p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p],
     'cis_dact_mul': [_p, _i32, _i32, _p, _i32, _i32, _p, _i32, _i32, _i64, _i32, _i32, _f32],
     'cis_add_slice': [_p, _i32, _i32, _p, _i32, _i32, _i64, _i32, _i32, _i32],

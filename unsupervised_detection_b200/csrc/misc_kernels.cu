@@ -29,11 +29,11 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 }
 
 // ------------------------------------------------------------------------------------------------ weights
-__global__ void pack_weights_kernel(const float* __restrict__ w, const int* __restrict__ kmap, int K_pad, int rows, int cout, int sn,
-                                    const int* __restrict__ nmap, bf16* __restrict__ wp) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+// The five parameter-space ops (BN fold, two weight packs, gradient un-pack, BN chain rule) exist as single launches AND as one
+// multi-job launch (cis_param_multi): blockIdx.y selects a job from a device-side table, so the ~75 per-layer launches that follow
+// every optimiser step and the ~35 that end every backward pass become a handful.
+__device__ __forceinline__ void pack_weights_body(size_t i, const float* __restrict__ w, const int* __restrict__ kmap, int K_pad, int rows, int cout,
+                                                  int sn, const int* __restrict__ nmap, bf16* __restrict__ wp) {
   if (i >= (size_t)rows * K_pad) return;
   const int n = (int)(i / K_pad), k = (int)(i % K_pad);
   const int km = kmap[k];
@@ -43,13 +43,11 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, const int* __re
 }
 // Pre-swizzled weight tiles for the halo kernel: block (ny, cc, t) = BN rows x 128 B, row n holds K = 64 channels of chunk cc for
 // tap t with the SWIZZLE_128B pattern already applied (16-byte chunk index ^= n & 7), so a plain bulk copy lands the UMMA layout.
-__global__ void pack_weights_tiled_kernel(const float* __restrict__ w, const int* __restrict__ kmap, int cin8, int ntaps, int n_tiles, int BN,
-                                          int cout, int sn, const int* __restrict__ nmap, bf16* __restrict__ out) {
-  pdl_launch_dependents();
-  pdl_wait();
+__device__ __forceinline__ void pack_weights_tiled_body(size_t i, const float* __restrict__ w, const int* __restrict__ kmap, int cin8, int ntaps,
+                                                        int n_tiles, int BN, int cout, int sn, const int* __restrict__ nmap,
+                                                        bf16* __restrict__ out) {
   const int nchunks = (cin8 + 63) / 64;
   const size_t total = (size_t)n_tiles * nchunks * ntaps * BN * 64;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int pos = (int)(i % 64);            // physical element position inside the 128-byte row
   size_t r = i / 64;
@@ -68,11 +66,9 @@ __global__ void pack_weights_tiled_kernel(const float* __restrict__ w, const int
   }
   out[i] = __float2bfloat16(v);
 }
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const int* __restrict__ kmap, int K_pad, int cout, int nsplit,
-                                    float* __restrict__ dw, const float* __restrict__ colpart, int nblocks, int nch, float* __restrict__ db) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void unpack_wgrad_body(size_t i, const float* __restrict__ dwp, const int* __restrict__ kmap, int K_pad, int cout,
+                                                  int nsplit, float* __restrict__ dw, const float* __restrict__ colpart, int nblocks, int nch,
+                                                  float* __restrict__ db) {
   const size_t nw = (size_t)cout * K_pad;
   if (i < nw) {
     const int n = (int)(i / K_pad), k = (int)(i % K_pad);
@@ -99,24 +95,19 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const int* __
   }
 }
 #define BN_RSQRT 0.99950037468777323f /* 1/sqrt(1 + 1e-3): tf.layers.batch_normalization defaults, convolution_utils.py:50 */
-__global__ void bn_fold_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
-                               const float* __restrict__ beta, size_t nw, int cout, float* __restrict__ w_eff, float* __restrict__ b_eff) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void bn_fold_body(size_t i, const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
+                                             const float* __restrict__ beta, size_t nw, int cout, float* __restrict__ w_eff,
+                                             float* __restrict__ b_eff) {
   if (i < nw) w_eff[i] = w[i] * gamma[i % cout] * BN_RSQRT;
   if (i < (size_t)cout) b_eff[i] = bias[i] * gamma[i] * BN_RSQRT + beta[i];
 }
-__global__ void bn_chain_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
-                                float* __restrict__ dwe, const float* __restrict__ dbe, size_t nw, int cout, float* __restrict__ dbias,
-                                float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  pdl_launch_dependents();
-  pdl_wait();
-  const int co = blockIdx.x;
+// one 256-thread block per output channel co
+__device__ __forceinline__ void bn_chain_body(int co, const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
+                                              float* __restrict__ dwe, const float* __restrict__ dbe, size_t nw, int cout,
+                                              float* __restrict__ dbias, float* __restrict__ dgamma, float* __restrict__ dbeta, float* red) {
   const size_t rows = nw / cout;
   float acc = 0.f;
   for (size_t r = threadIdx.x; r < rows; r += blockDim.x) acc += dwe[r * cout + co] * w[r * cout + co];
-  __shared__ float red[32];
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
   __syncthreads();
@@ -133,6 +124,74 @@ __global__ void bn_chain_kernel(const float* __restrict__ w, const float* __rest
   __syncthreads();
   const float g = gamma[co] * BN_RSQRT;
   for (size_t r = threadIdx.x; r < rows; r += blockDim.x) dwe[r * cout + co] *= g;
+}
+__global__ void pack_weights_kernel(const float* __restrict__ w, const int* __restrict__ kmap, int K_pad, int rows, int cout, int sn,
+                                    const int* __restrict__ nmap, bf16* __restrict__ wp) {
+  pdl_launch_dependents();
+  pdl_wait();
+  pack_weights_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, w, kmap, K_pad, rows, cout, sn, nmap, wp);
+}
+__global__ void pack_weights_tiled_kernel(const float* __restrict__ w, const int* __restrict__ kmap, int cin8, int ntaps, int n_tiles, int BN,
+                                          int cout, int sn, const int* __restrict__ nmap, bf16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  pack_weights_tiled_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, w, kmap, cin8, ntaps, n_tiles, BN, cout, sn, nmap, out);
+}
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const int* __restrict__ kmap, int K_pad, int cout, int nsplit,
+                                    float* __restrict__ dw, const float* __restrict__ colpart, int nblocks, int nch, float* __restrict__ db) {
+  pdl_launch_dependents();
+  pdl_wait();
+  unpack_wgrad_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, dwp, kmap, K_pad, cout, nsplit, dw, colpart, nblocks, nch, db);
+}
+__global__ void bn_fold_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, size_t nw, int cout, float* __restrict__ w_eff, float* __restrict__ b_eff) {
+  pdl_launch_dependents();
+  pdl_wait();
+  bn_fold_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, w, bias, gamma, beta, nw, cout, w_eff, b_eff);
+}
+__global__ void bn_chain_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
+                                float* __restrict__ dwe, const float* __restrict__ dbe, size_t nw, int cout, float* __restrict__ dbias,
+                                float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[32];
+  bn_chain_body(blockIdx.x, w, bias, gamma, dwe, dbe, nw, cout, dbias, dgamma, dbeta, red);
+}
+// multi-job form: a flat 1-D grid; job j owns blocks [jobs[j].i[7], jobs[j+1].i[7]) (binary search), fields in the argument order of the
+// single-launch entry points
+__global__ void param_multi_kernel(const CisParamJob* __restrict__ jobs, int njobs) {
+  pdl_launch_dependents();
+  pdl_wait();
+  int lo = 0, hi = njobs - 1;
+  while (lo < hi) {                       // last job whose first block is <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[mid].i[7] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const CisParamJob j = jobs[lo];
+  const int blk = (int)blockIdx.x - j.i[7];
+  const size_t i = (size_t)blk * blockDim.x + threadIdx.x;
+  __shared__ float red[32];
+  switch (j.kind) {
+    case CIS_JOB_PACK:
+      pack_weights_body(i, (const float*)j.p[0], (const int*)j.p[1], j.i[0], j.i[1], j.i[2], j.i[3], (const int*)j.p[2], (bf16*)j.p[3]);
+      break;
+    case CIS_JOB_PACK_TILED:
+      pack_weights_tiled_body(i, (const float*)j.p[0], (const int*)j.p[1], j.i[0], j.i[1], j.i[2], j.i[3], j.i[4], j.i[5], (const int*)j.p[2],
+                              (bf16*)j.p[3]);
+      break;
+    case CIS_JOB_UNPACK:
+      unpack_wgrad_body(i, (const float*)j.p[0], (const int*)j.p[1], j.i[0], j.i[1], j.i[2], (float*)j.p[2], (const float*)j.p[3], j.i[3], j.i[4],
+                        (float*)j.p[4]);
+      break;
+    case CIS_JOB_BN_FOLD:
+      bn_fold_body(i, (const float*)j.p[0], (const float*)j.p[1], (const float*)j.p[2], (const float*)j.p[3], (size_t)j.n, j.i[0], (float*)j.p[4],
+                   (float*)j.p[5]);
+      break;
+    case CIS_JOB_BN_CHAIN:      // one block per output channel; the host gives the job exactly cout blocks
+      bn_chain_body(blk, (const float*)j.p[0], (const float*)j.p[1], (const float*)j.p[2], (float*)j.p[3], (const float*)j.p[4], (size_t)j.n,
+                    j.i[0], (float*)j.p[5], (float*)j.p[6], (float*)j.p[7], red);
+      break;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ gradient helpers
@@ -950,6 +1009,11 @@ int cis_unpack_wgrad(const float* dwp, const int32_t* kmap, int32_t K_pad, int32
   CIS_LAUNCH(unpack_wgrad_kernel, nblk((size_t)cout * K_pad + (colpart ? nch : 0)), 256, 0, ST, dwp, kmap, K_pad, cout, nsplit, dw, colpart, nblocks,
              nch, db);
   return cis_check_launch("unpack_wgrad");
+}
+int cis_param_multi(const CisParamJob* jobs_dev, int32_t njobs, int32_t total_blocks, cis_stream_t stream) {
+  if (!jobs_dev || njobs < 1 || total_blocks < 1) return cis_set_error(CIS_ERR_BAD_ARG, "cis_param_multi: bad job table");
+  CIS_LAUNCH(param_multi_kernel, (unsigned)total_blocks, 256, 0, ST, jobs_dev, njobs);
+  return cis_check_launch("param_multi");
 }
 int cis_bn_fold(const float* w, const float* bias, const float* gamma, const float* beta, int64_t nw, int32_t cout, float* w_eff, float* b_eff,
                 cis_stream_t stream) {

@@ -27,6 +27,7 @@ def same_pad(n_in, k, s=1, d=1):
 
 SIDE_STREAM = True
 _SIDE = {}
+MULTI_PARAM_OPS = os.environ.get('CIS_MULTI_PARAM', '1') == '1'   # per-layer pack / un-pack / BN launches batched into multi-job launches
 
 
 def _side_stream(device, key=0):
@@ -107,6 +108,58 @@ class Plan(object):
             ev = torch.cuda.Event()
             ev.record(side)
             main.wait_event(ev)
+
+    def batch_param_ops(self, device):
+        """A plan made only of the five parameter-space ops (BN fold, weight packs, gradient un-pack, BN chain rule), one launch per
+        layer each -> one multi-job launch per kind (cis_param_multi), in dependency order: fold -> packs, un-pack -> chain rule."""
+        from ._lib import CisParamJob, JOB_PACK, JOB_PACK_TILED, JOB_UNPACK, JOB_BN_FOLD, JOB_BN_CHAIN
+        if not MULTI_PARAM_OPS or not self.ops:
+            return self
+        jobs = {k: [] for k in range(5)}
+        for fn, a, name, _, _ in self.ops:
+            j = CisParamJob()
+            if name == 'cis_pack_weights':
+                w, kmap, K_pad, rows, cout, sn, nmap, wp = a
+                j.kind, blocks = JOB_PACK, -(-(rows * K_pad) // 256)
+                ptrs, ints = [w, kmap, nmap, wp], [K_pad, rows, cout, sn]
+            elif name == 'cis_pack_weights_tiled':
+                w, kmap, cin8, ntaps, n_tiles, BN, cout, sn, nmap, out = a
+                j.kind, blocks = JOB_PACK_TILED, -(-(n_tiles * (-(-cin8 // 64)) * ntaps * BN * 64) // 256)
+                ptrs, ints = [w, kmap, nmap, out], [cin8, ntaps, n_tiles, BN, cout, sn]
+            elif name == 'cis_unpack_wgrad':
+                dwp, kmap, K_pad, cout, nsplit, dw, colpart, nblocks, nch, db = a
+                j.kind, blocks = JOB_UNPACK, -(-(cout * K_pad + nch) // 256)
+                ptrs, ints = [dwp, kmap, dw, colpart, db], [K_pad, cout, nsplit, nblocks, nch]
+            elif name == 'cis_bn_fold':
+                w, bias, gamma, beta, nw, cout, w_eff, b_eff = a
+                j.kind, blocks, j.n = JOB_BN_FOLD, -(-max(nw, cout) // 256), nw
+                ptrs, ints = [w, bias, gamma, beta, w_eff, b_eff], [cout]
+            elif name == 'cis_bn_chain':
+                w, bias, gamma, dwe, dbe, nw, cout, dbias, dgamma, dbeta = a
+                j.kind, blocks, j.n = JOB_BN_CHAIN, cout, nw
+                ptrs, ints = [w, bias, gamma, dwe, dbe, dbias, dgamma, dbeta], [cout]
+            else:
+                return self          # something else in the plan: leave it as it is
+            for q, v in enumerate(ptrs):
+                j.p[q] = v
+            for q, v in enumerate(ints):
+                j.i[q] = v
+            jobs[j.kind].append((j, blocks))
+        out = Plan(self.name + '.multi')
+        out.keep = self.keep
+        for kind in (JOB_BN_FOLD, JOB_PACK_TILED, JOB_PACK, JOB_UNPACK, JOB_BN_CHAIN):
+            if not jobs[kind]:
+                continue
+            arr = (CisParamJob * len(jobs[kind]))()
+            first = 0
+            for q, (j, blocks) in enumerate(jobs[kind]):
+                j.i[7] = first
+                arr[q] = j
+                first += blocks
+            tab = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(device)
+            out.keep.append(tab)
+            out.add('cis_param_multi', tab.data_ptr(), len(jobs[kind]), first)
+        return out
 
     def count(self):
         """Kernel launches of one replay (a two-launch split-K conv counts twice)."""

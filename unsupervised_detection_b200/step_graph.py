@@ -140,7 +140,7 @@ class CISGraph(object):
                 for pl in (pre, head, body):
                     full.extend(pl)
                 full.join()            # weight-gradient lane -> main lane before the packed gradients are unpacked
-                full.extend(fin)
+                full.extend(fin.batch_param_ops(device))
                 self.bwd[mode] = full
                 ad = Plan('adam_' + mode)
                 if mode == 'G':
@@ -157,6 +157,7 @@ class CISGraph(object):
             L.plan_pack(self.pack_gen, dgrad=train)
         for L in self.rec.all_layers():
             L.plan_pack(self.pack_rec, dgrad=train)
+        self.pack_gen, self.pack_rec, self.pack_pwc = (pl.batch_param_ops(device) for pl in (self.pack_gen, self.pack_rec, self.pack_pwc))
         self._pwc_packed = False
         self._dirty = True      # packed bf16 operands out of date w.r.t. the fp32 master weights
         self.graphs = {}

@@ -39,7 +39,6 @@ __device__ int g_trace_cap = 0;
 static constexpr int kBM = 128;       // GEMM rows per CTA
 static constexpr int kBK = 64;        // bf16 K elements per stage (128-byte swizzled rows)
 static constexpr int kAStage = kBM * 128;
-static constexpr int kProducerThreads = 128;
 static constexpr int kThreads = 160;  // halo / wgrad kernels: 4 producer/epilogue warps + 1 MMA warp
 static constexpr int kGProducers = 256;   // gather kernel: 8 producer/epilogue warps (its cp.async address arithmetic is the bottleneck)
 static constexpr int kGThreads = 288;     // + 1 MMA warp
@@ -1173,7 +1172,7 @@ struct WgradMaps {
   CUtensorMap x[CIS_MAX_SRC];    // (C8, W, H, N) activation slices, box (64, 8, 8, 1)
 };
 
-__global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_constant__ CisWgrad p, const __grid_constant__ WgradMaps maps) {
+__global__ void __launch_bounds__(kGThreads) conv_wgrad_kernel(const __grid_constant__ CisWgrad p, const __grid_constant__ WgradMaps maps) {
   constexpr int S = kWStages;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * S + 1];
@@ -1184,6 +1183,9 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
   const uint32_t bar_empty = smem_u32(&bars[S]);
   const uint32_t bar_accum = smem_u32(&bars[2 * S]);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // blockDim = producer/epilogue warps + 1 MMA warp: 4 + 1 on the TMA operand path (one thread issues the loads), 8 + 1 on the
+  // cp.async gather path, whose address arithmetic is the bottleneck (thin or strided layers)
+  const int nprod = (int)blockDim.x - 32, mma_warp = nprod >> 5;
   pdl_launch_dependents();
   if (tid < p.ntaps) {
     s_dh[tid] = p.dh[tid];
@@ -1201,10 +1203,10 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
   const int nkb = kb1 - kb0;
   if (nkb <= 0) return;  // never taken: cis_conv_wgrad rejects split counts that leave a split without work (its slice would be garbage)
 
-  if (warp == 4) {
+  if (warp == mma_warp) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(bar_full + 8 * s, p.tma ? 1 : kProducerThreads);
+        mbar_init(bar_full + 8 * s, p.tma ? 1 : nprod);
         mbar_init(bar_empty + 8 * s, 1);
       }
       mbar_init(bar_accum, 1);
@@ -1219,7 +1221,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  if (warp < 4) {
+  if (warp < mma_warp) {
     if (p.tma) {
       if (tid == 0) {
         // two 64-column groups of this CTA: group = tap * nchunks64 + chunk64 -> (tap offset, source map, channel offset)
@@ -1308,8 +1310,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
       mbar_wait(bar_empty + 8 * s, ph ^ 1u);
       const uint32_t st = tile_base + s * kWStage;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = rl + 16 * i;
+      for (int r = rl; r < 64; r += nprod >> 3) {
         const int g = (kb0 + it) * 64 + r;
         const bool rv = g < M;
         int n = 0, h0 = 0, w0 = 0;
@@ -1351,11 +1352,12 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
     // epilogue: row = output channel co, columns = packed K columns of this n-tile
     mbar_wait(bar_accum, 0);
     tc_fence_after();
-    const int co = warp * 32 + lane;
-    const uint32_t t_row = tmem + ((uint32_t)(warp * 32) << 16);
+    const int co = (warp & 3) * 32 + lane;          // warps w and w + 4 share a TMEM lane quarter and split the 128 columns
+    const uint32_t t_row = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int c_lo = mma_warp == 8 ? (warp >> 2) * 64 : 0, c_hi = mma_warp == 8 ? c_lo + 64 : 128;
     const int kcol0 = blockIdx.x * 128;
 #pragma unroll 1
-    for (int c0 = 0; c0 < 128; c0 += 16) {
+    for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
       float v[16];
       tmem_ld16(t_row + c0, v);
       if (co < p.Cout && kcol0 + c0 < p.K_pad) {     // K_pad % 64 == 0: a 16-column group is inside or outside as a whole
@@ -1387,7 +1389,7 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const __grid_const
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc<128>(tmem);
+  if (warp == mma_warp) tmem_dealloc<128>(tmem);
 }
 
 
@@ -1910,7 +1912,7 @@ extern "C" int cis_conv_wgrad(const CisWgrad* d, cis_stream_t stream) {
     if (!ok) return cis_set_error(CIS_ERR_CUDA, "cis_conv_wgrad: cuTensorMapEncodeTiled failed / unavailable");
   }
   dim3 grid((d->K_pad + 127) / 128, d->splits);
-  cudaError_t le = launch_pdl(conv_wgrad_kernel, grid, dim3(kThreads), kWSmem, (cudaStream_t)stream, *d, maps);
+  cudaError_t le = launch_pdl(conv_wgrad_kernel, grid, dim3(d->tma ? kThreads : kGThreads), kWSmem, (cudaStream_t)stream, *d, maps);
   if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_wgrad)");
   return cis_check_launch("conv_wgrad");
 }

@@ -190,6 +190,12 @@ int cis_add_slice(void* dst, int32_t dst_pitch, int32_t dst_coff, const void* sr
  * cis_unpack_wgrad adds them up in block order (deterministic bias gradient). */
 int cis_colsum(const void* g, int32_t g_pitch, int32_t g_coff, int64_t npix, int32_t nch, float* part, int32_t nblocks, cis_stream_t stream);
 
+/* cis_dact_mul and cis_colsum of the same gradient slice in one pass: g *= act'(y - res) in place, part[b][c] = block b's column sums of
+ * the rounded product (bit-identical to the two separate calls with the same nblocks). */
+int cis_dact_colsum(void* g, int32_t g_pitch, int32_t g_coff, const void* y, int32_t y_pitch, int32_t y_coff, const void* res,
+                    int32_t res_pitch, int32_t res_coff, int64_t npix, int32_t nch, int32_t act, float alpha, float* part, int32_t nblocks,
+                    cis_stream_t stream);
+
 /* ---- resampling (App. A.5/A.6 semantics) ---- */
 /* tf.image.resize_images / resize_bilinear legacy (convolution_utils.py:88, nets.py:108) on a bf16 slice */
 int cis_resize_bilinear_bf16(const void* src, int32_t s_pitch, int32_t s_coff, int32_t N, int32_t H, int32_t W, void* dst,

@@ -559,11 +559,65 @@ struct HaloMaps {
 // MMAs of one weight stage (gt taps of one 64-channel chunk, MT stacked tiles, NK K=16 steps each), issued by ONE thread.  The tap
 // offsets come from a shared-memory table; the next tap's offset is fetched BEFORE the current tap's MMAs are issued so the
 // LDS -> R2UR -> descriptor chain (~100 clk, measured 220 clk per single-MMA tap in r02) overlaps the previous issue.
+// MT == 1 (every thin layer): straight-line groups of four taps -- the four tap offsets of the NEXT group are loaded before this group's
+// MMAs are issued, no per-tap branch or tile loop.  (r02 trace: the generic loop below cost 105-157 clk per single-MMA tap, 3-4x the
+// 36 clk the tensor pipe needs for a 128x16x16 MMA; the thin layers were bound by this thread, not by shared memory.)
+template <int NK>
+__device__ __forceinline__ void halo_issue_mt1(const uint32_t tmem, const uint32_t hlo, uint32_t blo, const uint32_t* s_aoff, const int gt,
+                                               const uint32_t bstep, const uint32_t ahi, const uint32_t bhi, const uint32_t idesc,
+                                               const bool first) {
+  int tt = 0;
+  uint32_t acc = first ? 0u : 1u;
+  uint32_t o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+  if (gt >= 4) {
+    o0 = s_aoff[0];
+    o1 = s_aoff[1];
+    o2 = s_aoff[2];
+    o3 = s_aoff[3];
+  }
+  for (; tt + 4 <= gt; tt += 4) {
+    const uint32_t a0 = hlo + o0, a1 = hlo + o1, a2 = hlo + o2, a3 = hlo + o3;
+    if (tt + 8 <= gt) {
+      o0 = s_aoff[tt + 4];
+      o1 = s_aoff[tt + 5];
+      o2 = s_aoff[tt + 6];
+      o3 = s_aoff[tt + 7];
+    }
+#pragma unroll
+    for (int k = 0; k < NK; ++k) umma_bf16_lh(tmem, a0 + 2 * k, ahi, blo + 2 * k, bhi, idesc, k ? 1u : acc);
+#pragma unroll
+    for (int k = 0; k < NK; ++k) umma_bf16_lh(tmem, a1 + 2 * k, ahi, blo + bstep + 2 * k, bhi, idesc, 1u);
+#pragma unroll
+    for (int k = 0; k < NK; ++k) umma_bf16_lh(tmem, a2 + 2 * k, ahi, blo + 2 * bstep + 2 * k, bhi, idesc, 1u);
+#pragma unroll
+    for (int k = 0; k < NK; ++k) umma_bf16_lh(tmem, a3 + 2 * k, ahi, blo + 3 * bstep + 2 * k, bhi, idesc, 1u);
+    acc = 1u;
+    blo += 4 * bstep;
+  }
+  if (tt < gt) {              // 1-3 left-over taps
+    const uint32_t r0 = s_aoff[tt], r1 = tt + 1 < gt ? s_aoff[tt + 1] : 0u, r2 = tt + 2 < gt ? s_aoff[tt + 2] : 0u;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) umma_bf16_lh(tmem, hlo + r0 + 2 * k, ahi, blo + 2 * k, bhi, idesc, k ? 1u : acc);
+    if (tt + 1 < gt) {
+#pragma unroll
+      for (int k = 0; k < NK; ++k) umma_bf16_lh(tmem, hlo + r1 + 2 * k, ahi, blo + bstep + 2 * k, bhi, idesc, 1u);
+    }
+    if (tt + 2 < gt) {
+#pragma unroll
+      for (int k = 0; k < NK; ++k) umma_bf16_lh(tmem, hlo + r2 + 2 * k, ahi, blo + 2 * bstep + 2 * k, bhi, idesc, 1u);
+    }
+  }
+}
+
 template <int NK>
 __device__ __forceinline__ void halo_issue_stage(const uint32_t tmem, const uint32_t hlo, uint32_t blo, const uint32_t* s_aoff, const int gt,
                                                  const int MT, const int BN, const uint32_t ahi, const uint32_t bhi, const uint32_t a_mstep,
                                                  const uint32_t idesc, const bool first) {
   const uint32_t bstep = (uint32_t)(BN * 128) >> 4;
+  if (NK == 1 && MT == 1) {      // single-MMA taps: the loop overhead below would dominate
+    halo_issue_mt1<NK>(tmem, hlo, blo, s_aoff, gt, bstep, ahi, bhi, idesc, first);
+    return;
+  }
   uint32_t off0 = s_aoff[0], off1 = gt > 1 ? s_aoff[1] : 0u;
 #pragma unroll 2
   for (int tt = 0; tt < gt; ++tt, blo += bstep) {
@@ -701,8 +755,9 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
           }
           const int nmod = s_src[si].n_mod;
           mbar_expect_tx(bar_hfull + 8 * hs, (uint32_t)(HP * 128));
-          tma_load_4d(h_base + hs * halo_stage_bytes, &maps.m[si * nph + ph], bar_hfull + 8 * hs, c * 8, tx * 8 + hox, ty * 16 * MT + hoy,
-                      nmod ? (n % nmod) : n);
+          // dilated layer: the map strides by d pixels from any start, the start carries this CTA's phase (pa, pb)
+          tma_load_4d(h_base + hs * halo_stage_bytes, &maps.m[si * nph + ph], bar_hfull + 8 * hs, c * 8, pb + d * (tx * 8 + hox),
+                      pa + d * (ty * 16 * MT + hoy), nmod ? (n % nmod) : n);
         }
       }
       __syncwarp();
@@ -944,7 +999,7 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const __grid_constan
 static constexpr int kPThreads = 384;
 
 template <int BN>
-__global__ void __launch_bounds__(kPThreads) conv_halo_persist_kernel(const __grid_constant__ CisConv p, const int halo_stage_bytes,
+__global__ void __launch_bounds__(kPThreads, 2) conv_halo_persist_kernel(const __grid_constant__ CisConv p, const int halo_stage_bytes,
                                                                        const int BS, const int NHS, const int AS, const int G,
                                                                        const __grid_constant__ HaloMaps maps, const int ws) {
   constexpr int kBStage = BN * 128;
@@ -1632,7 +1687,10 @@ static EncodeTiledFn get_encode_tiled() {
 }
 // (C, W, H, N) bf16 map of one concat source slice; box (64, bw, bh, 1), 128B swizzle, zero OOB fill.  step = 2 selects the
 // space-to-depth phase (py, px) of the image: pixel (y, x) of the map is input pixel (2y + py, 2x + px).
-static bool encode_src_map(CUtensorMap* m, const CisSrc& s, int N, int H, int W, int bw, int bh, int step = 1, int py = 0, int px = 0) {
+// step/py/px: a stride-2 phase view (coarser grid through the global strides, phase offset in the base address).
+// estride: dilated layers -- ONE map per source, every estride-th pixel of a box that starts at any (phase-carrying) coordinate.
+static bool encode_src_map(CUtensorMap* m, const CisSrc& s, int N, int H, int W, int bw, int bh, int step = 1, int py = 0, int px = 0,
+                           int estride = 1) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
   const int nb = s.n_mod > 0 ? s.n_mod : N;
@@ -1640,8 +1698,8 @@ static bool encode_src_map(CUtensorMap* m, const CisSrc& s, int N, int H, int W,
   if (Hq < 1 || Wq < 1) return false;
   cuuint64_t dims[4] = {(cuuint64_t)s.chunks * 8, (cuuint64_t)Wq, (cuuint64_t)Hq, (cuuint64_t)nb};
   cuuint64_t strides[3] = {(cuuint64_t)step * s.pitch * 2, (cuuint64_t)step * W * s.pitch * 2, (cuuint64_t)H * W * s.pitch * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {64, (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), 1};   // extent in the un-strided pixel space
+  cuuint32_t es[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
   void* base = (void*)((const char*)s.ptr + ((size_t)(py * W + px) * s.pitch + (size_t)s.c_off) * 2);
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -1727,13 +1785,14 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   // TMA halo path: undilated, every concat source except the last a multiple of 64 channels (a chunk never straddles sources)
   HaloMaps maps;
   const int nph = d->nph > 1 ? d->nph : 1;
-  int use_tma = (d->dil == 1 && Wh <= 256 && Hh <= 256) ? 1 : 0;
+  static const int dil_tma = getenv("CIS_DIL_TMA") ? atoi(getenv("CIS_DIL_TMA")) : 1;
+  int use_tma = ((d->dil == 1 || dil_tma) && Wh * d->dil <= 256 && Hh * d->dil <= 256) ? 1 : 0;
   for (int i = 0; use_tma && i < d->nsrc - 1; ++i)
     if (d->src[i].chunks % 8) use_tma = 0;
   for (int i = 0; use_tma && i < d->nsrc; ++i) {
     if (((uintptr_t)d->src[i].ptr + (size_t)d->src[i].c_off * 2) % 16) use_tma = 0;
     for (int ph = 0; use_tma && ph < nph; ++ph)
-      if (!encode_src_map(&maps.m[i * nph + ph], d->src[i], d->N, d->H, d->W, Wh, Hh, nph > 1 ? 2 : 1, ph >> 1, ph & 1)) use_tma = 0;
+      if (!encode_src_map(&maps.m[i * nph + ph], d->src[i], d->N, d->H, d->W, Wh, Hh, nph > 1 ? 2 : 1, ph >> 1, ph & 1, d->dil)) use_tma = 0;
   }
   if (!use_tma) memset(&maps, 0, sizeof(maps));
   if (nph > 1 && !use_tma) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_conv_igemm(halo): stride-2 phases need the TMA halo path");
@@ -1743,7 +1802,7 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   const int persist_mode = g_persist_mode >= 0 ? g_persist_mode : (getenv("CIS_PERSIST_MODE") ? atoi(getenv("CIS_PERSIST_MODE")) : 1);
   static const int p_min_tiles = getenv("CIS_PERSIST_MIN_TILES") ? atoi(getenv("CIS_PERSIST_MIN_TILES")) : 296;
   static const int p_ws_kb = getenv("CIS_PERSIST_WS_KB") ? atoi(getenv("CIS_PERSIST_WS_KB")) : 112;
-  if (persist_mode > 0 && use_tma && d->n_tiles == 1 && splits == 1 && nph == 1 && nsub == 1) {
+  if (persist_mode > 0 && use_tma && d->n_tiles == 1 && splits == 1 && nph == 1 && nsub == 1 && dd == 1) {
     const int total = tiles * d->N;
     const int per_tile = nchunks * d->ntaps;
     const int AS = (2 * d->MT * BN <= 512) ? 2 : 1;

@@ -263,6 +263,49 @@ __global__ void colsum_kernel(const bf16* __restrict__ g, int gp, int gc, size_t
   }
 }
 
+// dact_mul + colsum in one pass (layers that have an activation AND accumulate a bias gradient in this backward pass): g *= act'(y - res)
+// in place, part[blockIdx.x][c] = this block's column sums of the ROUNDED product (what a separate colsum launch would read back).
+__global__ void dact_colsum_kernel(bf16* g, int gp, int gc, const bf16* __restrict__ y, int yp, int yc, const bf16* __restrict__ res, int rp,
+                                   int rc, size_t npix, int nch, int chunks, int act, float alpha, float* __restrict__ part) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float sm[];  // [P][chunks*8]
+  const int P = blockDim.x / chunks;
+  const int ck = threadIdx.x % chunks, pl = threadIdx.x / chunks;
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (pl < P) {
+    for (size_t p = (size_t)blockIdx.x * P + pl; p < npix; p += (size_t)gridDim.x * P) {
+      uint4* gpp = reinterpret_cast<uint4*>(g + p * gp + gc + ck * 8);
+      float gv[8], yv[8], rv[8];
+      unpack8(*gpp, gv);
+      unpack8(*reinterpret_cast<const uint4*>(y + p * yp + yc + ck * 8), yv);
+      if (res) {
+        unpack8(*reinterpret_cast<const uint4*>(res + p * rp + rc + ck * 8), rv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) yv[e] -= rv[e];
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float u = yv[e];
+        gv[e] *= (act == CIS_ACT_ELU) ? (u > 0.f ? 1.f : u + 1.f) : (u > 0.f ? 1.f : alpha);
+      }
+      const uint4 pk = pack8(gv);
+      *gpp = pk;
+      unpack8(pk, gv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] += gv[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sm[pl * chunks * 8 + ck * 8 + e] = a[e];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < nch; c += blockDim.x) {
+    float s = 0.f;
+    for (int q = 0; q < P; ++q) s += sm[q * chunks * 8 + c];
+    part[(size_t)blockIdx.x * nch + c] = s;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ resampling
 // TF<=1.13 legacy bilinear (align_corners=False, no half-pixel centres): App. A.6.
 struct Lerp {
@@ -1043,6 +1086,17 @@ int cis_colsum(const void* g, int32_t gp, int32_t gc, int64_t npix, int32_t nch,
   const int P = 256 / chunks;
   CIS_LAUNCH(colsum_kernel, (unsigned)nblocks, 256, P * chunks * 8 * sizeof(float), ST, (cbf)g, gp, gc, (size_t)npix, nch, chunks, part);
   return cis_check_launch("colsum");
+}
+int cis_dact_colsum(void* g, int32_t gp, int32_t gc, const void* y, int32_t yp, int32_t yc, const void* res, int32_t rp, int32_t rc, int64_t npix,
+                    int32_t nch, int32_t act, float alpha, float* part, int32_t nblocks, cis_stream_t stream) {
+  const int chunks = (nch + 7) / 8;
+  if (act == CIS_ACT_NONE) return cis_colsum(g, gp, gc, npix, nch, part, nblocks, stream);
+  if (chunks > 32) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_dact_colsum: more than 256 channels");
+  if (nblocks < 1 || nblocks > 592) return cis_set_error(CIS_ERR_BAD_ARG, "cis_dact_colsum: nblocks must be in [1, 592]");
+  const int P = 256 / chunks;
+  CIS_LAUNCH(dact_colsum_kernel, (unsigned)nblocks, 256, P * chunks * 8 * sizeof(float), ST, (mbf)g, gp, gc, (cbf)y, yp, yc, (cbf)res, rp, rc,
+             (size_t)npix, nch, chunks, act, alpha, part);
+  return cis_check_launch("dact_colsum");
 }
 int cis_resize_bilinear_bf16(const void* src, int32_t sp, int32_t sc, int32_t N, int32_t H, int32_t W, void* dst, int32_t dp, int32_t dc, int32_t OH,
                              int32_t OW, int32_t chunks, cis_stream_t stream) {

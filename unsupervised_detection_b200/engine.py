@@ -28,6 +28,7 @@ def same_pad(n_in, k, s=1, d=1):
 SIDE_STREAM = True
 _SIDE = {}
 MULTI_PARAM_OPS = os.environ.get('CIS_MULTI_PARAM', '1') == '1'   # per-layer pack / un-pack / BN launches batched into multi-job launches
+DACT_COLSUM = os.environ.get('CIS_DACT_COLSUM', '1') == '1'       # activation derivative and bias-gradient partials of a layer in one launch
 
 
 def _side_stream(device, key=0):
@@ -834,10 +835,22 @@ class Builder(object):
             bp.add('cis_add_slice', pg.ptr, pg.pitch, pg.c_off, G.ptr, G.pitch, G.c_off, npix, G.C8 // 8, 1,
                    1 if post_add.grad_written.get(mode) else 0)
             post_add.grad_written[mode] = True
-        if layer.act != ACT_NONE:
-            bp.add('cis_dact_mul', G.ptr, G.pitch, G.c_off, out.ptr, out.pitch, out.c_off,
-                   post_add.ptr if post_add is not None else None, post_add.pitch if post_add is not None else 0,
-                   post_add.c_off if post_add is not None else 0, npix, G.C8 // 8, layer.act, layer.alpha)
+        if layer.tag == mode:
+            chunks = -(-layer.cout // 8)
+            ppb = (256 // chunks) * 16                      # pixels per colsum block (cis_colsum: P lanes x 16 pixels each)
+            if not hasattr(layer, 'col_blocks'):
+                layer.col_blocks = {}
+            layer.col_blocks[mode] = max(1, min(592, -(-npix // ppb)))
+            if getattr(layer, 'colpart', None) is None:
+                layer.colpart = torch.empty(592 * layer.cout, dtype=torch.float32, device=self.device)
+        res = (post_add.ptr, post_add.pitch, post_add.c_off) if post_add is not None else (None, 0, 0)
+        fused_colsum = bool(DACT_COLSUM and layer.act != ACT_NONE and layer.tag == mode)
+        if fused_colsum:      # activation derivative + bias-gradient partials in one pass over the gradient
+            bp.add('cis_dact_colsum', G.ptr, G.pitch, G.c_off, out.ptr, out.pitch, out.c_off, res[0], res[1], res[2], npix, layer.cout,
+                   layer.act, layer.alpha, layer.colpart.data_ptr(), layer.col_blocks[mode])
+        elif layer.act != ACT_NONE:
+            bp.add('cis_dact_mul', G.ptr, G.pitch, G.c_off, out.ptr, out.pitch, out.c_off, res[0], res[1], res[2], npix, G.C8 // 8,
+                   layer.act, layer.alpha)
         s0 = srcs[0]
         H, W = s0.H, s0.W
         taps, _, _ = layer.fwd_taps(H, W)
@@ -862,7 +875,7 @@ class Builder(object):
                     layer.wg_kmap = torch.from_numpy(km).to(self.device)
                 else:
                     layer.wg_K_pad, layer.wg_kmap = layer.K_pad, layer.fwd_kmap
-                layer.dwp, layer.wg_splits, layer.col_blocks = None, {}, {}
+                layer.dwp, layer.wg_splits = None, {}
             w = CisWgrad()
             w.N, w.H, w.W, w.OH, w.OW, w.sh, w.sw = nb, H, W, out.H, out.W, layer.stride, layer.stride
             _fill_taps(w, taps)
@@ -885,12 +898,8 @@ class Builder(object):
             bp.keep.append(w)
             bp.add('cis_conv_wgrad', C.byref(w), flops=2.0 * npix * layer.k * layer.k * layer.cin * layer.cout, lane=1)
             layer.wgrad_modes = getattr(layer, 'wgrad_modes', set()) | {mode}
-            chunks = -(-layer.cout // 8)
-            ppb = (256 // chunks) * 16                      # pixels per colsum block (cis_colsum: P lanes x 16 pixels each)
-            layer.col_blocks[mode] = max(1, min(592, -(-npix // ppb)))
-            if getattr(layer, 'colpart', None) is None:
-                layer.colpart = torch.empty(592 * layer.cout, dtype=torch.float32, device=self.device)
-            bp.add('cis_colsum', G.ptr, G.pitch, G.c_off, npix, layer.cout, layer.colpart.data_ptr(), layer.col_blocks[mode], lane=1)
+            if not fused_colsum:
+                bp.add('cis_colsum', G.ptr, G.pitch, G.c_off, npix, layer.cout, layer.colpart.data_ptr(), layer.col_blocks[mode], lane=1)
         need = [s for s in srcs if mode in s.dep]
         if not need:
             return

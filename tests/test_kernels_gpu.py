@@ -169,3 +169,29 @@ def test_fused_resize_concat_and_its_transpose(size):
     assert float((grads[0].float().cpu() - xr[0].grad).abs().max()) <= tol(xr[0].grad)
     assert float((grads[1].float().cpu() - (xr[1].grad + pre)).abs().max()) <= tol(xr[1].grad + pre)
     assert float((grads[2].float() - 7.0).abs().max()) == 0                      # untouched
+
+
+@pytest.mark.parametrize('nch,act', [(32, 1), (2, 2), (128, 1), (20, 2)])
+def test_dact_colsum_equals_the_two_separate_passes(nch, act):
+    """cis_dact_colsum = cis_dact_mul followed by cis_colsum on the same slice: the gradient and every per-block partial bit-identical
+    (same block count, same pixel order), with a residual source and a slice at a channel offset inside a wider buffer."""
+    g = torch.Generator().manual_seed(5)
+    npix, c8, nblocks = 3 * 37 * 29, (nch + 7) // 8 * 8, 17
+    pitch = c8 + 16
+    grad = torch.zeros(npix, pitch, dtype=torch.bfloat16, device='cuda')
+    grad[:, 8:8 + c8] = torch.randn(npix, c8, generator=g).cuda().to(torch.bfloat16)
+    y = torch.randn(npix, c8, generator=g).cuda().to(torch.bfloat16)
+    res = (0.5 * torch.randn(npix, c8, generator=g)).cuda().to(torch.bfloat16)
+    g0, g2 = grad.clone(), grad.clone()
+    p1 = torch.full((nblocks, nch), -1.0, device='cuda')
+    p2 = torch.full((nblocks, nch), -1.0, device='cuda')
+    _lib.call('cis_dact_mul', grad.data_ptr(), pitch, 8, y.data_ptr(), c8, 0, res.data_ptr(), c8, 0, npix, c8 // 8, act, 0.1, ST())
+    _lib.call('cis_colsum', grad.data_ptr(), pitch, 8, npix, nch, p1.data_ptr(), nblocks, ST())
+    _lib.call('cis_dact_colsum', g2.data_ptr(), pitch, 8, y.data_ptr(), c8, 0, res.data_ptr(), c8, 0, npix, nch, act, 0.1, p2.data_ptr(), nblocks, ST())
+    torch.cuda.synchronize()
+    assert torch.equal(grad, g2) and torch.equal(p1, p2)
+    u = y.float() - res.float()
+    d = torch.where(u > 0, torch.ones_like(u), u + 1 if act == 1 else torch.full_like(u, 0.1))
+    assert torch.equal(g2[:, 8:8 + c8], (g0[:, 8:8 + c8].float() * d).to(torch.bfloat16))
+    assert float((p2.sum(0) - g2[:, 8:8 + nch].float().sum(0)).abs().max()) <= 1e-3 * npix ** 0.5
+    assert float(g2[:, :8].abs().max()) == 0 and float(g2[:, 8 + c8:].abs().max()) == 0

@@ -1758,7 +1758,10 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   if (G > ntaps_max) G = ntaps_max;
   const int fixed = nhs * halo_stage + HP * 4 + 1024;
   // two co-resident CTAs per SM overlap one CTA's epilogue with the other's main loop -- when the grid has that many CTAs
-  const int limit = (ncta_all > 148 && fixed + 2 * kB <= 113 * 1024) ? 113 * 1024 : 226 * 1024;
+  static const int lim_small_kb = getenv("CIS_HALO_SMALL_KB") ? atoi(getenv("CIS_HALO_SMALL_KB")) : 226;   // grids of <= 148 CTAs
+  static const int lim_kb = getenv("CIS_HALO_LIMIT_KB") ? atoi(getenv("CIS_HALO_LIMIT_KB")) : 113;
+  int limit = (ncta_all > 148 && fixed + 2 * kB <= lim_kb * 1024) ? lim_kb * 1024 : 226 * 1024;
+  if (ncta_all <= 148 && fixed + 2 * kB <= lim_small_kb * 1024) limit = lim_small_kb * 1024;
   while (G > 1 && fixed + 2 * G * kB > limit) --G;
   const int groups = cper * ((nsub > 1 ? 1 : (ntaps_max + G - 1) / G));   // pipeline stages one CTA walks (grouped: at least one per chunk)
   int BS = (limit - fixed) / (G * kB);

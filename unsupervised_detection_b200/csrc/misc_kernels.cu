@@ -397,12 +397,14 @@ struct RcArgs {
 };
 __global__ void resize_concat_bf16_kernel(const RcArgs a, int N, int H, int W, bf16* __restrict__ dst, int dp, int dc, int OH, int OW,
                                           int total_chunks) {
+  // grid.y = destination row (n, oy), grid.x * 256 threads = (ox, 8-channel chunk) of that row: no 64-bit divisions per thread
   pdl_launch_dependents();
   pdl_wait();
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)N * OH * OW * total_chunks) return;
-  int ck = (int)(i % total_chunks);
-  const size_t pix = i / total_chunks;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned)(OW * total_chunks)) return;
+  const int ox = (int)(t / (unsigned)total_chunks);
+  int ck = (int)(t - (unsigned)ox * (unsigned)total_chunks);
+  const int n = (int)(blockIdx.y / (unsigned)OH), oy = (int)(blockIdx.y - (unsigned)n * (unsigned)OH);
   const int off = ck * 8;
   int si = 0;
   while (si < a.nsrc - 1 && ck >= a.s[si].chunks) {
@@ -413,24 +415,26 @@ __global__ void resize_concat_bf16_kernel(const RcArgs a, int N, int H, int W, b
   if (si == 1) sd = a.s[1];
   if (si == 2) sd = a.s[2];
   if (si == 3) sd = a.s[3];
-  const int ox = (int)(pix % OW);
-  const int oy = (int)((pix / OW) % OH);
-  const int n = (int)(pix / ((size_t)OW * OH));
   const int ns = sd.n_mod ? n % sd.n_mod : n;
-  const Lerp ly = legacy_lerp(oy, H, (float)H / (float)OH), lx = legacy_lerp(ox, W, (float)W / (float)OW);
-  float tl[8], tr[8], bl[8], br[8], o[8];
   const bf16* b = reinterpret_cast<const bf16*>(sd.ptr) + (size_t)ns * H * W * sd.pitch + sd.c_off + ck * 8;
+  uint4* o = reinterpret_cast<uint4*>(dst + ((size_t)blockIdx.y * OW + ox) * dp + dc + off);
+  if (H == OH && W == OW) {          // same resolution: a plain gather of the channel slices
+    *o = *reinterpret_cast<const uint4*>(b + ((size_t)oy * W + ox) * sd.pitch);
+    return;
+  }
+  const Lerp ly = legacy_lerp(oy, H, (float)H / (float)OH), lx = legacy_lerp(ox, W, (float)W / (float)OW);
+  float tl[8], tr[8], bl[8], br[8], r[8];
   unpack8(*reinterpret_cast<const uint4*>(b + ((size_t)ly.lo * W + lx.lo) * sd.pitch), tl);
   unpack8(*reinterpret_cast<const uint4*>(b + ((size_t)ly.lo * W + lx.hi) * sd.pitch), tr);
   unpack8(*reinterpret_cast<const uint4*>(b + ((size_t)ly.hi * W + lx.lo) * sd.pitch), bl);
   unpack8(*reinterpret_cast<const uint4*>(b + ((size_t)ly.hi * W + lx.hi) * sd.pitch), br);
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const float t = tl[e] + (tr[e] - tl[e]) * lx.f;
+    const float tp = tl[e] + (tr[e] - tl[e]) * lx.f;
     const float bo = bl[e] + (br[e] - bl[e]) * lx.f;
-    o[e] = t + (bo - t) * ly.f;
+    r[e] = tp + (bo - tp) * ly.f;
   }
-  *reinterpret_cast<uint4*>(dst + pix * dp + dc + off) = pack8(o);
+  *o = pack8(r);
 }
 // its transpose: for every source with want != 0, dsrc (=|+=) sum over broadcast replicas of R^T ddst[.., slice of that source]
 struct RcGrad {
@@ -443,12 +447,15 @@ struct RcGradArgs {
 };
 __global__ void resize_concat_bf16_bwd_kernel(const bf16* __restrict__ dd, int dp, int dc, int N, int OH, int OW, const RcGradArgs a, int H,
                                               int W, int total_chunks) {
+  // grid.y = source row (n, y), grid.x * 256 threads = (x, 8-channel chunk).  The x weights of the (<= 8 wide) candidate window are
+  // evaluated once per thread, not once per (dy, dx) pair.
   pdl_launch_dependents();
   pdl_wait();
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)N * H * W * total_chunks) return;
-  int ck = (int)(i % total_chunks);
-  const size_t pix = i / total_chunks;
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned)(W * total_chunks)) return;
+  const int x = (int)(t / (unsigned)total_chunks);
+  int ck = (int)(t - (unsigned)x * (unsigned)total_chunks);
+  const int n = (int)(blockIdx.y / (unsigned)H), y = (int)(blockIdx.y - (unsigned)n * (unsigned)H);
   const int off = ck * 8;
   int si = 0;
   while (si < a.nsrc - 1 && ck >= a.s[si].chunks) {
@@ -459,29 +466,52 @@ __global__ void resize_concat_bf16_bwd_kernel(const bf16* __restrict__ dd, int d
   if (si == 1) sd = a.s[1];
   if (si == 2) sd = a.s[2];
   if (si == 3) sd = a.s[3];
-  const int x = (int)(pix % W);
-  const int y = (int)((pix / W) % H);
-  const int n = (int)(pix / ((size_t)W * H));
   if (!sd.want || (sd.n_mod && n >= sd.n_mod)) return;
   const int reps = sd.n_mod ? N / sd.n_mod : 1;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tv[8];
+  uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(sd.ptr) + ((size_t)(n * H + y) * W + x) * sd.pitch + sd.c_off + ck * 8);
+  if (sd.accumulate) unpack8(*o, acc);
+  if (H == OH && W == OW) {          // same resolution: fold the broadcast replicas of this pixel
+    for (int r = 0; r < reps; ++r) {
+      unpack8(*reinterpret_cast<const uint4*>(dd + ((size_t)((n + r * sd.n_mod) * OH + y) * OW + x) * dp + dc + off), tv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += tv[e];
+    }
+    *o = pack8(acc);
+    return;
+  }
   const float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
   int y0, y1, x0, x1;
   legacy_range(y, OH, sy, y0, y1);
   legacy_range(x, OW, sx, x0, x1);
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t[8];
-  uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(sd.ptr) + ((size_t)(n * H + y) * W + x) * sd.pitch + sd.c_off + ck * 8);
-  if (sd.accumulate) unpack8(*o, acc);
-  for (int r = 0; r < reps; ++r) {
-    const int nd = n + r * sd.n_mod;
-    for (int dy = y0; dy <= y1; ++dy) {
-      const float wy = legacy_w(dy, y, H, sy);
-      if (wy == 0.f) continue;
+  const int nx = x1 - x0 + 1;
+  const bool pre = nx <= 8;
+  float wxv[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) wxv[k] = (pre && k < nx) ? legacy_w(x0 + k, x, W, sx) : 0.f;
+  for (int dy = y0; dy <= y1; ++dy) {
+    const float wy = legacy_w(dy, y, H, sy);
+    if (wy == 0.f) continue;
+    if (pre) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float wt = wy * wxv[k];
+        if (wt == 0.f) continue;
+        for (int r = 0; r < reps; ++r) {
+          unpack8(*reinterpret_cast<const uint4*>(dd + ((size_t)((n + r * sd.n_mod) * OH + dy) * OW + x0 + k) * dp + dc + off), tv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += wt * tv[e];
+        }
+      }
+    } else {
       for (int dx = x0; dx <= x1; ++dx) {
         const float wt = wy * legacy_w(dx, x, W, sx);
         if (wt == 0.f) continue;
-        unpack8(*reinterpret_cast<const uint4*>(dd + ((size_t)(nd * OH + dy) * OW + dx) * dp + dc + off), t);
+        for (int r = 0; r < reps; ++r) {
+          unpack8(*reinterpret_cast<const uint4*>(dd + ((size_t)((n + r * sd.n_mod) * OH + dy) * OW + dx) * dp + dc + off), tv);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] += wt * t[e];
+          for (int e = 0; e < 8; ++e) acc[e] += wt * tv[e];
+        }
       }
     }
   }
@@ -1121,7 +1151,9 @@ int cis_resize_concat_bf16(const CisSrc* srcs, int32_t nsrc, int32_t N, int32_t 
     total += srcs[i].chunks;
   }
   if ((dp | dc) & 7) return cis_set_error(CIS_ERR_BAD_ARG, "cis_resize_concat_bf16: destination must be 8-channel aligned");
-  CIS_LAUNCH(resize_concat_bf16_kernel, nblk((size_t)N * OH * OW * total), 256, 0, ST, a, N, H, W, (mbf)dst, dp, dc, OH, OW, total);
+  if ((size_t)N * OH > 65535 || (size_t)OW * total > 0x7fffffff) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_resize_concat_bf16: too many rows");
+  CIS_LAUNCH(resize_concat_bf16_kernel, dim3((unsigned)((OW * total + 255) / 256), (unsigned)(N * OH)), 256, 0, ST, a, N, H, W, (mbf)dst, dp, dc, OH, OW,
+             total);
   return cis_check_launch("resize_concat_bf16");
 }
 int cis_resize_concat_bf16_bwd(const void* ddst, int32_t dp, int32_t dc, int32_t N, int32_t OH, int32_t OW, const CisSrc* grads, const int32_t* want,
@@ -1142,7 +1174,9 @@ int cis_resize_concat_bf16_bwd(const void* ddst, int32_t dp, int32_t dc, int32_t
     if (grads[i].n_mod && N % grads[i].n_mod) return cis_set_error(CIS_ERR_BAD_ARG, "cis_resize_concat_bf16_bwd: N must be a multiple of n_mod");
     total += grads[i].chunks;
   }
-  CIS_LAUNCH(resize_concat_bf16_bwd_kernel, nblk((size_t)N * H * W * total), 256, 0, ST, (cbf)ddst, dp, dc, N, OH, OW, a, H, W, total);
+  if ((size_t)N * H > 65535 || (size_t)W * total > 0x7fffffff) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_resize_concat_bf16_bwd: too many rows");
+  CIS_LAUNCH(resize_concat_bf16_bwd_kernel, dim3((unsigned)((W * total + 255) / 256), (unsigned)(N * H)), 256, 0, ST, (cbf)ddst, dp, dc, N, OH, OW, a, H,
+             W, total);
   return cis_check_launch("resize_concat_bf16_bwd");
 }
 int cis_resize_bilinear_f32(const float* src, int32_t N, int32_t H, int32_t W, int32_t C, float* dst, int32_t OH, int32_t OW, float scale,

@@ -29,6 +29,7 @@ SIDE_STREAM = True
 _SIDE = {}
 MULTI_PARAM_OPS = os.environ.get('CIS_MULTI_PARAM', '1') == '1'   # per-layer pack / un-pack / BN launches batched into multi-job launches
 DACT_COLSUM = os.environ.get('CIS_DACT_COLSUM', '1') == '1'       # activation derivative and bias-gradient partials of a layer in one launch
+COLSUM_PIX = int(os.environ.get('CIS_COLSUM_PIX', '4'))            # pixels per thread of the column-sum passes (fewer = more blocks, <= 592)
 
 
 def _side_stream(device, key=0):
@@ -837,7 +838,7 @@ class Builder(object):
             post_add.grad_written[mode] = True
         if layer.tag == mode:
             chunks = -(-layer.cout // 8)
-            ppb = (256 // chunks) * 16                      # pixels per colsum block (cis_colsum: P lanes x 16 pixels each)
+            ppb = (256 // chunks) * COLSUM_PIX                      # pixels per colsum block (P pixel lanes x COLSUM_PIX pixels each)
             if not hasattr(layer, 'col_blocks'):
                 layer.col_blocks = {}
             layer.col_blocks[mode] = max(1, min(592, -(-npix // ppb)))

@@ -36,3 +36,23 @@ for m in 'RG':
 for m in 'RG':
     print('pipelined step %s                                   : %.3f ms' % (m, t(lambda: g.train_step(m, use_graph=True, pipeline=True))))
     print('sequential step %s                                  : %.3f ms' % (m, t(lambda: g.train_step(m, use_graph=True))))
+
+# ---- where the train branch spends its time: forward, backward main lane (data gradients) and side lane (weight gradients) on their own
+from unsupervised_detection_b200.engine import Plan
+pp = g._pipe_state()
+
+
+def sub(plan, keep):
+    q = Plan(plan.name + '.sub')
+    q.ops = [op for op in plan.ops if keep(op)]
+    q.keep = plan.keep
+    return q
+
+
+print('train branch forward only                          : %.3f ms' % t(g._capture_plans('tb_fwd', [pp['rest']]).replay))
+for m in 'RG':
+    bw = g.bwd[m]
+    both = g._capture_plans('tb_bwd_' + m, [bw])
+    main = g._capture_plans('tb_bwd_main_' + m, [sub(bw, lambda op: op[4] == 0)])
+    side = g._capture_plans('tb_bwd_side_' + m, [sub(bw, lambda op: op[4] == 1 or op[0] is None)])
+    print('backward %s: both lanes %.3f ms | main lane alone %.3f ms | side lane alone %.3f ms' % (m, t(both.replay), t(main.replay), t(side.replay)))

@@ -232,16 +232,19 @@ __device__ __forceinline__ void epi_row(const CisConv& p, const uint32_t t_row, 
 // slices in a fixed order and runs the fused epilogue.
 template <int BN>
 __device__ __forceinline__ void splitk_store_partial(float* slice, uint32_t t_row, int row, int c_lo = 0, int c_hi = BN) {
-  // slice = this split's private [128][BN] fp32 tile: plain 16-byte stores, no atomics, fixed summation order later
+  // slice = this split's private fp32 tile, stored as float4 COLUMNS: element (row, c) at ((c / 4) * 128 + row) * 4 + c % 4.  A warp
+  // (32 consecutive accumulator rows, same columns) then writes 512 contiguous bytes per store instruction; the row-major layout of
+  // r01/r02 made every st.v4 touch 32 different 128-byte lines and the LSU, not HBM, bounded the epilogue (~10k clk per 128x128 tile
+  // in the CIS_TRACE build -- as long as the whole MMA loop of a split).  No atomics, fixed summation order later.
 #pragma unroll 1
   for (int c0 = c_lo; c0 < c_hi; c0 += 16) {
     float v[16];
     tmem_ld16(t_row + c0, v);
-    float4* o = reinterpret_cast<float4*>(slice + (size_t)row * BN + c0);
+    float4* o = reinterpret_cast<float4*>(slice) + (size_t)(c0 / 4) * kBM + row;
     o[0] = make_float4(v[0], v[1], v[2], v[3]);
-    o[1] = make_float4(v[4], v[5], v[6], v[7]);
-    o[2] = make_float4(v[8], v[9], v[10], v[11]);
-    o[3] = make_float4(v[12], v[13], v[14], v[15]);
+    o[kBM] = make_float4(v[4], v[5], v[6], v[7]);
+    o[2 * kBM] = make_float4(v[8], v[9], v[10], v[11]);
+    o[3 * kBM] = make_float4(v[12], v[13], v[14], v[15]);
   }
 }
 // sum of the nsplit private slices of one tile for (row, c0..c0+15); loads are plain L2 loads (__ldcg) issued in batches of
@@ -250,7 +253,7 @@ template <int BN>
 __device__ __forceinline__ void splitk_reduce16(const float* tile0, int nsplit, int row, int c0, float* v) {
 #pragma unroll
   for (int e = 0; e < 16; ++e) v[e] = 0.f;
-  const float4* q0 = reinterpret_cast<const float4*>(tile0 + (size_t)row * BN + c0);
+  const float4* q0 = reinterpret_cast<const float4*>(tile0) + (size_t)(c0 / 4) * kBM + row;    // float4-column layout of splitk_store_partial
   const size_t zstride = (size_t)kBM * BN / 4;
   int z = 0;
   for (; z + 4 <= nsplit; z += 4) {
@@ -258,7 +261,7 @@ __device__ __forceinline__ void splitk_reduce16(const float* tile0, int nsplit, 
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int h = 0; h < 4; ++h) t[u][h] = __ldcg(q0 + (size_t)(z + u) * zstride + h);
+      for (int h = 0; h < 4; ++h) t[u][h] = __ldcg(q0 + (size_t)(z + u) * zstride + h * kBM);
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
@@ -269,7 +272,7 @@ __device__ __forceinline__ void splitk_reduce16(const float* tile0, int nsplit, 
   for (; z < nsplit; ++z) {
     float4 t[4];
 #pragma unroll
-    for (int h = 0; h < 4; ++h) t[h] = __ldcg(q0 + (size_t)z * zstride + h);
+    for (int h = 0; h < 4; ++h) t[h] = __ldcg(q0 + (size_t)z * zstride + h * kBM);
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
       v[4 * h] += t[h].x; v[4 * h + 1] += t[h].y; v[4 * h + 2] += t[h].z; v[4 * h + 3] += t[h].w;
@@ -933,8 +936,8 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
 // ======================================================================================================= split-K finish
 // Second launch of split-K.  (Round 1 let the last-arriving CTA of a tile read all nsplit x 64 KB slices by itself -- one SM pulling up
 // to 1 MB through L2 -- which cost more than the split saved on the low-resolution layers it is meant for.)  Here the reduction + fused
-// epilogue of a tile is spread over 128 * BN/16 threads of several CTAs: thread = (accumulator row, 16-column group), column group
-// fastest so slice reads and NHWC stores coalesce.
+// epilogue of a tile is spread over 128 * BN/16 threads of several CTAs: thread = (accumulator row, 16-column group), row fastest so
+// the reads of the float4-column slices coalesce (the bf16 output is 1 / (2 * nsplit) of the bytes: its 32-byte pieces matter less).
 template <int BN>
 __global__ void __launch_bounds__(256) splitk_finish_kernel(const __grid_constant__ CisConv p) {
   constexpr int G = BN / 16;                               // 16-column groups per row
@@ -946,7 +949,7 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const __grid_constan
   if (tid >= kBlock) return;
   const int m = blockIdx.z / kSub;
   const int item = (blockIdx.z % kSub) * kBlock + tid;
-  const int r = item / G, c0 = (item % G) * 16;
+  const int r = item % 128, c0 = (item / 128) * 16;        // row fastest: a warp reads 512 contiguous bytes of every slice
   const int ny = blockIdx.y;
   const int nsplit = p.splits;
   const int tile_id = blockIdx.x * gridDim.y + ny;

@@ -322,7 +322,10 @@ __device__ __forceinline__ void tmem_to_stage(const uint32_t t_row, const int ro
 
 template <int BN>
 struct FwdCfg {
+  // kLag + 1 K blocks of gathers are in flight per producer thread (the im2col loads are L2 round trips of ~1 us).  A deeper ring
+  // (5-6 stages for BN <= 32) was measured SLOWER: it drops the thin layers from 3 to 2 co-resident CTAs per SM.
   static constexpr int kStages = (BN == 128) ? 3 : 4;
+  static constexpr int kLag = kStages - 2;
   static constexpr int kBStage = BN * 128;
   static constexpr int kSmem = kStages * (kAStage + kBStage) + 1024;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
@@ -459,15 +462,22 @@ __global__ void __launch_bounds__(kGThreads) conv_igemm_kernel(const __grid_cons
         if (rl < BN) cp_async16(b_dst, wrow + (kb_lo + kb) * kBK, 16u);
       }
       cp_async_commit();
-      if (kb >= 1) {                 // publish block kb-1 (its copies have landed) while block kb is in flight: the first MMA starts
-        cp_async_wait<1>();          // after two blocks are issued -- most launches of this kernel have < 10 K blocks
+      if (kb >= Cfg::kLag) {         // publish block kb-kLag (its copies have landed) while the kLag younger blocks are in flight
+        cp_async_wait<Cfg::kLag>();
         fence_proxy_async();
-        mbar_arrive(bar_full + 8 * ((kb - 1) % S));
+        mbar_arrive(bar_full + 8 * ((kb - Cfg::kLag) % S));
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    mbar_arrive(bar_full + 8 * ((nkb - 1) % S));
+#pragma unroll
+    for (int i = Cfg::kLag - 1; i >= 0; --i) {   // drain: block nkb-1-i has i younger groups behind it
+      if (nkb - 1 - i < 0) continue;
+      if (i == 3) cp_async_wait<3>();
+      else if (i == 2) cp_async_wait<2>();
+      else if (i == 1) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      fence_proxy_async();
+      mbar_arrive(bar_full + 8 * ((nkb - 1 - i) % S));
+    }
 
     // ------------------------------------------------------------------ epilogue: warps w and w + 4 share a TMEM lane quarter and split the columns
     mbar_wait(bar_accum, 0);

@@ -357,7 +357,6 @@ __global__ void __launch_bounds__(kGThreads) conv_igemm_kernel(const __grid_cons
     for (int i = 0; i < p.nsrc; ++i) s += p.src[i].chunks;
     return s;
   }();
-  const int k_chunks = p.ntaps * m_chunks;
   const int nkb_all = p.K_pad / kBK;
   const int nsplit = p.splits > 1 ? p.splits : 1;
   const int kper = (nkb_all + nsplit - 1) / nsplit;
@@ -403,7 +402,13 @@ __global__ void __launch_bounds__(kGThreads) conv_igemm_kernel(const __grid_cons
     const int j = tid & 7;          // 16-byte chunk within the 128-byte K row
     const int rl = tid >> 3;        // 0..31
     const uint32_t sw_off = (uint32_t)((j ^ (rl & 7)) << 4);
-    int hb[4], wb[4], nb[4];
+    // Per-row constants (this thread's 4 rows): top-left input pixel, and the linear pixel index of it in the plain and in the
+    // batch-broadcast (n % n_mod) view of the sources.  The K loop below is division-free: r02's ncu source view showed the producer
+    // warps issue-bound on the integer divisions / 64-bit address arithmetic of every (K block, row), not on the loads.
+    int hb[4], wb[4], pre[4], prem[4];
+    int nm0 = 0;                          // the batch-broadcast modulus (sources with n_mod > 0 share one; others: slow path)
+    for (int i = 0; i < p.nsrc; ++i)
+      if (p.src[i].n_mod > 0 && nm0 == 0) nm0 = p.src[i].n_mod;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int g = blockIdx.x * kBM + rl + 32 * i;
@@ -411,47 +416,58 @@ __global__ void __launch_bounds__(kGThreads) conv_igemm_kernel(const __grid_cons
         const int ow = g % p.OW;
         const int t = g / p.OW;
         const int oh = t % p.OH;
-        nb[i] = t / p.OH;
+        const int n = t / p.OH;
         hb[i] = oh * p.sh;
         wb[i] = ow * p.sw;
+        pre[i] = (n * p.H + hb[i]) * p.W + wb[i];
+        prem[i] = ((nm0 ? n % nm0 : n) * p.H + hb[i]) * p.W + wb[i];
       } else {
-        nb[i] = 0;
         hb[i] = -(1 << 20);
         wb[i] = 0;
+        pre[i] = prem[i] = 0;
       }
     }
     const __nv_bfloat16* wrow = reinterpret_cast<const __nv_bfloat16*>(p.wpack) + (size_t)(ny * BN + rl) * p.K_pad + j * 8;
+    // (tap, channel chunk) of this thread's K chunk, advanced by 8 chunks per K block without dividing
+    const int adv_t = 8 / m_chunks, adv_c = 8 - adv_t * m_chunks;
+    int t = (kb_lo * 8 + j) / m_chunks, c = (kb_lo * 8 + j) - t * m_chunks;
 
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % S;
       const uint32_t ph = (uint32_t)((kb / S) & 1);
       mbar_wait(bar_empty + 8 * s, ph ^ 1u);
-      // ---- A: decode this thread's K chunk -> (tap, source, channel chunk)
-      const int q = (kb_lo + kb) * 8 + j;
-      const bool kvalid = q < k_chunks;
-      int t = 0, c = 0;
-      if (kvalid) {
-        t = q / m_chunks;
-        c = q - t * m_chunks;
-      }
-      int si = 0;
-      while (si < p.nsrc - 1 && c >= s_src[si].chunks) {
-        c -= s_src[si].chunks;
+      // ---- A: this thread's K chunk -> (tap t, source si, channel chunk cs)
+      const bool kvalid = t < p.ntaps;
+      const int tt = kvalid ? t : 0;
+      int si = 0, cs = c;
+      while (si < p.nsrc - 1 && cs >= s_src[si].chunks) {
+        cs -= s_src[si].chunks;
         ++si;
       }
       const __nv_bfloat16* sp = s_src[si].ptr;
       const int pitch = s_src[si].pitch;
-      const int coff = s_src[si].c_off + c * 8;
       const int nmod = s_src[si].n_mod;
-      const int dh = s_dh[t], dw = s_dw[t];
+      const int dh = s_dh[tt], dw = s_dw[tt];
+      const int toff = dh * p.W + dw;
+      const __nv_bfloat16* spc = sp + s_src[si].c_off + cs * 8;
+      const bool slow_mod = nmod != 0 && nmod != nm0;
       const uint32_t a_dst = a_base + s * kAStage + rl * 128 + sw_off;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int h = hb[i] + dh, w = wb[i] + dw;
         const bool ok = kvalid && (unsigned)h < (unsigned)p.H && (unsigned)w < (unsigned)p.W;
-        const int n = nmod ? (nb[i] % nmod) : nb[i];
-        const size_t off = ok ? ((size_t)((n * p.H + h) * p.W + w) * pitch + coff) : 0;
-        cp_async16(a_dst + i * 32 * 128, sp + off, ok ? 16u : 0u);
+        int pix = (nmod ? prem[i] : pre[i]) + toff;
+        if (slow_mod) {                    // a second, different modulus: recompute (never the case in this model)
+          const int n = (pre[i] / (p.H * p.W)) % nmod;
+          pix = (n * p.H + h) * p.W + w;
+        }
+        cp_async16(a_dst + i * 32 * 128, ok ? (const void*)(spc + (size_t)pix * pitch) : (const void*)sp, ok ? 16u : 0u);
+      }
+      t += adv_t;
+      c += adv_c;
+      if (c >= m_chunks) {
+        c -= m_chunks;
+        ++t;
       }
       // ---- B: packed weights, rows rl + 32 i
       const uint32_t b_dst = b_base + s * Cfg::kBStage + rl * 128 + sw_off;

@@ -190,6 +190,9 @@ int cis_add_slice(void* dst, int32_t dst_pitch, int32_t dst_coff, const void* sr
  * cis_unpack_wgrad adds them up in block order (deterministic bias gradient). */
 int cis_colsum(const void* g, int32_t g_pitch, int32_t g_coff, int64_t npix, int32_t nch, float* part, int32_t nblocks, cis_stream_t stream);
 
+/* zero-fill of the small accumulators a step starts from (flow statistics, loss sums, gradient magnitude): stream-ordered memset */
+int cis_zero(void* ptr, int64_t nbytes, cis_stream_t stream);
+
 /* cis_dact_mul and cis_colsum of the same gradient slice in one pass: g *= act'(y - res) in place, part[b][c] = block b's column sums of
  * the rounded product (bit-identical to the two separate calls with the same nblocks). */
 int cis_dact_colsum(void* g, int32_t g_pitch, int32_t g_coff, const void* y, int32_t y_pitch, int32_t y_coff, const void* res,

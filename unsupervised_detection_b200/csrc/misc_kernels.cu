@@ -1117,6 +1117,12 @@ int cis_colsum(const void* g, int32_t gp, int32_t gc, int64_t npix, int32_t nch,
   CIS_LAUNCH(colsum_kernel, (unsigned)nblocks, 256, P * chunks * 8 * sizeof(float), ST, (cbf)g, gp, gc, (size_t)npix, nch, chunks, part);
   return cis_check_launch("colsum");
 }
+int cis_zero(void* ptr, int64_t nbytes, cis_stream_t stream) {
+  if (!ptr || nbytes < 0) return cis_set_error(CIS_ERR_BAD_ARG, "cis_zero: bad buffer");
+  cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)nbytes, ST);     // a memset node under graph capture: no kernel, no library launch
+  if (e != cudaSuccess) return cis_set_cuda_error(e, "cudaMemsetAsync");
+  return CIS_OK;
+}
 int cis_dact_colsum(void* g, int32_t gp, int32_t gc, const void* y, int32_t yp, int32_t yc, const void* res, int32_t rp, int32_t rc, int64_t npix,
                     int32_t nch, int32_t act, float alpha, float* part, int32_t nblocks, cis_stream_t stream) {
   const int chunks = (nch + 7) / 8;

@@ -29,6 +29,7 @@ SIDE_STREAM = True
 _SIDE = {}
 MULTI_PARAM_OPS = os.environ.get('CIS_MULTI_PARAM', '1') == '1'   # per-layer pack / un-pack / BN launches batched into multi-job launches
 DACT_COLSUM = os.environ.get('CIS_DACT_COLSUM', '1') == '1'       # activation derivative and bias-gradient partials of a layer in one launch
+PLAN_MODEL = int(os.environ.get('CIS_PLAN_MODEL', '4'))           # MT choice of setup_halo: 1 wave model, 2 busiest-SM model, 3 smallest stack, 4 hybrid (default)
 COLSUM_PIX = int(os.environ.get('CIS_COLSUM_PIX', '4'))            # pixels per thread of the column-sum passes (fewer = more blocks, <= 592)
 
 
@@ -398,6 +399,18 @@ def setup_halo(d, taps, dil, n_tiles):
         t_mem = (d.BN * 128 * ntaps / 40.0 + HP * 128 / 16.0) * nchunks
         t_cta = max(t_mma, t_mem) + (4000.0 + 1500.0 * MT) / cps
         cost = -(-ncta // (NUM_SMS * cps)) * cps * t_cta / min(cps, max(1.0, ncta / float(NUM_SMS)))
+        if PLAN_MODEL == 2:
+            # busiest SM: its CTAs' throughput-bound parts add up, their fixed latencies overlap cps at a time
+            per_sm = -(-ncta // NUM_SMS)
+            cost = per_sm * max(t_mma, t_mem) + (4000.0 + 1500.0 * MT) * (-(-per_sm // cps))
+        if PLAN_MODEL == 3:
+            cost = float(MT)            # smallest feasible stack
+        if PLAN_MODEL == 4:
+            # measured r02 (A/B of models 1-3 over every layer of the step): the smallest feasible stack wins everywhere EXCEPT on
+            # big grids of short tiles (MMA loop below the fixed prologue + epilogue of a CTA), where the wave model's choice holds
+            n1 = d.N * dil * dil * tiles_x * (-(-Hp0 // 16)) * n_tiles
+            if not (2.0 * d.BN * ntaps * nchunks < 6000.0 and n1 > 4 * NUM_SMS):
+                cost = float(MT)
         if best is None or cost < best[0] - 1e-9:
             best = (cost, MT, util)
     if best is None:

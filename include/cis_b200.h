@@ -223,6 +223,10 @@ int cis_resize_bilinear_f32(const float* src, int32_t N, int32_t H, int32_t W, i
 int cis_upsample_nn2x(const void* src, int32_t N, int32_t H, int32_t W, int32_t pitch, void* dst, cis_stream_t stream);
 int cis_upsample_nn2x_bwd(const void* ddst, int32_t N, int32_t H, int32_t W, int32_t pitch, void* dsrc, int32_t accumulate,
                           cis_stream_t stream);
+/* central crop (box y0, x0, ch, cw of ONE Hs x Ws x C fp32 NHWC image) resized back to OH x OW with the legacy bilinear rule: the
+ * multi-crop test-time augmentation of test_generator_ensemble (data/davis2016_data_utils.py:130-134, 328-354) on the device */
+int cis_crop_resize_bilinear_f32(const float* src, int32_t Hs, int32_t Ws, int32_t C, int32_t y0, int32_t x0, int32_t ch, int32_t cw, float* dst,
+                                 int32_t OH, int32_t OW, cis_stream_t stream);
 /* tf.image.resize_images(NEAREST_NEIGHBOR) for GT masks (adversarial_learner.py:92-94) */
 int cis_resize_nn_f32(const float* src, int32_t N, int32_t H, int32_t W, int32_t C, float* dst, int32_t OH, int32_t OW,
                       cis_stream_t stream);

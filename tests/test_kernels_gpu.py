@@ -195,3 +195,29 @@ def test_dact_colsum_equals_the_two_separate_passes(nch, act):
     assert torch.equal(g2[:, 8:8 + c8], (g0[:, 8:8 + c8].float() * d).to(torch.bfloat16))
     assert float((p2.sum(0) - g2[:, 8:8 + nch].float().sum(0)).abs().max()) <= 1e-3 * npix ** 0.5
     assert float(g2[:, :8].abs().max()) == 0 and float(g2[:, 8 + c8:].abs().max()) == 0
+
+
+def test_device_central_crops_match_the_host_reader_rule():
+    """cis_crop_resize_bilinear_f32 (multi-crop ensemble inputs cut on the device) against data/crops.central_crops (host restatement of
+    Davis2016Reader.central_cropping, itself pinned in tests/test_davis_reader.py): same boxes, same legacy-bilinear values."""
+    from unsupervised_detection_b200.data.crops import central_crops
+    from unsupervised_detection_b200.data.davis2016_data_utils import central_crop_box
+    g = torch.Generator().manual_seed(23)
+    hs, ws = 96, 160
+    img = torch.rand(1, hs, ws, 3, generator=g)
+    gt = (torch.rand(1, hs, ws, 1, generator=g) > 0.5).float()
+    crops = [0.85, 0.9, 0.95, 1.0]
+    r1, _, rg = central_crops(img, img, gt, crops)
+    di, dg = img.cuda(), gt.cuda()
+    o1 = torch.empty(len(crops), hs, ws, 3, device='cuda')
+    og = torch.empty(len(crops), hs, ws, 1, device='cuda')
+    for i, c in enumerate(crops):
+        y0, x0, ch, cw = central_crop_box(hs, ws, c)
+        _lib.call('cis_crop_resize_bilinear_f32', di.data_ptr(), hs, ws, 3, y0, x0, ch, cw, o1[i].data_ptr(), hs, ws, ST())
+        _lib.call('cis_crop_resize_bilinear_f32', dg.data_ptr(), hs, ws, 1, y0, x0, ch, cw, og[i].data_ptr(), hs, ws, ST())
+    torch.cuda.synchronize()
+    assert float((o1.cpu() - r1).abs().max()) <= 2e-6
+    assert float((og.cpu() - rg).abs().max()) <= 2e-6
+    assert torch.equal(o1[3].cpu(), img[0]) and torch.equal(og[3].cpu(), gt[0])          # crop 1.0 is the identity
+    with pytest.raises(Exception):
+        _lib.call('cis_crop_resize_bilinear_f32', di.data_ptr(), hs, ws, 3, 10, 0, hs, ws, o1[0].data_ptr(), hs, ws, ST())

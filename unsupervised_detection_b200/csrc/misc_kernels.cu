@@ -535,6 +535,25 @@ __global__ void resize_bilinear_f32_kernel(const float* __restrict__ src, int N,
     dst[pix * C + c] = (t + (bo - t) * ly.f) * scale;
   }
 }
+// central crop + legacy-bilinear resize back to OH x OW of ONE fp32 NHWC image (the multi-crop ensemble inputs,
+// davis2016_data_utils.py:328-354 / 130-134): crop box (y0, x0, ch, cw) of the Hs x Ws source, same interpolation rule as above
+__global__ void crop_resize_f32_kernel(const float* __restrict__ src, int Ws, int C, int y0, int x0, int ch, int cw, float* __restrict__ dst,
+                                       int OH, int OW) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= OH * OW) return;
+  const int ox = pix % OW, oy = pix / OW;
+  const Lerp ly = legacy_lerp(oy, ch, (float)ch / (float)OH), lx = legacy_lerp(ox, cw, (float)cw / (float)OW);
+  const float* r0 = src + (size_t)(y0 + ly.lo) * Ws * C;
+  const float* r1 = src + (size_t)(y0 + ly.hi) * Ws * C;
+  for (int c = 0; c < C; ++c) {
+    const float tl = r0[(x0 + lx.lo) * C + c], tr = r0[(x0 + lx.hi) * C + c];
+    const float bl = r1[(x0 + lx.lo) * C + c], br = r1[(x0 + lx.hi) * C + c];
+    const float t = tl + (tr - tl) * lx.f, bo = bl + (br - bl) * lx.f;
+    dst[(size_t)pix * C + c] = t + (bo - t) * ly.f;
+  }
+}
 // transpose of the fp32 legacy resize, result stored as a bf16 8-channel chunk (C <= 8 real channels)
 __global__ void resize_f32_bwd_to_bf16_kernel(const float* __restrict__ dd, int N, int OH, int OW, int C, int H, int W, bf16* __restrict__ ds,
                                               int sp) {
@@ -1189,6 +1208,13 @@ int cis_resize_bilinear_f32(const float* src, int32_t N, int32_t H, int32_t W, i
                             cis_stream_t stream) {
   CIS_LAUNCH(resize_bilinear_f32_kernel, nblk((size_t)N * OH * OW), 256, 0, ST, src, N, H, W, C, dst, OH, OW, scale);
   return cis_check_launch("resize_bilinear_f32");
+}
+int cis_crop_resize_bilinear_f32(const float* src, int32_t Hs, int32_t Ws, int32_t C, int32_t y0, int32_t x0, int32_t ch, int32_t cw, float* dst,
+                                 int32_t OH, int32_t OW, cis_stream_t stream) {
+  if (!src || !dst || y0 < 0 || x0 < 0 || ch < 1 || cw < 1 || y0 + ch > Hs || x0 + cw > Ws || OH < 1 || OW < 1)
+    return cis_set_error(CIS_ERR_BAD_ARG, "cis_crop_resize_bilinear_f32: crop box outside the image");
+  CIS_LAUNCH(crop_resize_f32_kernel, nblk((size_t)OH * OW), 256, 0, ST, src, Ws, C, y0, x0, ch, cw, dst, OH, OW);
+  return cis_check_launch("crop_resize_f32");
 }
 int cis_upsample_nn2x(const void* src, int32_t N, int32_t H, int32_t W, int32_t pitch, void* dst, cis_stream_t stream) {
   CIS_LAUNCH(upsample_nn2x_kernel, nblk((size_t)N * 4 * H * W * (pitch / 8)), 256, 0, ST, (cbf)src, N, H, W, pitch, (mbf)dst);

@@ -468,23 +468,45 @@ class AdversarialLearner(object):
             raise IOError("Checkpoint file not found")                         # test_generator.py:58
         self.graph.load_params(p)
 
+    def _device_crops(self, img1, img2, gt):
+        """Multi-crop test-time augmentation on the device: host [1,Hs,Ws,C] tensors -> g.img1 / g.img2 rows (one per crop) and the
+        nearest-resized ground-truth crops [ncrop,H,W,1] (numpy).  Same geometry and interpolation as data/crops.central_crops."""
+        from ..data.davis2016_data_utils import central_crop_box
+        from .. import _lib
+        g = self.graph
+        g.pipeline_drain()
+        dev = g.img1.device
+        st = torch.cuda.current_stream().cuda_stream
+        hs, ws = int(img1.shape[1]), int(img1.shape[2])
+        d1, d2, dg = img1.to(dev, non_blocking=True), img2.to(dev, non_blocking=True), gt.to(dev, non_blocking=True)
+        nc = len(self.test_crops)
+        if getattr(self, '_gt_crops', None) is None or self._gt_crops.shape[0] != nc:
+            self._gt_crops = torch.empty(nc, hs, ws, 1, dtype=torch.float32, device=dev)
+            self._gt_small = torch.empty(nc, g.H, g.W, 1, dtype=torch.float32, device=dev)
+        for i, c in enumerate(self.test_crops):
+            y0, x0, ch, cw = central_crop_box(hs, ws, c)
+            for src, dst, C_ in ((d1, g.img1[i], 3), (d2, g.img2[i], 3), (dg, self._gt_crops[i], 1)):
+                _lib.call('cis_crop_resize_bilinear_f32', src.data_ptr(), hs, ws, C_, y0, x0, ch, cw, dst.data_ptr(), hs, ws, st)
+        _lib.call('cis_resize_nn_f32', self._gt_crops.data_ptr(), nc, hs, ws, 1, self._gt_small.data_ptr(), g.H, g.W, st)
+        self._keep_crop_src = (d1, d2, dg)
+        return self._gt_small.cpu().numpy()
+
     def inference(self, sess=None, batch=None):
         """adversarial_learner.py:606-623 -> dict with the reference's keys (numpy arrays)."""
         g = self.graph
         if batch is None:
             batch = self.reader.batch(1 if self.aug_test else self.local_batch)
         img1, img2, gt, names = batch
+        H, W = g.H, g.W
         if self.aug_test:
-            # crops [0.85,0.9,0.95,1.0] of ONE frame pair, each resized back to 384x640 (davis2016_data_utils.py:328-354)
-            from ..data.crops import central_crops
-            img1, img2, gt = central_crops(img1[:1], img2[:1], gt[:1], self.test_crops)
-        self.feed(img1, img2)
-        if self.aug_test:
+            # crops [0.85,0.9,0.95,1.0] of ONE frame pair, each resized back to 384x640 (davis2016_data_utils.py:328-354): the frame
+            # pair is uploaded once and cut / resized on the device (cis_crop_resize_bilinear_f32) straight into the network inputs
+            gtr = self._device_crops(img1[:1], img2[:1], gt[:1])
             g.forward_masks(use_graph=True)      # the multi-crop graph of the reference outputs masks only (:525-592)
         else:
+            self.feed(img1, img2)
             g.forward()
-        H, W = g.H, g.W
-        gtr = torch.nn.functional.interpolate(gt.permute(0, 3, 1, 2), size=(H, W), mode='nearest').permute(0, 2, 3, 1).numpy()
+            gtr = torch.nn.functional.interpolate(gt.permute(0, 3, 1, 2), size=(H, W), mode='nearest').permute(0, 2, 3, 1).numpy()
         masks = g.mask.cpu().numpy()
         if self.aug_test:
             outs = {'pred_masks': {}, 'gt_masks': {}, 'img_1s': {}}

@@ -281,6 +281,7 @@ MATERIALIZE_MISALIGNED_CONCAT = True
 
 
 WGRAD_CTAS_PER_SM = int(os.environ.get('CIS_WGRAD_CTAS_PER_SM', '2'))   # split-K target: CTAs per SM of one weight-gradient launch
+WGRAD_HALO_MIN_CH = int(os.environ.get('CIS_WGRAD_HALO_MIN_CH', '16'))   # thinner inputs: the per-tap 64-channel padding costs more than the gather path
 WGRAD_HALO = os.environ.get('CIS_WGRAD_HALO', '1') == '1'   # halo-resident swapped wgrad kernel (CisWgrad.tma = 2) where it fits
 
 
@@ -875,7 +876,7 @@ class Builder(object):
                 layer.wg_tma = bool(WGRAD_TMA and layer.stride == 1 and len(layer.in_chanmap) >= 32 and
                                     all(s_.C8 % 64 == 0 for s_ in srcs[:-1]))   # thin inputs: per-tap 64-channel padding would waste the loads
                 # (thin inputs are excluded like for the TMA path: every tap is padded to a 64-channel column group there)
-                layer.wg_halo = bool(WGRAD_HALO and len(layer.in_chanmap) >= 32 and wgrad_halo_fits(taps, layer.cout, layer.stride) and
+                layer.wg_halo = bool(WGRAD_HALO and len(layer.in_chanmap) >= WGRAD_HALO_MIN_CH and wgrad_halo_fits(taps, layer.cout, layer.stride) and
                                      all(s_.C8 % 64 == 0 for s_ in srcs[:-1]))
                 if layer.wg_tma or layer.wg_halo:
                     cin8 = len(layer.in_chanmap)

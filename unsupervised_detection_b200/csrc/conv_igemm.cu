@@ -40,6 +40,13 @@ static constexpr int kBM = 128;       // GEMM rows per CTA
 static constexpr int kBK = 64;        // bf16 K elements per stage (128-byte swizzled rows)
 static constexpr int kAStage = kBM * 128;
 static constexpr int kThreads = 160;  // halo / wgrad kernels: 4 producer/epilogue warps + 1 MMA warp
+// conv_halo_kernel<BN>: warps 0-3 producers + epilogue; BN >= 64 adds warps 4-7 (epilogue only: the wide epilogue is instruction-bound on its
+// warps); last warp = MMA issuer / TMEM owner.  BN <= 32 keeps 160 threads: there the number of co-resident CTAs matters more (measured).
+template <int BN> struct HaloCfg {
+  static constexpr int kMmaWarp = BN >= 64 ? 8 : 4;
+  static constexpr int kThreads = (kMmaWarp + 1) * 32;
+  static constexpr int kMinCtas = BN >= 64 ? 2 : (BN == 32 ? 3 : 4);
+};
 static constexpr int kGProducers = 256;   // gather kernel: 8 producer/epilogue warps (its cp.async address arithmetic is the bottleneck)
 static constexpr int kGThreads = 288;     // + 1 MMA warp
 
@@ -669,13 +676,14 @@ __device__ __forceinline__ void halo_issue_stage(const uint32_t tmem, const uint
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_constant__ CisConv p, const int halo_stage_bytes, const int BS, const int NHS,
+__global__ void __launch_bounds__(HaloCfg<BN>::kThreads, HaloCfg<BN>::kMinCtas) conv_halo_kernel(const __grid_constant__ CisConv p, const int halo_stage_bytes, const int BS, const int NHS,
                                                         const __grid_constant__ HaloMaps maps, const int use_tma, const int G) {
   // One weight pipeline stage = the tiles of G consecutive taps of one 64-channel chunk (contiguous in the pre-tiled operand, ONE
   // bulk copy): the single MMA-issuing thread then pays the per-stage cost (mbarrier wait, tcgen05 fence, election, commits: several
   // hundred clocks of dependent single-thread latency, measured with the CIS_TRACE build) once per 4*MT*G MMAs instead of once per
   // 4*MT -- that cost, not the tensor pipe, bounded every launch of round 1.
   constexpr int kBStage = BN * 128;
+  constexpr int kHMmaWarp_ = HaloCfg<BN>::kMmaWarp, kHThreads_ = HaloCfg<BN>::kThreads;
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bars[2 * 2 + 2 * kHaloMaxBStages + 1];
   __shared__ uint32_t tmem_slot;
@@ -732,13 +740,13 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
     s_src[tid].chunks = p.src[tid].chunks;
     s_src[tid].n_mod = p.src[tid].n_mod;
   }
-  for (int q = tid; q < (use_tma ? 0 : HP); q += kThreads) {
+  for (int q = tid; q < (use_tma ? 0 : HP); q += kHThreads_) {
     const int hy = q / Wh, hx = q - hy * Wh;
     const int gy = ty * 16 * MT + hy + hoy, gx = tx * 8 + hx + hox;
     const int y = pa + d * gy, x = pb + d * gx;
     pixtab[q] = (gy >= 0 && gx >= 0 && y < p.H && x < p.W) ? (y * p.W + x) : -1;
   }
-  if (warp == 4) {
+  if (warp == kHMmaWarp_) {
     if (lane == 0) {
       for (int s = 0; s < 2; ++s) {
         mbar_init(bar_hfull + 8 * s, use_tma ? 1 : 96);
@@ -763,7 +771,8 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   const uint32_t tmem = tmem_slot;
   if (tid == 0) CIS_TRACE_AT(0);
 
-  if (warp < 4) {
+  if (warp < kHMmaWarp_) {
+   if (warp < 4) {
     // ------------------------------------------------------------------ producers
     // Two independent roles so neither stream throttles the other: warps 0-1 stream the per-chunk halos (2 stages), warps 2-3
     // stream the per-(tap, chunk) weight tiles (BS stages).
@@ -861,30 +870,35 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
       }
     }
     __syncwarp();
+   }
 
-    // ------------------------------------------------------------------ epilogue
+    // ------------------------------------------------------------------ epilogue: warps w and w + 4 share TMEM lane quarter w % 4 and
+    // split the columns (the epilogue is instruction-bound on its warps: ~6k clk per 128x128 tile with four of them, r02 trace)
     mbar_wait(bar_accum, 0);
     tc_fence_after();
     if (tid == 0) CIS_TRACE_AT(2);
-    const int r = warp * 32 + lane;
+    const int qtr = warp & 3, half = warp >> 2;
+    const int r = qtr * 32 + lane;
+    const int c_lo = (kHMmaWarp_ == 8) ? half * (BN / 2) : 0, c_hi = (kHMmaWarp_ == 8) ? c_lo + BN / 2 : BN;
+    const uint32_t t_qtr = tmem + ((uint32_t)(qtr * 32) << 16);
     const int cbase = ny * BN;
     const int tile_id = blockIdx.x * gridDim.y + ny;
     if (nsplit > 1 && p.sk_cluster) {
       // cluster split-K: the MT partial tiles -> own shared memory (operand buffers are dead: every MMA has completed); reduced below
       for (int m = 0; m < MT; ++m)
-        tmem_to_stage(tmem + ((uint32_t)(warp * 32) << 16) + m * BN, r, tile_base + (uint32_t)m * (kBM * BN * 4), 0, BN);
+        if (c_lo < c_hi) tmem_to_stage(t_qtr + m * BN, r, tile_base + (uint32_t)m * (kBM * BN * 4), c_lo, c_hi);
     } else if (nsplit > 1) {
       // two-launch split-K: this split's private fp32 slices; splitk_finish_kernel reduces them and runs the fused epilogue
       for (int m = 0; m < MT; ++m)
-        splitk_store_partial<BN>(p.sk_scratch + (((size_t)tile_id * MT + m) * nsplit + blockIdx.z) * kBM * BN,
-                                 tmem + ((uint32_t)(warp * 32) << 16) + m * BN, r);
-    } else {
+        if (c_lo < c_hi)
+          splitk_store_partial<BN>(p.sk_scratch + (((size_t)tile_id * MT + m) * nsplit + blockIdx.z) * kBM * BN, t_qtr + m * BN, r, c_lo, c_hi);
+    } else if (c_lo < c_hi) {
       for (int m = 0; m < MT; ++m) {
         const int gy = ty * 16 * MT + 16 * m + (r >> 3), gx = tx * 8 + (r & 7);
         const int oy = pa + d * gy, ox = pb + d * gx;
         const bool valid = oy < OHs && ox < OWs;
         const size_t dpix = valid ? ((size_t)(n * p.DH + oy * p.osh + oa) * p.DW + ox * p.osw + ob) : 0;
-        epi_row<BN>(p, tmem + ((uint32_t)(warp * 32) << 16) + m * BN, cbase, dpix, valid, s_bias);
+        epi_cols<BN>(p, t_qtr + m * BN, cbase, dpix, valid, s_bias, c_lo, c_hi);
       }
     }
   } else {
@@ -956,7 +970,7 @@ __global__ void __launch_bounds__(kThreads) conv_halo_kernel(const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (tid == 0) CIS_TRACE_AT(3);
-  if (warp == 4) tmem_dealloc_dyn(tmem, ncols);
+  if (warp == kHMmaWarp_) tmem_dealloc_dyn(tmem, ncols);
 }
 
 // ======================================================================================================= split-K finish
@@ -1874,8 +1888,8 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
     }
   }
   cudaError_t le = (splits > 1 && d->sk_cluster)
-                       ? launch_pdl_zcluster(conv_halo_kernel<BN>, grid, dim3(kThreads), smem, st, splits, *d, halo_stage, BS, nhs, maps, use_tma, G)
-                       : launch_pdl(conv_halo_kernel<BN>, grid, dim3(kThreads), smem, st, *d, halo_stage, BS, nhs, maps, use_tma, G);
+                       ? launch_pdl_zcluster(conv_halo_kernel<BN>, grid, dim3(HaloCfg<BN>::kThreads), smem, st, splits, *d, halo_stage, BS, nhs, maps, use_tma, G)
+                       : launch_pdl(conv_halo_kernel<BN>, grid, dim3(HaloCfg<BN>::kThreads), smem, st, *d, halo_stage, BS, nhs, maps, use_tma, G);
   if (le != cudaSuccess) return cis_set_cuda_error(le, "launch(conv_halo)");
   if (splits > 1 && !d->sk_cluster) {
     le = launch_splitk_finish<BN>(d, grid, st);

@@ -105,7 +105,8 @@ typedef struct {
 } CisConv;
 
 /* Weight gradient of the same convolution: dWp[co][(t,c)] = sum_rows g[row][co] * A[row][(t,c)]  (fp32).  The reduction over rows
- * is split over `splits` CTAs per column tile; every split writes its own private slice dwp[split][co][K_pad] with plain stores
+ * is split over `splits` CTAs per column tile; every split writes its own private slice of Cout x K_pad floats with plain stores
+ * (element order: [co][K_pad] for tma == 2, float4 columns [K_pad/4][co][4] for tma 0 / 1 -- see cis_unpack_wgrad's `layout`)
  * (no atomics, nothing to zero) and cis_unpack_wgrad sums the slices in a fixed order -- the weight gradient is bit-reproducible.
  * Replaces the conv2d backprop-filter ops TF1 emits for tf.gradients (loss_utils.py:17). */
 typedef struct {
@@ -153,10 +154,11 @@ int cis_pack_weights(const float* w, const int32_t* kmap, int32_t K_pad, int32_t
  * same tap-major map (k = tap*cin8 + channel). */
 int cis_pack_weights_tiled(const float* w, const int32_t* kmap, int32_t cin8, int32_t ntaps, int32_t n_tiles, int32_t BN, int32_t cout,
                            int32_t sn, const int32_t* nmap, void* out, cis_stream_t stream);
-/* dw[kmap[k] + n] = sum_{s < nsplit} dwp[s][n][k] for kmap[k] >= 0, n < cout (fixed summation order; forward orientation, sn = 1);
- * and, when colpart != NULL, the bias gradient db[c] = sum_{b < nblocks} colpart[b][c], c < nch (the partials of cis_colsum). */
+/* dw[kmap[k] + n] = sum_{s < nsplit} dwp[s](n, k) for kmap[k] >= 0, n < cout (fixed summation order; forward orientation, sn = 1);
+ * and, when colpart != NULL, the bias gradient db[c] = sum_{b < nblocks} colpart[b][c], c < nch (the partials of cis_colsum).
+ * layout = how cis_conv_wgrad stored a slice: 0 = [cout][K_pad] (CisWgrad.tma == 2), 1 = float4 columns [K_pad/4][cout][4] (tma 0 / 1). */
 int cis_unpack_wgrad(const float* dwp, const int32_t* kmap, int32_t K_pad, int32_t cout, int32_t nsplit, float* dw, const float* colpart,
-                     int32_t nblocks, int32_t nch, float* db, cis_stream_t stream);
+                     int32_t nblocks, int32_t nch, float* db, int32_t layout, cis_stream_t stream);
 /* tf.layers.batch_normalization in inference mode folded into the conv (convolution_utils.py:46-51):
  * w_eff = w * gamma/sqrt(1+1e-3); b_eff = bias*gamma/sqrt(1+1e-3) + beta. */
 int cis_bn_fold(const float* w, const float* bias, const float* gamma, const float* beta, int64_t nw, int32_t cout, float* w_eff,

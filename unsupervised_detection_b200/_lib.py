@@ -67,7 +67,7 @@ _PROTOS = {
     'cis_conv_wgrad': [C.POINTER(CisWgrad)],
     'cis_pack_weights': [_p, _p, _i32, _i32, _i32, _i32, _p, _p],
     'cis_pack_weights_tiled': [_p, _p, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p],
-    'cis_unpack_wgrad': [_p, _p, _i32, _i32, _i32, _p, _p, _i32, _i32, _p],
+    'cis_unpack_wgrad': [_p, _p, _i32, _i32, _i32, _p, _p, _i32, _i32, _p, _i32],
     'cis_bn_fold': [_p, _p, _p, _p, _i64, _i32, _p, _p],
     'cis_param_multi': [_p, _i32, _i32],
     'cis_bn_chain': [_p, _p, _p, _p, _p, _i64, _i32, _p, _p, _p],

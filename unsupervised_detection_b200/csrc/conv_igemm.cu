@@ -1459,11 +1459,13 @@ __global__ void __launch_bounds__(kGThreads) conv_wgrad_kernel(const __grid_cons
       float v[16];
       tmem_ld16(t_row + c0, v);
       if (co < p.Cout && kcol0 + c0 < p.K_pad) {     // K_pad % 64 == 0: a 16-column group is inside or outside as a whole
-        float4* o = reinterpret_cast<float4*>(p.dwp + ((size_t)blockIdx.y * p.Cout + co) * p.K_pad + kcol0 + c0);   // this split's private slice
+        // this split's private slice, float4-COLUMN layout [K_pad / 4][Cout][4]: the warp's 32 consecutive output channels write 512
+        // contiguous bytes per store (row-major [Cout][K_pad] made every store touch 32 lines, the LSU-bound pattern of the split-K slices)
+        float4* o = reinterpret_cast<float4*>(p.dwp) + (size_t)blockIdx.y * p.Cout * (p.K_pad / 4) + (size_t)((kcol0 + c0) / 4) * p.Cout + co;
         o[0] = make_float4(v[0], v[1], v[2], v[3]);
-        o[1] = make_float4(v[4], v[5], v[6], v[7]);
-        o[2] = make_float4(v[8], v[9], v[10], v[11]);
-        o[3] = make_float4(v[12], v[13], v[14], v[15]);
+        o[p.Cout] = make_float4(v[4], v[5], v[6], v[7]);
+        o[2 * p.Cout] = make_float4(v[8], v[9], v[10], v[11]);
+        o[3 * p.Cout] = make_float4(v[12], v[13], v[14], v[15]);
       }
     }
   } else {
@@ -1802,7 +1804,9 @@ static int launch_halo(const CisConv* d, cudaStream_t st) {
   const int fixed = nhs * halo_stage + HP * 4 + 1024;
   // two co-resident CTAs per SM overlap one CTA's epilogue with the other's main loop -- when the grid has that many CTAs
   static const int lim_small_kb = getenv("CIS_HALO_SMALL_KB") ? atoi(getenv("CIS_HALO_SMALL_KB")) : 226;   // grids of <= 148 CTAs
-  static const int lim_kb = getenv("CIS_HALO_LIMIT_KB") ? atoi(getenv("CIS_HALO_LIMIT_KB")) : 113;
+  static const int lim_kb_wide = getenv("CIS_HALO_LIMIT_KB") ? atoi(getenv("CIS_HALO_LIMIT_KB")) : 113;
+  static const int lim_kb_thin = getenv("CIS_HALO_LIMIT_THIN_KB") ? atoi(getenv("CIS_HALO_LIMIT_THIN_KB")) : 113;   // BN <= 32
+  const int lim_kb = BN <= 32 ? lim_kb_thin : lim_kb_wide;
   int limit = (ncta_all > 148 && fixed + 2 * kB <= lim_kb * 1024) ? lim_kb * 1024 : 226 * 1024;
   if (ncta_all <= 148 && fixed + 2 * kB <= lim_small_kb * 1024) limit = lim_small_kb * 1024;
   while (G > 1 && fixed + 2 * G * kB > limit) --G;

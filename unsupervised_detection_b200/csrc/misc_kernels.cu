@@ -68,10 +68,21 @@ __device__ __forceinline__ void pack_weights_tiled_body(size_t i, const float* _
 }
 __device__ __forceinline__ void unpack_wgrad_body(size_t i, const float* __restrict__ dwp, const int* __restrict__ kmap, int K_pad, int cout,
                                                   int nsplit, float* __restrict__ dw, const float* __restrict__ colpart, int nblocks, int nch,
-                                                  float* __restrict__ db) {
+                                                  float* __restrict__ db, int layout) {
   const size_t nw = (size_t)cout * K_pad;
   if (i < nw) {
-    const int n = (int)(i / K_pad), k = (int)(i % K_pad);
+    // slice element i -> (output channel n, packed column k): layout 0 = [cout][K_pad] (halo-resident wgrad), layout 1 = float4 columns
+    // [K_pad / 4][cout][4] (gather / TMA-tile wgrad kernels)
+    int n, k;
+    if (layout == 0) {
+      n = (int)(i / K_pad);
+      k = (int)(i % K_pad);
+    } else {
+      const size_t g4 = i / ((size_t)cout * 4);
+      const int rem = (int)(i - g4 * cout * 4);
+      n = rem >> 2;
+      k = (int)g4 * 4 + (rem & 3);
+    }
     const int km = kmap[k];
     if (km < 0) return;
     // fixed-order sum of the private split-K slices; 8 independent loads in flight per thread
@@ -138,10 +149,11 @@ __global__ void pack_weights_tiled_kernel(const float* __restrict__ w, const int
   pack_weights_tiled_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, w, kmap, cin8, ntaps, n_tiles, BN, cout, sn, nmap, out);
 }
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const int* __restrict__ kmap, int K_pad, int cout, int nsplit,
-                                    float* __restrict__ dw, const float* __restrict__ colpart, int nblocks, int nch, float* __restrict__ db) {
+                                    float* __restrict__ dw, const float* __restrict__ colpart, int nblocks, int nch, float* __restrict__ db,
+                                    int layout) {
   pdl_launch_dependents();
   pdl_wait();
-  unpack_wgrad_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, dwp, kmap, K_pad, cout, nsplit, dw, colpart, nblocks, nch, db);
+  unpack_wgrad_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, dwp, kmap, K_pad, cout, nsplit, dw, colpart, nblocks, nch, db, layout);
 }
 __global__ void bn_fold_kernel(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ gamma,
                                const float* __restrict__ beta, size_t nw, int cout, float* __restrict__ w_eff, float* __restrict__ b_eff) {
@@ -181,7 +193,7 @@ __global__ void param_multi_kernel(const CisParamJob* __restrict__ jobs, int njo
       break;
     case CIS_JOB_UNPACK:
       unpack_wgrad_body(i, (const float*)j.p[0], (const int*)j.p[1], j.i[0], j.i[1], j.i[2], (float*)j.p[2], (const float*)j.p[3], j.i[3], j.i[4],
-                        (float*)j.p[4]);
+                        (float*)j.p[4], j.i[5]);
       break;
     case CIS_JOB_BN_FOLD:
       bn_fold_body(i, (const float*)j.p[0], (const float*)j.p[1], (const float*)j.p[2], (const float*)j.p[3], (size_t)j.n, j.i[0], (float*)j.p[4],
@@ -1096,10 +1108,11 @@ int cis_pack_weights_tiled(const float* w, const int32_t* kmap, int32_t cin8, in
   return cis_check_launch("pack_weights_tiled");
 }
 int cis_unpack_wgrad(const float* dwp, const int32_t* kmap, int32_t K_pad, int32_t cout, int32_t nsplit, float* dw, const float* colpart,
-                     int32_t nblocks, int32_t nch, float* db, cis_stream_t stream) {
-  if (nsplit < 1 || (colpart && (nblocks < 1 || !db))) return cis_set_error(CIS_ERR_BAD_ARG, "cis_unpack_wgrad: bad split / column-sum arguments");
+                     int32_t nblocks, int32_t nch, float* db, int32_t layout, cis_stream_t stream) {
+  if (nsplit < 1 || (colpart && (nblocks < 1 || !db)) || (layout != 0 && layout != 1) || K_pad % 4)
+    return cis_set_error(CIS_ERR_BAD_ARG, "cis_unpack_wgrad: bad split / column-sum / layout arguments");
   CIS_LAUNCH(unpack_wgrad_kernel, nblk((size_t)cout * K_pad + (colpart ? nch : 0)), 256, 0, ST, dwp, kmap, K_pad, cout, nsplit, dw, colpart, nblocks,
-             nch, db);
+             nch, db, layout);
   return cis_check_launch("unpack_wgrad");
 }
 int cis_param_multi(const CisParamJob* jobs_dev, int32_t njobs, int32_t total_blocks, cis_stream_t stream) {

@@ -131,9 +131,9 @@ class Plan(object):
                 j.kind, blocks = JOB_PACK_TILED, -(-(n_tiles * (-(-cin8 // 64)) * ntaps * BN * 64) // 256)
                 ptrs, ints = [w, kmap, nmap, out], [cin8, ntaps, n_tiles, BN, cout, sn]
             elif name == 'cis_unpack_wgrad':
-                dwp, kmap, K_pad, cout, nsplit, dw, colpart, nblocks, nch, db = a
+                dwp, kmap, K_pad, cout, nsplit, dw, colpart, nblocks, nch, db, layout = a
                 j.kind, blocks = JOB_UNPACK, -(-(cout * K_pad + nch) // 256)
-                ptrs, ints = [dwp, kmap, dw, colpart, db], [K_pad, cout, nsplit, nblocks, nch]
+                ptrs, ints = [dwp, kmap, dw, colpart, db], [K_pad, cout, nsplit, nblocks, nch, layout]
             elif name == 'cis_bn_fold':
                 w, bias, gamma, beta, nw, cout, w_eff, b_eff = a
                 j.kind, blocks, j.n = JOB_BN_FOLD, -(-max(nw, cout) // 256), nw
@@ -681,7 +681,7 @@ class ConvLayer(object):
         s = self.store
         bp.add('cis_unpack_wgrad', self.dwp.data_ptr(), self.wg_kmap.data_ptr(), self.wg_K_pad, self.cout, self.wg_splits[mode],
                s.ptr(self.wkey, 'grad'), self.colpart.data_ptr(), self.col_blocks[mode], self.cout,
-               (self.db_eff.data_ptr() if self.bn else s.ptr(self.bkey, 'grad')))
+               (self.db_eff.data_ptr() if self.bn else s.ptr(self.bkey, 'grad')), 0 if self.wg_halo else 1)
         if self.bn:
             bp.add('cis_bn_chain', s.ptr(self.wkey), s.ptr(self.bkey), s.ptr(self.name + '/gamma'), s.ptr(self.wkey, 'grad'),
                    self.db_eff.data_ptr(), self.k * self.k * self.cin * self.cout, self.cout, s.ptr(self.bkey, 'grad'),

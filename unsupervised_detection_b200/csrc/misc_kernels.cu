@@ -448,6 +448,49 @@ __global__ void resize_concat_bf16_kernel(const RcArgs a, int N, int H, int W, b
   }
   *o = pack8(r);
 }
+// exact x2 case (OH = 2H, OW = 2W: every `deconv` of the recover decoder at power-of-two sizes): one thread per SOURCE pixel chunk loads the
+// 2x2 source neighbourhood once and writes the four destination pixels it determines -- same lerp expressions (fractions 0 / 0.5, clamped
+// last row / column), so the result is bit-identical to the generic kernel with a quarter of the loads and index arithmetic.
+__global__ void resize_concat_x2_bf16_kernel(const RcArgs a, int N, int H, int W, bf16* __restrict__ dst, int dp, int dc, int total_chunks) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned)(W * total_chunks)) return;
+  const int x = (int)(t / (unsigned)total_chunks);
+  int ck = (int)(t - (unsigned)x * (unsigned)total_chunks);
+  const int n = (int)(blockIdx.y / (unsigned)H), y = (int)(blockIdx.y - (unsigned)n * (unsigned)H);
+  const int off = ck * 8;
+  int si = 0;
+  while (si < a.nsrc - 1 && ck >= a.s[si].chunks) {
+    ck -= a.s[si].chunks;
+    ++si;
+  }
+  CisSrc sd = a.s[0];
+  if (si == 1) sd = a.s[1];
+  if (si == 2) sd = a.s[2];
+  if (si == 3) sd = a.s[3];
+  const int ns = sd.n_mod ? n % sd.n_mod : n;
+  const bf16* b = reinterpret_cast<const bf16*>(sd.ptr) + (size_t)ns * H * W * sd.pitch + sd.c_off + ck * 8;
+  const int x1 = min(x + 1, W - 1), y1 = min(y + 1, H - 1);
+  float s00[8], s01[8], s10[8], s11[8], r[8];
+  unpack8(*reinterpret_cast<const uint4*>(b + ((size_t)y * W + x) * sd.pitch), s00);
+  unpack8(*reinterpret_cast<const uint4*>(b + ((size_t)y * W + x1) * sd.pitch), s01);
+  unpack8(*reinterpret_cast<const uint4*>(b + ((size_t)y1 * W + x) * sd.pitch), s10);
+  unpack8(*reinterpret_cast<const uint4*>(b + ((size_t)y1 * W + x1) * sd.pitch), s11);
+  const int OW = 2 * W;
+  bf16* o = dst + (((size_t)(n * 2 * H + 2 * y)) * OW + 2 * x) * dp + dc + off;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float fy = (q >> 1) ? 0.5f : 0.f, fx = (q & 1) ? 0.5f : 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float tp = s00[e] + (s01[e] - s00[e]) * fx;
+      const float bo = s10[e] + (s11[e] - s10[e]) * fx;
+      r[e] = tp + (bo - tp) * fy;
+    }
+    *reinterpret_cast<uint4*>(o + ((size_t)(q >> 1) * OW + (q & 1)) * dp) = pack8(r);
+  }
+}
 // its transpose: for every source with want != 0, dsrc (=|+=) sum over broadcast replicas of R^T ddst[.., slice of that source]
 struct RcGrad {
   void* ptr;
@@ -493,16 +536,27 @@ __global__ void resize_concat_bf16_bwd_kernel(const bf16* __restrict__ dd, int d
     return;
   }
   const float sy = (float)H / (float)OH, sx = (float)W / (float)OW;
-  int y0, y1, x0, x1;
-  legacy_range(y, OH, sy, y0, y1);
-  legacy_range(x, OW, sx, x0, x1);
+  const bool x2 = OH == 2 * H && OW == 2 * W;     // exact x2: the transpose weights are 0.5 / 1 / 0.5 (1 on the clamped last row / column),
+  int y0, y1, x0, x1;                             // the same values legacy_w returns, without evaluating it 14 times per thread
+  if (x2) {
+    y0 = max(2 * y - 1, 0);
+    y1 = 2 * y + 1;
+    x0 = max(2 * x - 1, 0);
+    x1 = 2 * x + 1;
+  } else {
+    legacy_range(y, OH, sy, y0, y1);
+    legacy_range(x, OW, sx, x0, x1);
+  }
   const int nx = x1 - x0 + 1;
   const bool pre = nx <= 8;
   float wxv[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) wxv[k] = (pre && k < nx) ? legacy_w(x0 + k, x, W, sx) : 0.f;
+  for (int k = 0; k < 8; ++k) {
+    const int dx = x0 + k;
+    wxv[k] = !(pre && k < nx) ? 0.f : x2 ? ((dx == 2 * x || (dx == 2 * x + 1 && x == W - 1)) ? 1.f : 0.5f) : legacy_w(dx, x, W, sx);
+  }
   for (int dy = y0; dy <= y1; ++dy) {
-    const float wy = legacy_w(dy, y, H, sy);
+    const float wy = x2 ? ((dy == 2 * y || (dy == 2 * y + 1 && y == H - 1)) ? 1.f : 0.5f) : legacy_w(dy, y, H, sy);
     if (wy == 0.f) continue;
     if (pre) {
 #pragma unroll
@@ -1190,6 +1244,10 @@ int cis_resize_concat_bf16(const CisSrc* srcs, int32_t nsrc, int32_t N, int32_t 
   }
   if ((dp | dc) & 7) return cis_set_error(CIS_ERR_BAD_ARG, "cis_resize_concat_bf16: destination must be 8-channel aligned");
   if ((size_t)N * OH > 65535 || (size_t)OW * total > 0x7fffffff) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_resize_concat_bf16: too many rows");
+  if (OH == 2 * H && OW == 2 * W) {
+    CIS_LAUNCH(resize_concat_x2_bf16_kernel, dim3((unsigned)((W * total + 255) / 256), (unsigned)(N * H)), 256, 0, ST, a, N, H, W, (mbf)dst, dp, dc, total);
+    return cis_check_launch("resize_concat_x2_bf16");
+  }
   CIS_LAUNCH(resize_concat_bf16_kernel, dim3((unsigned)((OW * total + 255) / 256), (unsigned)(N * OH)), 256, 0, ST, a, N, H, W, (mbf)dst, dp, dc, OH, OW,
              total);
   return cis_check_launch("resize_concat_bf16");

@@ -653,40 +653,42 @@ __device__ __forceinline__ int nn_src(int d, int n_in) {
   return min((int)roundf(d * scale), n_in - 1);
 }
 __global__ void upsample_nn2x_kernel(const bf16* __restrict__ src, int N, int H, int W, int pitch, bf16* __restrict__ dst) {
+  // grid.y = destination row (n, oy); threads = (ox, 8-channel chunk): 32-bit index math, one source row per block row
   pdl_launch_dependents();
   pdl_wait();
   const int chunks = pitch / 8;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)N * 4 * H * W * chunks) return;
-  const int c = (int)(i % chunks) * 8;
-  size_t pix = i / chunks;
-  const int ox = (int)(pix % (2 * W));
-  const int oy = (int)((pix / (2 * W)) % (2 * H));
-  const int n = (int)(pix / ((size_t)4 * W * H));
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned)(2 * W * chunks)) return;
+  const int ox = (int)(t / (unsigned)chunks), c = (int)(t - (unsigned)ox * (unsigned)chunks) * 8;
+  const int n = (int)(blockIdx.y / (unsigned)(2 * H)), oy = (int)(blockIdx.y - (unsigned)n * (unsigned)(2 * H));
   const int sy = nn_src(oy, H), sx = nn_src(ox, W);
-  *reinterpret_cast<uint4*>(dst + pix * pitch + c) = *reinterpret_cast<const uint4*>(src + ((size_t)(n * H + sy) * W + sx) * pitch + c);
+  *reinterpret_cast<uint4*>(dst + ((size_t)blockIdx.y * 2 * W + ox) * pitch + c) =
+      *reinterpret_cast<const uint4*>(src + ((size_t)(n * H + sy) * W + sx) * pitch + c);
 }
 __global__ void upsample_nn2x_bwd_kernel(const bf16* __restrict__ dd, int N, int H, int W, int pitch, bf16* ds, int accumulate) {
+  // grid.y = source row (n, y); the (<= 6) candidate destination rows / columns are tested once per thread, not once per pair
   pdl_launch_dependents();
   pdl_wait();
   const int chunks = pitch / 8;
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)N * H * W * chunks) return;
-  const int c = (int)(i % chunks) * 8;
-  size_t pix = i / chunks;
-  const int x = (int)(pix % W);
-  const int y = (int)((pix / W) % H);
-  const int n = (int)(pix / ((size_t)W * H));
-  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t[8];
-  uint4* o = reinterpret_cast<uint4*>(ds + pix * pitch + c);
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned)(W * chunks)) return;
+  const int x = (int)(t / (unsigned)chunks), c = (int)(t - (unsigned)x * (unsigned)chunks) * 8;
+  const int n = (int)(blockIdx.y / (unsigned)H), y = (int)(blockIdx.y - (unsigned)n * (unsigned)H);
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tv[8];
+  uint4* o = reinterpret_cast<uint4*>(ds + ((size_t)blockIdx.y * W + x) * pitch + c);
   if (accumulate) unpack8(*o, a);
+  const int dx0 = max(0, 2 * x - 2), dx1 = min(2 * W - 1, 2 * x + 3);
+  unsigned xm = 0;                                   // bit k: destination column dx0 + k maps to this source column
+  for (int dx = dx0; dx <= dx1; ++dx)
+    if (nn_src(dx, W) == x) xm |= 1u << (dx - dx0);
   for (int dy = max(0, 2 * y - 2); dy <= min(2 * H - 1, 2 * y + 3); ++dy) {
     if (nn_src(dy, H) != y) continue;
-    for (int dx = max(0, 2 * x - 2); dx <= min(2 * W - 1, 2 * x + 3); ++dx) {
-      if (nn_src(dx, W) != x) continue;
-      unpack8(*reinterpret_cast<const uint4*>(dd + ((size_t)(n * 2 * H + dy) * 2 * W + dx) * pitch + c), t);
+    const bf16* row = dd + ((size_t)(n * 2 * H + dy) * 2 * W) * pitch + c;
+    for (int dx = dx0; dx <= dx1; ++dx) {
+      if (!((xm >> (dx - dx0)) & 1u)) continue;
+      unpack8(*reinterpret_cast<const uint4*>(row + (size_t)dx * pitch), tv);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) a[e] += t[e];
+      for (int e = 0; e < 8; ++e) a[e] += tv[e];
     }
   }
   *o = pack8(a);
@@ -1288,11 +1290,15 @@ int cis_crop_resize_bilinear_f32(const float* src, int32_t Hs, int32_t Ws, int32
   return cis_check_launch("crop_resize_f32");
 }
 int cis_upsample_nn2x(const void* src, int32_t N, int32_t H, int32_t W, int32_t pitch, void* dst, cis_stream_t stream) {
-  CIS_LAUNCH(upsample_nn2x_kernel, nblk((size_t)N * 4 * H * W * (pitch / 8)), 256, 0, ST, (cbf)src, N, H, W, pitch, (mbf)dst);
+  if ((size_t)N * 2 * H > 65535) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_upsample_nn2x: too many rows");
+  CIS_LAUNCH(upsample_nn2x_kernel, dim3((unsigned)((2 * W * (pitch / 8) + 255) / 256), (unsigned)(N * 2 * H)), 256, 0, ST, (cbf)src, N, H, W, pitch,
+             (mbf)dst);
   return cis_check_launch("upsample_nn2x");
 }
 int cis_upsample_nn2x_bwd(const void* dd, int32_t N, int32_t H, int32_t W, int32_t pitch, void* ds, int32_t accumulate, cis_stream_t stream) {
-  CIS_LAUNCH(upsample_nn2x_bwd_kernel, nblk((size_t)N * H * W * (pitch / 8)), 256, 0, ST, (cbf)dd, N, H, W, pitch, (mbf)ds, accumulate);
+  if ((size_t)N * H > 65535) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_upsample_nn2x_bwd: too many rows");
+  CIS_LAUNCH(upsample_nn2x_bwd_kernel, dim3((unsigned)((W * (pitch / 8) + 255) / 256), (unsigned)(N * H)), 256, 0, ST, (cbf)dd, N, H, W, pitch, (mbf)ds,
+             accumulate);
   return cis_check_launch("upsample_nn2x_bwd");
 }
 int cis_resize_nn_f32(const float* src, int32_t N, int32_t H, int32_t W, int32_t C, float* dst, int32_t OH, int32_t OW, cis_stream_t stream) {

@@ -140,7 +140,7 @@ class Plan(object):
                 ptrs, ints = [w, bias, gamma, beta, w_eff, b_eff], [cout]
             elif name == 'cis_bn_chain':
                 w, bias, gamma, dwe, dbe, nw, cout, dbias, dgamma, dbeta = a
-                j.kind, blocks, j.n = JOB_BN_CHAIN, cout, nw
+                j.kind, blocks, j.n = JOB_BN_CHAIN, -(-cout // 8), nw          # one block per 8 output channels (csrc: kBnChainCo)
                 ptrs, ints = [w, bias, gamma, dwe, dbe, dbias, dgamma, dbeta], [cout]
             else:
                 return self          # something else in the plan: leave it as it is

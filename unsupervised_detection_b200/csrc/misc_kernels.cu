@@ -66,6 +66,37 @@ __device__ __forceinline__ void pack_weights_tiled_body(size_t i, const float* _
   }
   out[i] = __float2bfloat16(v);
 }
+// Forward orientation (sn == 1: the fp32 master weights are HWIO, output channel fastest): one block per (ny, cc, t) tile of BN x 64
+// elements, read along n (contiguous in HWIO), transposed through shared memory, written along k (contiguous in the tile).  The flat
+// form above reads a column of the [tap*cin][cout] matrix per warp: 4 useful bytes per 32-byte sector.  tile: >= 64 * (BN + 1) floats.
+__device__ __forceinline__ void pack_weights_tiled_tile(int blk, const float* __restrict__ w, const int* __restrict__ kmap, int cin8, int ntaps,
+                                                        int n_tiles, int BN, int cout, const int* __restrict__ nmap, bf16* __restrict__ out,
+                                                        float* tile) {
+  const int nchunks = (cin8 + 63) / 64;
+  const int t = blk % ntaps;
+  const int r = blk / ntaps;
+  const int cc = r % nchunks, ny = r / nchunks;
+  const int ld = BN + 1;
+  for (int idx = threadIdx.x; idx < BN * 64; idx += blockDim.x) {
+    const int n = idx % BN, kk = idx / BN;
+    const int c = cc * 64 + kk;
+    float v = 0.f;
+    if (c < cin8) {
+      const int km = kmap[t * cin8 + c];
+      const int ng = ny * BN + n;
+      const int ne = nmap ? nmap[ng] : (ng < cout ? ng : -1);
+      if (km >= 0 && ne >= 0) v = w[(size_t)km + ne];
+    }
+    tile[kk * ld + n] = v;
+  }
+  __syncthreads();
+  bf16* o = out + (size_t)blk * BN * 64;
+  for (int idx = threadIdx.x; idx < BN * 64; idx += blockDim.x) {
+    const int pos = idx & 63, n = idx >> 6;
+    const int kk = (((pos >> 3) ^ (n & 7)) << 3) | (pos & 7);
+    o[idx] = __float2bfloat16(tile[kk * ld + n]);
+  }
+}
 __device__ __forceinline__ void unpack_wgrad_body(size_t i, const float* __restrict__ dwp, const int* __restrict__ kmap, int K_pad, int cout,
                                                   int nsplit, float* __restrict__ dw, const float* __restrict__ colpart, int nblocks, int nch,
                                                   float* __restrict__ db, int layout) {
@@ -151,7 +182,9 @@ __global__ void pack_weights_tiled_kernel(const float* __restrict__ w, const int
                                           int cout, int sn, const int* __restrict__ nmap, bf16* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
-  pack_weights_tiled_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, w, kmap, cin8, ntaps, n_tiles, BN, cout, sn, nmap, out);
+  __shared__ float tile[64 * 129];
+  if (sn == 1) pack_weights_tiled_tile(blockIdx.x, w, kmap, cin8, ntaps, n_tiles, BN, cout, nmap, out, tile);
+  else pack_weights_tiled_body((size_t)blockIdx.x * blockDim.x + threadIdx.x, w, kmap, cin8, ntaps, n_tiles, BN, cout, sn, nmap, out);
 }
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, const int* __restrict__ kmap, int K_pad, int cout, int nsplit,
                                     float* __restrict__ dw, const float* __restrict__ colpart, int nblocks, int nch, float* __restrict__ db,
@@ -188,13 +221,18 @@ __global__ void param_multi_kernel(const CisParamJob* __restrict__ jobs, int njo
   const int blk = (int)blockIdx.x - j.i[7];
   const size_t i = (size_t)blk * blockDim.x + threadIdx.x;
   __shared__ float red[256];
+  __shared__ float tile[64 * 129];
   switch (j.kind) {
     case CIS_JOB_PACK:
       pack_weights_body(i, (const float*)j.p[0], (const int*)j.p[1], j.i[0], j.i[1], j.i[2], j.i[3], (const int*)j.p[2], (bf16*)j.p[3]);
       break;
     case CIS_JOB_PACK_TILED:
-      pack_weights_tiled_body(i, (const float*)j.p[0], (const int*)j.p[1], j.i[0], j.i[1], j.i[2], j.i[3], j.i[4], j.i[5], (const int*)j.p[2],
-                              (bf16*)j.p[3]);
+      if (j.i[5] == 1)       // forward orientation: one block per tile, transposed through shared memory
+        pack_weights_tiled_tile(blk, (const float*)j.p[0], (const int*)j.p[1], j.i[0], j.i[1], j.i[2], j.i[3], j.i[4], (const int*)j.p[2],
+                                (bf16*)j.p[3], tile);
+      else
+        pack_weights_tiled_body(i, (const float*)j.p[0], (const int*)j.p[1], j.i[0], j.i[1], j.i[2], j.i[3], j.i[4], j.i[5], (const int*)j.p[2],
+                                (bf16*)j.p[3]);
       break;
     case CIS_JOB_UNPACK:
       unpack_wgrad_body(i, (const float*)j.p[0], (const int*)j.p[1], j.i[0], j.i[1], j.i[2], (float*)j.p[2], (const float*)j.p[3], j.i[3], j.i[4],
@@ -1165,7 +1203,9 @@ int cis_pack_weights(const float* w, const int32_t* kmap, int32_t K_pad, int32_t
 int cis_pack_weights_tiled(const float* w, const int32_t* kmap, int32_t cin8, int32_t ntaps, int32_t n_tiles, int32_t BN, int32_t cout, int32_t sn,
                            const int32_t* nmap, void* out, cis_stream_t stream) {
   const size_t total = (size_t)n_tiles * ((cin8 + 63) / 64) * ntaps * BN * 64;
-  CIS_LAUNCH(pack_weights_tiled_kernel, nblk(total), 256, 0, ST, w, kmap, cin8, ntaps, n_tiles, BN, cout, sn, nmap, (mbf)out);
+  const unsigned blocks = sn == 1 ? (unsigned)(n_tiles * ((cin8 + 63) / 64) * ntaps) : nblk(total);
+  if (BN > 128) return cis_set_error(CIS_ERR_UNSUPPORTED, "cis_pack_weights_tiled: BN > 128");
+  CIS_LAUNCH(pack_weights_tiled_kernel, blocks, 256, 0, ST, w, kmap, cin8, ntaps, n_tiles, BN, cout, sn, nmap, (mbf)out);
   return cis_check_launch("pack_weights_tiled");
 }
 int cis_unpack_wgrad(const float* dwp, const int32_t* kmap, int32_t K_pad, int32_t cout, int32_t nsplit, float* dw, const float* colpart,

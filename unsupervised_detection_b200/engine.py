@@ -129,6 +129,8 @@ class Plan(object):
             elif name == 'cis_pack_weights_tiled':
                 w, kmap, cin8, ntaps, n_tiles, BN, cout, sn, nmap, out = a
                 j.kind, blocks = JOB_PACK_TILED, -(-(n_tiles * (-(-cin8 // 64)) * ntaps * BN * 64) // 256)
+                if sn == 1:               # forward orientation: one block per BN x 64 tile (transposed through shared memory)
+                    blocks = n_tiles * (-(-cin8 // 64)) * ntaps
                 ptrs, ints = [w, kmap, nmap, out], [cin8, ntaps, n_tiles, BN, cout, sn]
             elif name == 'cis_unpack_wgrad':
                 dwp, kmap, K_pad, cout, nsplit, dw, colpart, nblocks, nch, db, layout = a

@@ -283,6 +283,7 @@ MATERIALIZE_MISALIGNED_CONCAT = True
 
 
 WGRAD_CTAS_PER_SM = int(os.environ.get('CIS_WGRAD_CTAS_PER_SM', '2'))   # split-K target: CTAs per SM of one weight-gradient launch
+WGRAD_MAX_SLICE_MB = float(os.environ.get('CIS_WGRAD_MAX_SLICE_MB', '16'))  # 0 = no cap on splits x Cout x K_pad x 4 bytes per layer
 WGRAD_HALO_MIN_CH = int(os.environ.get('CIS_WGRAD_HALO_MIN_CH', '16'))   # thinner inputs: the per-tap 64-channel padding costs more than the gather path
 WGRAD_HALO = os.environ.get('CIS_WGRAD_HALO', '1') == '1'   # halo-resident swapped wgrad kernel (CisWgrad.tma = 2) where it fits
 
@@ -906,6 +907,8 @@ class Builder(object):
             if w.tma == 2:      # grid.x = 64-channel chunks of the input, grid.z = 64-channel halves of Cout
                 ntile = (-(-len(layer.in_chanmap) // 64)) * (2 if layer.cout > 64 else 1)
             splits = max(1, min(nkb // 8 if nkb >= 8 else 1, max(1, (WGRAD_CTAS_PER_SM * NUM_SMS) // ntile)))
+            if WGRAD_MAX_SLICE_MB > 0:      # the private slices are written once and read once more by the un-pack job: bound their volume
+                splits = max(1, min(splits, int(WGRAD_MAX_SLICE_MB * 1e6 / (layer.cout * layer.wg_K_pad * 4.0))))
             splits = -(-nkb // (-(-nkb // splits)))        # every split owns >= 1 reduction block (its slice is written, not accumulated)
             w.splits = splits
             layer.wg_splits[mode] = splits

@@ -1004,10 +1004,19 @@ __global__ void cis_loss_fwd_kernel(const float* __restrict__ flow, const float*
     a[3] += m * e[2];           // den_red       :179
     a[4] += (1.f - m) * e[2];   // den_red_compl :186
   }
+  // block-level reduction first: one fp64 atomic per (block, sum) instead of one per warp -- 23.7 k atomics on 20 addresses serialised
+  // in L2 for ~25 us of this kernel's 31 us, between the forward and the backward pass of every step
+  __shared__ float red[8][5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
     const float s = warp_sum(a[k]);
-    if ((threadIdx.x & 31) == 0) atomicAdd(sums + b * 5 + k, (double)s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += (double)red[w][threadIdx.x];
+    atomicAdd(sums + b * 5 + threadIdx.x, t);
   }
 }
 __global__ void cis_loss_reduce_kernel(const double* __restrict__ sums, int B, int GB, double hw, float eps, float* __restrict__ scalars,

@@ -39,6 +39,10 @@ def _check_conv(d):
         assert util >= (0.2 if d.dil == 1 else 0.5)               # engine.HALO_MIN_UTIL; dilated phases keep the old rule
         for t in range(d.ntaps):
             assert 0 <= d.dh[t] <= d.ey and 0 <= d.dw[t] <= d.ex                                   # taps are halo-relative
+        if d.MT > 1 and d.nsub <= 1 and engine.PLAN_MODEL == 4:
+            # planner rule measured in r02: a taller tile stack only on big grids of short tiles (MMA loop < a CTA's fixed costs)
+            n1 = d.N * d.dil * d.dil * (-(-wp0 // 8)) * (-(-hp0 // 16)) * d.n_tiles
+            assert 2.0 * d.BN * d.ntaps * (-(-chunks // 8)) < 6000.0 and n1 > 4 * 148
     if d.splits > 1:                                  # two-launch split-K (default): private slices, no ticket counters, every split owns work
         assert d.sk_scratch and not d.sk_counters and 2 <= d.splits <= 16
         units = -(-chunks // 8) if d.halo else d.K_pad // 64
@@ -59,6 +63,8 @@ def test_every_conv_descriptor_is_launchable(graph):
             w = a[0]._obj
             assert w.Cout <= 128 and w.K_pad % 64 == 0 and w.splits >= 1 and w.g and w.dwp and w.tma in (0, 1, 2)
             assert lane == 1                                                                       # weight gradients run on the side lane
+            # the private split slices of a layer (written once, read back once by the un-pack job) stay under engine.WGRAD_MAX_SLICE_MB
+            assert w.splits == 1 or w.splits * w.Cout * w.K_pad * 4 <= engine.WGRAD_MAX_SLICE_MB * 1e6
             if w.tma:
                 assert w.sh == 1 and all(w.src[i].chunks % 8 == 0 for i in range(w.nsrc - 1))
 

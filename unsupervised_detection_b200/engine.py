@@ -481,6 +481,7 @@ def setup_halo_s2(d, taps, n_tiles):
 
 
 GROUP_PARITY = os.environ.get('CIS_GROUP_PARITY', '1') == '1'   # the 4 output-parity launches of a stride-2 dgrad / transposed conv as one
+GROUP_PARITY_MAX_TILES = int(os.environ.get('CIS_GROUP_PARITY_MAX_TILES', '1000000'))   # optional cap on the 16x8 tiles per parity (600: +0.4 % device-resident, within noise end to end)
 
 
 def merge_parity_launches(descs):
@@ -497,6 +498,10 @@ def merge_parity_launches(descs):
         if any(bytes(d.src[i]) != bytes(d0.src[i]) for i in range(d0.nsrc)):
             return None
     if sum(d.ntaps for d in descs) > _lib.MAX_TAPS:
+        return None
+    # big grids are better off as separate launches (each becomes a persistent weight-resident launch when it qualifies): measured
+    # layer by layer in r02 -- grouping wins below ~600 tiles per parity (one launch instead of four latency-bound ones), loses above
+    if max(d.N * (-(-d.OH // 16)) * (-(-d.OW // 8)) for d in descs) > GROUP_PARITY_MAX_TILES:
         return None
     g = CisConv.from_buffer_copy(bytes(d0))
     g.MT, g.ey, g.ex = min(d.MT for d in descs), max(d.ey for d in descs), max(d.ex for d in descs)

@@ -107,3 +107,52 @@ def test_experiment_switches_change_only_what_they_claim(monkeypatch):
     assert changed and all(a == 1 and b == 0 for a, b in changed)                  # only halo -> gather moves
     assert all(sum(d.src[i].chunks for i in range(d.nsrc)) * 8 <= 8 and d.ntaps >= 16
                for d, e in zip(_convs(base.fwd), _convs(g2.fwd)) if d.halo != e.halo)
+
+
+def test_param_job_tables_follow_the_device_side_block_mapping(graph):
+    """cis_param_multi's job tables (engine.Plan.batch_param_ops) against the rules the kernel applies (csrc/misc_kernels.cu:
+    param_multi_kernel): first-block prefix sums, one block per 8 output channels for the BN chain rule, one block per BN x 64 tile for the
+    forward-orientation tiled pack, flat 256-element blocks otherwise, and the slice layout flag of every un-pack job."""
+    import ctypes as C
+    from unsupervised_detection_b200._lib import CisParamJob, JOB_PACK, JOB_PACK_TILED, JOB_UNPACK, JOB_BN_FOLD, JOB_BN_CHAIN
+    g = graph
+    plans = [g.pack_gen, g.pack_rec, g.bwd['G'], g.bwd['R']]
+    seen = set()
+    slice_writer = {}          # slice buffer -> kernel path that fills it (CisWgrad.tma), from the weight-gradient launches themselves
+    for m in 'GR':
+        for fn, a, name, fl, lane in g.bwd[m].ops:
+            if name == 'cis_conv_wgrad':
+                slice_writer[a[0]._obj.dwp] = a[0]._obj.tma
+    for plan in plans:
+        for fn, a, name, fl, lane in plan.ops:
+            if name != 'cis_param_multi':
+                continue
+            tab = next(t for t in plan.keep if hasattr(t, 'data_ptr') and t.data_ptr() == a[0])
+            njobs, total = a[1], a[2]
+            raw = bytes(tab.cpu().numpy().tobytes())
+            jobs = [CisParamJob.from_buffer_copy(raw[q * C.sizeof(CisParamJob):(q + 1) * C.sizeof(CisParamJob)]) for q in range(njobs)]
+            assert len({j.kind for j in jobs}) == 1                                   # one kind per launch
+            first = 0
+            for j in jobs:
+                assert j.i[7] == first
+                if j.kind == JOB_BN_CHAIN:
+                    blocks = -(-j.i[0] // 8)
+                elif j.kind == JOB_PACK_TILED:
+                    cin8, ntaps, n_tiles, BN, cout, sn = (j.i[q] for q in range(6))
+                    tiles = n_tiles * (-(-cin8 // 64)) * ntaps
+                    blocks = tiles if sn == 1 else -(-(tiles * BN * 64) // 256)
+                    assert BN <= 128
+                elif j.kind == JOB_UNPACK:
+                    K_pad, cout, nsplit, nblocks, nch, layout = (j.i[q] for q in range(6))
+                    blocks = -(-(cout * K_pad + nch) // 256)
+                    assert layout in (0, 1) and K_pad % 4 == 0 and nsplit >= 1 and 1 <= nblocks <= 592
+                    assert layout == (0 if slice_writer[j.p[0]] == 2 else 1)          # reader and writer agree on the slice layout
+                elif j.kind == JOB_PACK:
+                    blocks = -(-(j.i[1] * j.i[0]) // 256)
+                else:
+                    assert j.kind == JOB_BN_FOLD
+                    blocks = -(-max(j.n, j.i[0]) // 256)
+                first += blocks
+                seen.add(j.kind)
+            assert first == total
+    assert seen == {JOB_PACK, JOB_PACK_TILED, JOB_UNPACK, JOB_BN_FOLD, JOB_BN_CHAIN}
